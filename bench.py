@@ -1,0 +1,496 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the big-linear-algebra B200 hot path.
+
+Workload (BASELINE.json configs[2], the data-parallel one): one mini-batch SGD step of the
+reference's MNIST MLP (model/mnist_nn.c:193-337; 784-256-128-10, ReLU/ReLU/softmax, CE loss) on a
+GLOBAL batch of 60,000 synthetic MNIST-shaped samples, sharded column-wise over the N GPUs of one
+box (one process per GPU, one NCCL all-reduce of the flat gradient buffer per step).  A "step" is
+one pass of that hot loop.  `value` = samples/s with inputs resident in HBM; `e2e` = the same step
+called through the C-ABI with pinned HOST buffers (H2D of the batch and D2H of the loss inside the
+timed region).  `roofline` describes the dominant kernel (the layer-1 GEMM, 40 % of the step's
+flops), timed alone with CUDA events on the library stream.  `extras` carries the other numbers
+BASELINE.json's metric names: the square GEMM sweep (TFLOP/s, FP32 and 3xTF32 paths) and the
+elementwise / norm kernels (GB/s against measured HBM bandwidth).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extras]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+--impl reference times the reference's own single-threaded C (oracle/_ref, built from
+/root/reference by oracle/build_ref.sh; falls back to the pinned restatement in oracle/) on the
+host CPU on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DIMS = (784, 256, 128, 10)
+GLOBAL_BATCH = 60000
+FLOP_PER_SAMPLE = 1007104          # fwd 469,504 + wgrad 469,504 + dgrad 68,096
+LR = 0.02
+METRIC = "mnist_mlp_train_samples_per_s"
+UNIT = "samples/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    sm_max_mhz=d.get("sm_max_mhz", 1965.0), source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, sm_max_mhz=1965.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own C on the host
+# ------------------------------------------------------------------------------------------------
+class CpuReference:
+    """One MLP SGD step in the call order of model/mnist_nn.c:218-315, every matrix operation executed
+    by the REFERENCE's compiled lib/matrix.c + lib/util.c (oracle/_ref/libref_f64.so); only relu' and the
+    loss bookkeeping (model-local loops, O(B) work) are numpy.  Falls back to the pinned restatement
+    (oracle/libbla_oracle_f64.so: orc_mlp_step) when oracle/_ref was not built."""
+
+    def __init__(self):
+        from helpers import load_oracle, load_ref, ref_available
+        self.kind = "reference" if ref_available("f64") else "port"
+        self.ref = load_ref("f64") if self.kind == "reference" else None
+        self.orc = load_oracle(np.float64)
+        rng = np.random.default_rng(42)
+        self.params = [rng.uniform(-r, r, s) for s, r in (((256, 784), 0.0875), ((256, 1), 0.0), ((128, 256), 0.153),
+                                                          ((128, 1), 0.0), ((10, 128), 0.2165), ((10, 1), 0.0))]
+
+    def step(self, X, Y):
+        if self.kind == "port":
+            dims = (C.c_int * 4)(*DIMS)
+            loss = C.c_double(); correct = C.c_int()
+            self.orc.orc_mlp_step(dims, X.shape[1], *[p.ctypes.data_as(C.c_void_p) for p in self.params],
+                                  X.ctypes.data_as(C.c_void_p), Y.ctypes.data_as(C.c_void_p), LR, 1, C.byref(loss),
+                                  C.byref(correct), None, 1)
+            return loss.value
+        from helpers import as_matrix, matrix_to_numpy
+        r = self.ref
+        P = C.POINTER(r.MatrixT)
+        W1, b1, W2, b2, W3, b3 = self.params
+        Bn = X.shape[1]
+
+        def mm(a, b):
+            return r.matrix_multiply(a if isinstance(a, r.MatrixT) else a.contents, b if isinstance(b, r.MatrixT) else b.contents)
+
+        def view(p):
+            m = p.contents
+            return np.ctypeslib.as_array(m.data, shape=(m.rows * m.cols,)).reshape(m.rows, m.cols)
+
+        Xs = X.copy(); xm = as_matrix(r, Xs)
+        r.matrix_scale(C.byref(xm), C.c_double(1 / np.float32(255.0)))
+        acts, raws = [], []
+        prev = xm
+        for W, b, last in ((W1, b1, False), (W2, b2, False), (W3, b3, True)):
+            z = mm(as_matrix(r, W), prev)
+            bm = as_matrix(r, b)
+            r.matrix_add_tile_columns(z, C.byref(bm))
+            a = r.clone_matrix(z.contents)
+            if last:
+                r.softmax(a.contents.data, DIMS[3], Bn)
+            else:
+                r.relu(a.contents.data, a.contents.rows * Bn)
+            raws.append(z); acts.append(a); prev = a
+        A3 = view(acts[2])
+        loss = float(-(Y.ravel() * np.log(A3.ravel() + 1e-15)).sum())
+        g = r.clone_matrix(acts[2].contents)
+        ym = as_matrix(r, Y)
+        r.matrix_scale(C.byref(ym), C.c_double(-1.0)); r.matrix_add(g, C.byref(ym)); r.matrix_scale(C.byref(ym), C.c_double(-1.0))
+        r.matrix_scale(g, C.c_double(1 / 784.0))
+        grads = []
+        below = [xm, acts[0], acts[1]]
+        Ws = [W1, W2, W3]
+        for l in (2, 1, 0):
+            a_prev = below[l]
+            ap = C.byref(a_prev) if isinstance(a_prev, r.MatrixT) else a_prev
+            r.matrix_transpose(ap)
+            dW = mm(g, a_prev)
+            r.matrix_transpose(ap)
+            db = r.matrix_col_sum(g.contents)
+            grads.append((l, dW, db))
+            if l > 0:
+                wm = as_matrix(r, Ws[l])
+                r.matrix_transpose(C.byref(wm))
+                da = mm(wm, g)
+                r.matrix_transpose(C.byref(wm))
+                gz = r.clone_matrix(raws[l - 1].contents)
+                v = view(gz); v[...] = (v > 0)                      # relu_ddx, model-local (mnist_nn.c:47-51)
+                r.matrix_multiply_elementwise(gz, da)
+                r.free_matrix(da); r.free_matrix(g)
+                g = gz
+        r.free_matrix(g)
+        for l, dW, db in grads:
+            for grad, param in ((dW, self.params[2 * l]), (db, self.params[2 * l + 1])):
+                r.frobenius_norm(grad.contents)                     # clip_gradient (no-op threshold, :76-81)
+                r.matrix_scale(grad, C.c_double(np.float32(-LR)))
+                pm = as_matrix(r, param)
+                r.matrix_add(C.byref(pm), grad)
+                r.free_matrix(grad)
+        for m in acts + raws:
+            r.free_matrix(m)
+        _ = (P, matrix_to_numpy)
+        return loss
+
+
+def synth_batch(B, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.integers(0, 256, (DIMS[0], B)).astype(np.float64)
+    labels = rng.integers(0, DIMS[3], B)
+    Y = np.zeros((DIMS[3], B)); Y[labels, np.arange(B)] = 1
+    return X, Y
+
+
+def time_cpu_reference(steps, warmup, budget_s):
+    """Bounded sample: pick a batch so that (warmup + steps) CPU steps fit the budget."""
+    cpu = CpuReference()
+    X, Y = synth_batch(128, 1)
+    t0 = time.perf_counter(); cpu.step(X, Y); probe = (time.perf_counter() - t0) / 128
+    total = max(1, warmup + steps)
+    B = int(budget_s / total / max(probe, 1e-9))
+    B = max(64, min(8192, B // 64 * 64))
+    X, Y = synth_batch(B, 2)
+    for _ in range(warmup):
+        cpu.step(X, Y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu.step(X, Y)
+    dt = time.perf_counter() - t0
+    return dict(value=B * steps / dt, unit=UNIT, cores=1, kind=cpu.kind, ms_per_step=1e3 * dt / steps,
+                sample=f"{steps} SGD steps of {B} synthetic samples (of the 60,000-sample step), reference C single-threaded "
+                       f"(it has no threads), gcc -O2, 1 of {os.cpu_count()} host cores")
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warmup = min(args.warmup, 1)
+    r = time_cpu_reference(steps, warmup, budget_s=90.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {"workload": "model/mnist_nn.c train step: MLP 784-256-128-10, global batch 60000 columns sharded over the GPUs",
+            "global_batch": GLOBAL_BATCH, "per_gpu_batch": GLOBAL_BATCH // world, "parallelism": f"dp{world}",
+            "flop_per_sample": FLOP_PER_SAMPLE, "lr": LR}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.proc:
+            self.proc.terminate()
+        rows = [l.split(", ") for t, l in self.samples if t0 - 0.05 <= t <= t1 + 0.15] or [l.split(", ") for _, l in self.samples[-3:]]
+        sm, mx, reasons = [], 0.0, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--path", default=os.environ.get("BLA_BENCH_PATH", "auto"), choices=["auto", "fp32", "3xtf32"])
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import bla_b200 as b
+    if b.bla_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the big-linear-algebra B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    b.bla_init(local_rank)
+    stream = torch.cuda.Stream()
+    b.bla_set_stream(C.c_void_p(stream.cuda_stream))
+    PATH = {"auto": b.GEMM_AUTO, "fp32": b.GEMM_FP32, "3xtf32": b.GEMM_3XTF32}[args.path]
+    b.bla_set_gemm_path(PATH)
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_ubyte * 128)()
+            b.bla_comm_unique_id(raw)
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+        b.bla_comm_init(raw, rank, world)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Bg = GLOBAL_BATCH
+    Bl = Bg // world
+    c0 = rank * Bl
+    if rank == world - 1:
+        Bl = Bg - c0
+    dims = (C.c_int * 4)(*DIMS)
+    net = b.bla_mlp_create(dims, Bl)
+    b.bla_mlp_init_params(net, 42)
+
+    # resident synthetic batches, rotated so the inputs of consecutive steps never sit in L2 together
+    x_bytes = DIMS[0] * Bl * 4
+    nbuf = max(2, -(-(256 << 20) // x_bytes))
+    Xd, Yd = [], []
+    rng = np.random.default_rng(1234 + rank)
+    for i in range(nbuf):
+        xd = b.bla_malloc_device(x_bytes)
+        b.bla_fill_uniform(xd, DIMS[0] * Bl, 1000 + 17 * i + 131 * rank, 0.0, 255.0)
+        labels = rng.integers(0, DIMS[3], Bl)
+        Y = np.zeros((DIMS[3], Bl), np.float32); Y[labels, np.arange(Bl)] = 1
+        yd = b.bla_malloc_device(Y.nbytes)
+        b.bla_copy_h2d(yd, Y.ctypes.data_as(C.c_void_p), Y.nbytes)
+        b.bla_sync()
+        Xd.append(xd); Yd.append(yd)
+
+    def step_resident(i):
+        b.bla_mlp_train_step(net, Xd[i % nbuf], Yd[i % nbuf], Bl, Bg, c0, LR, None)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = b.bla_launch_count(); h0 = b.bla_h2d_bytes(); d0 = b.bla_d2h_bytes()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        barrier()
+        t1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return dict(ms=ms, launches=b.bla_launch_count() - l0, h2d=b.bla_h2d_bytes() - h0, d2h=b.bla_d2h_bytes() - d0, t0=t0, t1=t1)
+
+    clocks = Clocks(local_rank) if rank == 0 else None
+    time.sleep(0.3)
+    res = timed(step_resident, args.steps, args.warmup)
+    clk = clocks.summary(res["t0"], res["t1"]) if clocks else None
+    ms_per_step = res["ms"] / args.steps
+    value = Bg / (ms_per_step * 1e-3)
+    stats = np.zeros(2)
+    b.bla_mlp_read_stats(net, stats.ctypes.data_as(C.c_void_p))
+
+    # ---- e2e: pinned host float32 batch -> H2D -> step -> D2H of {loss, correct}, every step ----
+    hx = b.bla_malloc_pinned(x_bytes)
+    hy = b.bla_malloc_pinned(DIMS[3] * Bl * 4)
+    hx_np = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_float)), shape=(DIMS[0] * Bl,))
+    hy_np = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(DIMS[3], Bl))
+    hx_np[:] = rng.integers(0, 256, DIMS[0] * Bl).astype(np.float32)
+    labels = rng.integers(0, DIMS[3], Bl)
+    hy_np[:] = 0; hy_np[labels, np.arange(Bl)] = 1
+    e2e_stats = np.zeros(2)
+
+    def step_e2e(i):
+        b.bla_mlp_train_step(net, hx, hy, Bl, Bg, c0, LR, e2e_stats.ctypes.data_as(C.c_void_p))
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e = timed(step_e2e, e2e_steps, 3)
+    e2e_ms = e2e["ms"] / e2e_steps
+    e2e_value = Bg / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: layer-1 forward GEMM (256 x 784 x Bl), alone ----
+    pk = peaks()
+    a1 = b.bla_malloc_device(DIMS[1] * Bl * 4)
+    w1 = b.bla_malloc_device(DIMS[1] * DIMS[0] * 4)
+    b.bla_fill_uniform(w1, DIMS[1] * DIMS[0], 7, -0.08, 0.08)
+
+    def gemm1(i):
+        b.bla_gemm(0, 0, DIMS[1], Bl, DIMS[0], w1, DIMS[0], Xd[i % nbuf], Bl, a1, Bl)
+
+    gr = timed(gemm1, 20, 5)
+    gemm_ms = gr["ms"] / 20
+    gemm_flop = 2.0 * DIMS[1] * DIMS[0] * Bl
+    achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12
+    used_tc = b.bla_get_gemm_path() != b.GEMM_FP32 and tc_available(b)
+    if used_tc:
+        peak = pk["bf16"] / 2.0 / 3.0
+        note = f"3xTF32: three tcgen05 TF32 MMAs per product; peak = {pk['source']} bf16 burst {pk['bf16']} TFLOP/s / 2 (tf32) / 3"
+        bound = "tensor"
+    else:
+        peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        note = "FP32 FMA on the SIMT pipe: peak = 148 SMs x 128 lanes x 2 x clocks.max.sm (not in MEASURED_PEAKS.json)"
+        bound = "fp32-simt"
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "layer-1 forward GEMM 256x784x%d (40%% of step flops)" % Bl, "ms_per_launch": gemm_ms, "peak_note": note}
+
+    extras = None
+    if not args.no_extras and rank == 0 and world == 1:
+        extras = run_extras(b, torch, stream, pk)
+
+    cpu = None
+    if rank == 0 and world == 1:
+        try:
+            r = time_cpu_reference(2, 1, args.cpu_budget)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"], "sample": r["sample"]}
+        except Exception as exc:   # the baseline is a reported number, never a reason to lose the bench line
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(exc)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": dict(workload_config(world), gemm_path=args.path,
+                               l2=f"inputs rotate over {nbuf} resident batches ({nbuf * x_bytes >> 20} MiB > 126 MB L2)"),
+                "tflops": value * FLOP_PER_SAMPLE / 1e12,
+                "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"] // e2e_steps,
+                        "d2h_bytes_per_step": e2e["d2h"] // e2e_steps, "ms_per_step": e2e_ms,
+                        "api": "bla_mlp_train_step(host float32 X[784xB], Y[10xB], &stats)"},
+                "gpu_launches": int(res["launches"]), "clocks": clk,
+                "loss_per_sample_last": float(stats[0] / max(1, Bg * args.steps)) if world == 1 else None,
+                "extras": extras}
+        print(json.dumps(line), flush=True)
+    if dist:
+        b.bla_comm_destroy()
+        dist.destroy_process_group()
+
+
+def tc_available(b):
+    return bool(getattr(b, "bla_tc_available", lambda: 0)())
+
+
+def run_extras(b, torch, stream, pk):
+    """GEMM sweep (TFLOP/s) and elementwise / norm kernels (GB/s): the other numbers BASELINE.json's metric names."""
+    out = {"gemm_sweep": [], "elementwise": []}
+
+    def t(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    saved = b.bla_get_gemm_path()
+    for n in (1024, 2048, 4096, 8192, 16384):
+        A = b.bla_malloc_device(n * n * 4); B = b.bla_malloc_device(n * n * 4); Cc = b.bla_malloc_device(n * n * 4)
+        b.bla_fill_uniform(A, n * n, 1, -0.5, 0.5); b.bla_fill_uniform(B, n * n, 2, -0.5, 0.5)
+        row = {"n": n}
+        for name, path in (("fp32", b.GEMM_FP32), ("3xtf32", b.GEMM_3XTF32)):
+            if path == b.GEMM_3XTF32 and not tc_available(b):
+                continue
+            b.bla_set_gemm_path(path)
+            iters = 20 if n <= 2048 else (5 if n <= 8192 else 2)
+            ms = t(lambda: b.bla_gemm(0, 0, n, n, n, A, n, B, n, Cc, n), iters)
+            tf = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
+            row[name + "_tflops"] = tf
+            row[name + "_frac"] = tf / (fp32_peak if name == "fp32" else pk["bf16"] / 6.0)
+        out["gemm_sweep"].append(row)
+        for p in (A, B, Cc):
+            b.bla_free(p)
+    b.bla_set_gemm_path(saved)
+    out["gemm_peaks"] = {"fp32_simt_tflops": fp32_peak, "3xtf32_tflops": pk["bf16"] / 6.0, "source": pk["source"]}
+
+    n = 1 << 26                                  # 256 MiB per operand, well past the 126 MB L2
+    rows, cols = 8192, 8192
+    X = b.bla_matrix_device(rows, cols); Y = b.bla_matrix_device(rows, cols)
+    b.bla_fill_uniform(C.cast(X.contents.data, C.c_void_p), n, 3, -1, 1); b.bla_fill_uniform(C.cast(Y.contents.data, C.c_void_p), n, 4, -1, 1)
+    bias = b.bla_matrix_device(rows, 1)
+    b.bla_fill_uniform(C.cast(bias.contents.data, C.c_void_p), rows, 5, -1, 1)
+    cases = [("matrix_scale", 8, lambda: b.matrix_scale(X, C.c_float(1.0000001))),
+             ("matrix_add", 12, lambda: b.matrix_add(X, Y)),
+             ("matrix_multiply_elementwise", 12, lambda: b.matrix_multiply_elementwise(X, Y)),
+             ("relu", 8, lambda: b.relu(C.cast(X.contents.data, C.c_void_p), n)),
+             ("matrix_add_tile_columns", 8, lambda: b.matrix_add_tile_columns(X, bias)),
+             ("matrix_col_sum", 4, lambda: b.free_matrix(b.matrix_col_sum(X.contents))),
+             ("matrix_transpose(+copy back)", 16, lambda: b.matrix_transpose(X))]
+    for name, bpe, fn in cases:
+        ms = t(fn, 10)
+        gbs = bpe * n / (ms * 1e-3) / 1e9
+        out["elementwise"].append({"op": name, "bytes_per_elem": bpe, "gbs": gbs, "frac_hbm": gbs / pk["hbm"]})
+    # group norm, U-Net shape batched: 256 images x 128 ch x 32x32, groups of 32 channels (8 / 12 B per element)
+    imgs, Cn, HW = 256, 128, 1024
+    ne = imgs * Cn * HW
+    gx = b.bla_malloc_device(ne * 4); gy = b.bla_malloc_device(ne * 4); gd = b.bla_malloc_device(ne * 4)
+    gv = b.bla_malloc_device(imgs * 4 * 4); gm = b.bla_malloc_device(imgs * 4 * 4)
+    b.bla_fill_uniform(gx, ne, 6, -1, 2); b.bla_fill_uniform(gd, ne, 7, -1, 1)
+    ms = t(lambda: b.bla_group_norm(gx, gy, gv, gm, imgs, Cn, HW, 32), 10)
+    out["elementwise"].append({"op": "group_norm fwd 256x128x32x32", "bytes_per_elem": 8, "gbs": 8 * ne / (ms * 1e-3) / 1e9,
+                               "frac_hbm": 8 * ne / (ms * 1e-3) / 1e9 / pk["hbm"]})
+    ms = t(lambda: b.bla_group_norm_ddx(gd, gy, gx, gm, gv, imgs, Cn, HW, 32), 10)
+    out["elementwise"].append({"op": "group_norm bwd 256x128x32x32", "bytes_per_elem": 12, "gbs": 12 * ne / (ms * 1e-3) / 1e9,
+                               "frac_hbm": 12 * ne / (ms * 1e-3) / 1e9 / pk["hbm"]})
+    out["hbm_peak_gbs"] = pk["hbm"]
+    return out
+
+
+if __name__ == "__main__":
+    main()

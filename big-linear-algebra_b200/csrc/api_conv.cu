@@ -1,0 +1,227 @@
+// api_conv.cu -- lib/conv.h: SAME-padded conv2d forward/backward on channel planes (SURVEY.md
+// K10/K11).  GEMM view: out[F][P] = K[F][C*k*k] . col^T, with P = Ho*Wo output pixels.
+// The reference-API entry points below must also fill the caller's ConvData scratch (model code
+// reads data->im2col / data->kernel_matrix back in conv_ddx, lib/conv.c:221-227), so they
+// materialise im2col once on the device and run the GEMMs with transpose flags instead of the
+// reference's four materialised matrix_transpose calls.  The batched, device-resident entry points
+// (bla_conv2d_*) in conv_implicit.cu never materialise im2col.
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../include/lib/conv.h"
+#include "kernels.h"
+#include "planes.h"
+#include "runtime.h"
+
+using namespace bla;
+
+namespace bla {
+
+struct ConvGeom {
+    int C, H, W, k, stride, Ho, Wo, pad_top, pad_left;
+};
+
+ConvGeom conv_geom(int C, int H, int W, int k, int stride) {
+    // TF-style SAME padding, lib/conv.c:12-24: floor(pad/2) in front
+    ConvGeom g;
+    g.C = C; g.H = H; g.W = W; g.k = k; g.stride = stride;
+    g.Ho = (H + stride - 1) / stride;
+    g.Wo = (W + stride - 1) / stride;
+    int pv = (g.Ho - 1) * stride + k - H; if (pv < 0) pv = 0;
+    int ph = (g.Wo - 1) * stride + k - W; if (ph < 0) ph = 0;
+    g.pad_top = pv / 2;
+    g.pad_left = ph / 2;
+    return g;
+}
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// col[p][c*k*k + ki*k + kj] = x[c][oi*s + ki - pt][oj*s + kj - pl] (0 outside)   lib/conv.c:59-74
+__global__ void __launch_bounds__(kThreads) im2col_kernel(const float* __restrict__ x, float* __restrict__ col, ConvGeom g) {
+    const int ck2 = g.C * g.k * g.k;
+    const size_t total = (size_t)g.Ho * g.Wo * ck2;
+    for (size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (size_t)gridDim.x * kThreads) {
+        const int q = (int)(e % ck2);
+        const int p = (int)(e / ck2);
+        const int kj = q % g.k, ki = (q / g.k) % g.k, c = q / (g.k * g.k);
+        const int oj = p % g.Wo, oi = p / g.Wo;
+        const int ii = oi * g.stride + ki - g.pad_top, jj = oj * g.stride + kj - g.pad_left;
+        float v = 0.f;
+        if (ii >= 0 && ii < g.H && jj >= 0 && jj < g.W) v = x[((size_t)c * g.H + ii) * g.W + jj];
+        col[e] = v;
+    }
+}
+
+// dx[c][i][j] = sum over the (ki,kj,oi,oj) that map onto (i,j) of dcol[...]: the adjoint of
+// im2col in gather form (deterministic; the reference scatter-adds, lib/conv.c:108-123).
+__global__ void __launch_bounds__(kThreads) col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, ConvGeom g) {
+    const int ck2 = g.C * g.k * g.k;
+    const size_t total = (size_t)g.C * g.H * g.W;
+    for (size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (size_t)gridDim.x * kThreads) {
+        const int j = (int)(e % g.W), i = (int)((e / g.W) % g.H), c = (int)(e / ((size_t)g.W * g.H));
+        float acc = 0.f;
+        // same visiting order as the reference's scatter: output pixels ascending, then (ki,kj)
+        for (int oi = 0; oi < g.Ho; ++oi) {
+            const int ki = i + g.pad_top - oi * g.stride;
+            if (ki < 0 || ki >= g.k) continue;
+            for (int oj = 0; oj < g.Wo; ++oj) {
+                const int kj = j + g.pad_left - oj * g.stride;
+                if (kj < 0 || kj >= g.k) continue;
+                acc += dcol[((size_t)oi * g.Wo + oj) * ck2 + c * g.k * g.k + ki * g.k + kj];
+            }
+        }
+        dx[e] = acc;
+    }
+}
+
+inline int grid_for(size_t n) {
+    size_t b = (n + kThreads - 1) / kThreads;
+    size_t cap = (size_t)rt().num_sms * 8;
+    if (b > cap) b = cap;
+    return (int)(b ? b : 1);
+}
+
+}  // namespace
+
+void k_im2col(const float* x, float* col, const ConvGeom& g, cudaStream_t s) {
+    im2col_kernel<<<grid_for((size_t)g.Ho * g.Wo * g.C * g.k * g.k), kThreads, 0, s>>>(x, col, g);
+    BLA_LAUNCH_CHECK();
+    count_launch();
+}
+void k_col2im(const float* dcol, float* dx, const ConvGeom& g, cudaStream_t s) {
+    col2im_kernel<<<grid_for((size_t)g.C * g.H * g.W), kThreads, 0, s>>>(dcol, dx, g);
+    BLA_LAUNCH_CHECK();
+    count_launch();
+}
+
+}  // namespace bla
+
+extern "C" {
+
+// lib/conv.c:8-77
+void _im2col(Matrix* in, Matrix* out, int kernel_size, int in_channels, int stride) {
+    CallScope sc;
+    ConvGeom g = conv_geom(in_channels, in[0].rows, in[0].cols, kernel_size, stride);
+    PlaneSet x(sc, in, in_channels, true);
+    float* col = sc.out(out->data, (size_t)g.Ho * g.Wo * g.C * g.k * g.k);
+    k_im2col(x.dev(), col, g, sc.stream());
+}
+
+// lib/conv.c:80-135 (mathematically correct for every stride; the reference is only for stride 1, D4)
+void _col2im(Matrix* in, Matrix* out, int kernel_size, int out_channels, int stride) {
+    CallScope sc;
+    ConvGeom g = conv_geom(out_channels, out[0].rows, out[0].cols, kernel_size, stride);
+    const float* dcol = sc.in(in->data, (size_t)g.Ho * g.Wo * g.C * g.k * g.k);
+    PlaneSet dx(sc, out, out_channels, false);
+    k_col2im(dcol, dx.dev(), g, sc.stream());
+    dx.write_back();
+}
+
+// lib/conv.c:138-153: (F,C,k,k) -> (C*k*k, F)
+void _reshape_kernels_matrix(Matrix** kernels, Matrix* matrix) {
+    CallScope sc;
+    const int k = kernels[0][0].rows, F = matrix->cols, C = matrix->rows / (k * k);
+    PlaneSet kr(sc, kernels, F, C, true);
+    float* km = sc.out(matrix->data, (size_t)matrix->rows * F);
+    k_transpose(kr.dev(), km, F, C * k * k, sc.stream());
+}
+
+// lib/conv.c:156-171: (C*k*k, F) -> (F,C,k,k)
+void _reshape_matrix_kernels(Matrix* matrix, Matrix** kernels) {
+    CallScope sc;
+    const int k = kernels[0][0].rows, F = matrix->cols, C = matrix->rows / (k * k);
+    const float* km = sc.in(matrix->data, (size_t)matrix->rows * F);
+    PlaneSet kr(sc, kernels, F, C, false);
+    k_transpose(km, kr.dev(), C * k * k, F, sc.stream());
+    kr.write_back();
+}
+
+// lib/conv.c:174-187, intended direction (D3): channels (C,H,W) -> matrix (H*W, C)
+void reshape_channels_matrix(Matrix* channels, Matrix* matrix) {
+    CallScope sc;
+    const int C = matrix->cols, HW = channels[0].rows * channels[0].cols;
+    PlaneSet ch(sc, channels, C, true);
+    float* m = sc.out(matrix->data, (size_t)HW * C);
+    k_transpose(ch.dev(), m, C, HW, sc.stream());
+}
+
+// lib/conv.c:190-203, intended direction (D3): matrix (H*W, C) -> channels (C,H,W)
+void reshape_matrix_channels(Matrix* matrix, Matrix* channels) {
+    CallScope sc;
+    const int C = matrix->cols, HW = channels[0].rows * channels[0].cols;
+    const float* m = sc.in(matrix->data, (size_t)HW * C);
+    PlaneSet ch(sc, channels, C, false);
+    k_transpose(m, ch.dev(), HW, C, sc.stream());
+    ch.write_back();
+}
+
+// lib/conv.c:205-212
+void conv(Matrix* X, Matrix** kernels, ConvData* data, int in_channels, int out_channels, int stride) {
+    (void)out_channels;   // unused by the reference too
+    CallScope sc;
+    const int k = kernels[0][0].cols;
+    const int F = data->kernel_matrix->cols;
+    ConvGeom g = conv_geom(in_channels, X[0].rows, X[0].cols, k, stride);
+    const int P = g.Ho * g.Wo, ck2 = in_channels * k * k;
+    PlaneSet x(sc, X, in_channels, true);
+    PlaneSet kr(sc, kernels, F, in_channels, true);
+    PlaneSet y(sc, data->output, F, false);
+    float* col = sc.out(data->im2col->data, (size_t)P * ck2);
+    float* km = sc.out(data->kernel_matrix->data, (size_t)ck2 * F);
+    float* prod = sc.out(data->product->data, (size_t)P * F);
+    cudaStream_t s = sc.stream();
+    k_im2col(x.dev(), col, g, s);                       // (P, ck2)
+    k_transpose(kr.dev(), km, F, ck2, s);               // (ck2, F)   _reshape_kernels_matrix
+    GemmArgs a{};                                       // y[F][P] = K[F][ck2] . col^T
+    a.m = F; a.n = P; a.k = ck2;
+    a.a = kr.dev(); a.lda = ck2;
+    a.b = col; a.ldb = ck2; a.tb = true;
+    a.c = y.dev(); a.ldc = P;
+    gemm(a, s);
+    k_transpose(y.dev(), prod, F, P, s);                // (P, F) as the reference leaves it in data->product
+    y.write_back();
+}
+
+// lib/conv.c:214-229
+void conv_ddx(Matrix* del_Y, ConvData* data, ConvData* grad_data, Matrix** del_kernels, Matrix* del_input, int in_channels,
+              int stride) {
+    CallScope sc;
+    const int k = del_kernels[0][0].cols;
+    const int F = data->kernel_matrix->cols;
+    ConvGeom g = conv_geom(in_channels, del_input[0].rows, del_input[0].cols, k, stride);
+    const int P = g.Ho * g.Wo, ck2 = in_channels * k * k;
+    if (data->im2col->rows != P || data->im2col->cols != ck2) {
+        printf("conv_ddx: im2col scratch is %dx%d, expected %dx%d, exiting\n", data->im2col->rows, data->im2col->cols, P, ck2);
+        exit(1);
+    }
+    PlaneSet dy(sc, del_Y, F, true);
+    PlaneSet dk(sc, del_kernels, F, in_channels, false);
+    PlaneSet dx(sc, del_input, in_channels, false);
+    const float* col = sc.in(data->im2col->data, (size_t)P * ck2);
+    const float* km = sc.in(data->kernel_matrix->data, (size_t)ck2 * F);
+    float* dq = sc.out(grad_data->product->data, (size_t)P * F);
+    float* dkm = sc.out(grad_data->kernel_matrix->data, (size_t)ck2 * F);
+    float* dcol = sc.out(grad_data->im2col->data, (size_t)P * ck2);
+    cudaStream_t s = sc.stream();
+    k_transpose(dy.dev(), dq, F, P, s);                 // reshape_channels_matrix(del_Y, del_Q)
+    GemmArgs w{};                                       // wgrad: dK[F][ck2] = dy[F][P] . col[P][ck2]
+    w.m = F; w.n = ck2; w.k = P;
+    w.a = dy.dev(); w.lda = P;
+    w.b = col; w.ldb = ck2;
+    w.c = dk.dev(); w.ldc = ck2;
+    gemm(w, s);
+    k_transpose(dk.dev(), dkm, F, ck2, s);              // what the reference leaves in grad_data->kernel_matrix
+    GemmArgs d{};                                       // dgrad: dcol[P][ck2] = dy^T[P][F] . km^T[F][ck2]
+    d.m = P; d.n = ck2; d.k = F;
+    d.a = dy.dev(); d.lda = P; d.ta = true;
+    d.b = km; d.ldb = F; d.tb = true;
+    d.c = dcol; d.ldc = ck2;
+    gemm(d, s);
+    k_col2im(dcol, dx.dev(), g, s);
+    dk.write_back();
+    dx.write_back();
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// api_layer.cu -- lib/layer.h on the device: per-sample dense layers with MSE
+// back-propagation.  These layers are tiny (2-3-2, 3-2-2, 784-200-10): the work is latency-bound,
+// so each step is ONE fused kernel (GEMV + bias + activation; delta + outer product; W^T.g), and
+// the arithmetic inside a kernel keeps the reference's order and rounding (separate IEEE multiply
+// and add, k ascending) so results are bit-identical to the reference's float build.
+//
+// Activations are host function pointers (lib/layer.h:11-12).  A callback is probed once on a
+// fixed host vector; ReLU, ReLU' (0/1 step) and constant-valued derivatives are recognised exactly
+// and fused into the kernels; any other callback is applied on the host to the host-visible
+// (managed) result, exactly as the reference would.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+
+#include "../../include/lib/layer.h"
+#include "../../include/lib/matrix.h"
+#include "kernels.h"
+#include "runtime.h"
+
+using namespace bla;
+
+extern "C" float* bla_read_csv_floats(const char* filepath, int* count);
+
+namespace {
+
+enum ActKind { kActHost = 0, kActIdentity = 1, kActRelu = 2, kActStep = 3, kActConst = 4 };
+struct ActInfo { int kind; float c; };
+
+ActInfo probe(void (*fn)(float*, int)) {
+    static std::unordered_map<void*, ActInfo> cache;
+    auto it = cache.find((void*)fn);
+    if (it != cache.end()) return it->second;
+    const float in[13] = {-1e30f, -100.f, -2.f, -0.5f, -1e-30f, -0.0f, 0.f, 1e-30f, 0.5f, 1.f, 3.f, 100.f, 1e30f};
+    float out[13];
+    memcpy(out, in, sizeof(in));
+    fn(out, 13);
+    bool ident = true, relu = true, step = true, cst = true;
+    for (int i = 0; i < 13; ++i) {
+        float r = in[i] < 0 ? 0.f : in[i];
+        float s = in[i] > 0 ? 1.f : 0.f;
+        ident &= memcmp(&out[i], &in[i], 4) == 0;
+        relu &= memcmp(&out[i], &r, 4) == 0;
+        step &= out[i] == s;
+        cst &= out[i] == out[0];
+    }
+    ActInfo a{kActHost, 0.f};
+    if (ident) a.kind = kActIdentity;
+    else if (relu) a.kind = kActRelu;
+    else if (step) a.kind = kActStep;
+    else if (cst) { a.kind = kActConst; a.c = out[0]; }
+    cache[(void*)fn] = a;
+    return a;
+}
+
+__device__ __forceinline__ float act_apply(int kind, float c, float v) {
+    if (kind == kActRelu) return v < 0.f ? 0.f : v;
+    if (kind == kActStep) return v > 0.f ? 1.f : 0.f;
+    if (kind == kActConst) return c;
+    return v;
+}
+
+// raw[i] = (sum_k W[i][k]*x[k]) + b[i]; nodes[i] = act(raw[i]).   lib/layer.c:10-18
+__global__ void dense_forward_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ x, float* raw,
+                                     float* nodes, int n, int np, int act, float c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int k = 0; k < np; ++k) acc = __fadd_rn(acc, __fmul_rn(W[(size_t)i * np + k], x[k]));
+    acc = __fadd_rn(acc, b[i]);
+    raw[i] = acc;
+    nodes[i] = act_apply(act, c, acc);
+}
+
+// g[i] = ddx(raw[i]) * dcda[i]   (ddx values supplied in `ddx_vals` when the callback ran on the host)
+// db[i] = g[i] * (-lr);  dW[i][j] = db[i] * prev[j]          lib/layer.c:63-70 / :90-97
+__global__ void dense_delta_kernel(const float* __restrict__ raw, const float* __restrict__ ddx_vals, const float* __restrict__ dcda,
+                                   const float* __restrict__ prev, float* db, float* dW, int n, int np, float neg_lr, int ddx, float c) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * np) return;
+    const int i = idx / np, j = idx % np;
+    const float d = ddx_vals ? ddx_vals[i] : act_apply(ddx, c, raw[i]);
+    const float bi = __fmul_rn(__fmul_rn(d, dcda[i]), neg_lr);
+    if (j == 0) db[i] = bi;
+    dW[idx] = __fmul_rn(bi, prev[j]);
+}
+
+// out[j] = sum_i W[i][j] * (ddx(raw[i]) * dcda[i])            lib/layer.c:53-58
+__global__ void dense_input_grad_kernel(const float* __restrict__ W, const float* __restrict__ raw, const float* __restrict__ ddx_vals,
+                                        const float* __restrict__ dcda, float* out, int n, int np, int ddx, float c) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np) return;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const float d = ddx_vals ? ddx_vals[i] : act_apply(ddx, c, raw[i]);
+        acc = __fadd_rn(acc, __fmul_rn(W[(size_t)i * np + j], __fmul_rn(d, dcda[i])));
+    }
+    out[j] = acc;
+}
+
+// dcda[i] = 2 * (nodes[i] - expectations[i])                  lib/layer.c:85-88
+__global__ void mse_grad_kernel(const float* __restrict__ nodes, const float* __restrict__ expect, float* dcda, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dcda[i] = __fmul_rn(2.f, __fsub_rn(nodes[i], expect[i]));
+}
+
+Matrix* new_struct(int rows, int cols, float* data) {
+    Matrix* p = (Matrix*)malloc(sizeof(Matrix));
+    p->rows = rows; p->cols = cols; p->data = data;
+    return p;
+}
+
+void release(Matrix* m) {
+    if (!m) return;
+    if (m->data && !pool_free(m->data)) free(m->data);
+    free(m);
+}
+
+// Host-evaluated derivative of `raw` for callbacks that were not recognised: returns a managed
+// buffer holding ddx(raw) (the reference applies act_ddx in place to a clone of raw, lib/layer.c:61-62).
+float* host_ddx(const Matrix* raw, void (*fn)(float*, int), int n) {
+    float* buf = (float*)pool_alloc(kManaged, (size_t)n * sizeof(float));
+    BLA_CUDA(cudaMemcpyAsync(buf, raw->data, (size_t)n * sizeof(float), cudaMemcpyDefault, rt().stream));
+    BLA_CUDA(cudaStreamSynchronize(rt().stream));
+    fn(buf, n);
+    return buf;
+}
+
+// One layer of the backward sweep.  `dcda` is dC/da of layer l (device-usable, n floats).
+// Computes this layer's steps, recurses towards the input with PRE-update weights, then applies.
+void backward_from(struct Layer* l, const float* dcda, float learn_rate) {
+    if (!l->has_previous_layer) return;
+    const int n = l->num_nodes, np = l->previous_layer->num_nodes;
+    cudaStream_t s = rt().stream;
+    const ActInfo ddx = probe(l->activation_ddx);
+    float* ddx_vals = ddx.kind == kActHost ? host_ddx(l->raw_nodes, l->activation_ddx, n) : nullptr;
+
+    float *db, *dW, *next_dcda = nullptr;
+    {
+        CallScope sc;
+        const float* raw = sc.in(l->raw_nodes->data, n);
+        const float* prev = sc.in(l->previous_layer->nodes->data, np);
+        sc.note_kind(kManaged);
+        db = (float*)pool_alloc(kManaged, (size_t)n * sizeof(float));
+        dW = (float*)pool_alloc(kManaged, (size_t)n * np * sizeof(float));
+        dense_delta_kernel<<<ceil_div(n * np, 128), 128, 0, s>>>(raw, ddx_vals, dcda, prev, db, dW, n, np, -learn_rate, ddx.kind, ddx.c);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+        if (l->previous_layer->has_previous_layer) {
+            const float* W = sc.in(l->weights->data, (size_t)n * np);
+            next_dcda = (float*)pool_alloc(kManaged, (size_t)np * sizeof(float));
+            dense_input_grad_kernel<<<ceil_div(np, 128), 128, 0, s>>>(W, raw, ddx_vals, dcda, next_dcda, n, np, ddx.kind, ddx.c);
+            BLA_LAUNCH_CHECK();
+            count_launch();
+        }
+    }
+    if (next_dcda) {
+        backward_from(l->previous_layer, next_dcda, learn_rate);
+        pool_free(next_dcda);
+    }
+    {   // lib/layer.c:72-73 / :101-102: applied on the way out of the recursion
+        CallScope sc;
+        k_add(sc.inout(l->weights->data, (size_t)n * np), dW, (size_t)n * np, s);
+        k_add(sc.inout(l->biases->data, n), db, n, s);
+    }
+    pool_free(db);
+    pool_free(dW);
+    if (ddx_vals) pool_free(ddx_vals);
+}
+
+}  // namespace
+
+extern "C" {
+
+// lib/layer.c:6-20
+void feed_forward(struct Layer* l) {
+    if (!l->has_previous_layer) return;
+    const int n = l->num_nodes, np = l->previous_layer->num_nodes;
+    if (l->weights->cols != l->previous_layer->nodes->rows) {
+        printf("Attempted to multiply %dx%d matrix by %dx%d matrix, exiting\n", l->weights->rows, l->weights->cols,
+               l->previous_layer->nodes->rows, l->previous_layer->nodes->cols);
+        exit(1);
+    }
+    const ActInfo act = probe(l->activation);
+    float *raw, *nodes;
+    {
+        CallScope sc;
+        const float* W = sc.in(l->weights->data, (size_t)n * np);
+        const float* b = sc.in(l->biases->data, n);
+        const float* x = sc.in(l->previous_layer->nodes->data, np);
+        sc.note_kind(kManaged);   // results must be host-visible: model code reads nodes->data
+        raw = sc.new_result(n);
+        nodes = sc.new_result(n);
+        dense_forward_kernel<<<ceil_div(n, 128), 128, 0, sc.stream()>>>(W, b, x, raw, nodes, n, np, act.kind, act.c);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+    }   // synchronised here
+    if (act.kind == kActHost) l->activation(nodes, n);   // unrecognised callback: host, on managed memory
+    if (l->has_nodes) {
+        // the reference frees only the structs here (lib/layer.c:13-14) and leaks the data; the
+        // data of OUR previous results goes back to the pool
+        release(l->raw_nodes);
+        release(l->nodes);
+    }
+    l->raw_nodes = new_struct(n, 1, raw);
+    l->nodes = new_struct(n, 1, nodes);
+    l->has_nodes = 1;
+}
+
+// lib/layer.c:22-32
+void free_layer_data(struct Layer l) {
+    if (l.has_nodes) {
+        release(l.raw_nodes);
+        release(l.nodes);
+    }
+    if (!l.has_previous_layer) return;
+    release(l.weights);
+    release(l.biases);
+}
+
+// lib/layer.c:34-39
+void load_weights_from_csv(struct Layer* l, const char* filepath) {
+    if (!l->has_previous_layer) return;
+    l->weights = new_struct(l->num_nodes, l->previous_layer->num_nodes, bla_read_csv_floats(filepath, nullptr));
+}
+
+// lib/layer.c:41-46
+void load_biases_from_csv(struct Layer* l, const char* filepath) {
+    if (!l->has_previous_layer) return;
+    l->biases = new_struct(l->num_nodes, 1, bla_read_csv_floats(filepath, nullptr));
+}
+
+// lib/layer.c:48-78.  The reference's signature: `l` is the layer to update, `next_layer` the one
+// above it whose dC/da is given.
+void do_back_propagate_errors(struct Layer* l, struct Layer* next_layer, struct Matrix* cost_ddx_next_layer_activation, float learn_rate) {
+    if (!l->has_previous_layer) return;
+    const int n = next_layer->num_nodes, np = l->num_nodes;
+    const ActInfo ddx = probe(next_layer->activation_ddx);
+    float* ddx_vals = ddx.kind == kActHost ? host_ddx(next_layer->raw_nodes, next_layer->activation_ddx, n) : nullptr;
+    float* dcda = (float*)pool_alloc(kManaged, (size_t)np * sizeof(float));
+    {
+        CallScope sc;
+        const float* W = sc.in(next_layer->weights->data, (size_t)n * np);
+        const float* raw = sc.in(next_layer->raw_nodes->data, n);
+        const float* up = sc.in(cost_ddx_next_layer_activation->data, n);
+        dense_input_grad_kernel<<<ceil_div(np, 128), 128, 0, sc.stream()>>>(W, raw, ddx_vals, up, dcda, n, np, ddx.kind, ddx.c);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+    }
+    backward_from(l, dcda, learn_rate);
+    pool_free(dcda);
+    if (ddx_vals) pool_free(ddx_vals);
+}
+
+// lib/layer.c:80-107
+void back_propagate_errors(struct Layer* l, float* expectations, float learn_rate) {
+    if (!l->has_previous_layer) return;
+    const int n = l->num_nodes;
+    float* dcda = (float*)pool_alloc(kManaged, (size_t)n * sizeof(float));
+    {
+        CallScope sc;
+        const float* nodes = sc.in(l->nodes->data, n);
+        const float* ex = sc.in(expectations, n);
+        mse_grad_kernel<<<ceil_div(n, 128), 128, 0, sc.stream()>>>(nodes, ex, dcda, n);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+    }
+    backward_from(l, dcda, learn_rate);
+    pool_free(dcda);
+}
+
+}  // extern "C"

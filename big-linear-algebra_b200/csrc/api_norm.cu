@@ -1,0 +1,220 @@
+// api_norm.cu -- lib/norm.h: group normalisation forward / backward.
+// HBM-bound: forward 8 B/elem (read x, write y), backward 12 B/elem (read dy, x; write dx).
+// One CTA owns one (image, group): the group's slab (group_size channels x H*W, contiguous in the
+// [C][H*W] layout) is read ONCE from HBM into shared memory with 128-bit loads, the mean and the
+// centred second moment are reduced there (two passes over shared memory, like the reference's two
+// passes over DRAM, lib/norm.c:13-37), and the normalised values are written straight out.  Slabs
+// larger than shared memory fall back to re-reading global memory (L2-resident at these sizes).
+#include <cstdint>
+
+#include "../../include/lib/norm.h"
+#include "kernels.h"
+#include "planes.h"
+#include "runtime.h"
+
+using namespace bla;
+
+namespace bla {
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr size_t kSmemSlabFloats = 48 * 1024;   // 192 KB of the 227 KB a CTA may use
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// every thread receives the block total
+__device__ __forceinline__ float block_total(float v, float* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32) {
+        t = warp_sum(t);
+        if (threadIdx.x == 0) sh[0] = t;
+    }
+    __syncthreads();
+    t = sh[0];
+    return t;
+}
+
+struct GnParams {
+    int C, HW, group_size, G;   // per image
+    int quirk;
+};
+
+// grid = (G, images).  x,y: [images][C][HW]; means/vars: [images][G]
+template <bool IN_SMEM>
+__global__ void __launch_bounds__(kThreads) group_norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* vars, float* means,
+                                                                  GnParams p) {
+    extern __shared__ __align__(16) float slab[];
+    __shared__ float red[kThreads / 32];
+    const int g = blockIdx.x, img = blockIdx.y;
+    const int c0 = g * p.group_size;
+    const int nc = min(p.group_size, p.C - c0);
+    const size_t n = (size_t)nc * p.HW;
+    const size_t off = ((size_t)img * p.C + c0) * p.HW;
+    const float* xs = x + off;
+    float* ys = y + off;
+    const bool vec = ((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(ys)) & 15) == 0 && (n & 3) == 0;
+
+    float s = 0.f;
+    if (vec) {
+        for (size_t i = threadIdx.x; i < n / 4; i += kThreads) {
+            float4 v = reinterpret_cast<const float4*>(xs)[i];
+            if (IN_SMEM) reinterpret_cast<float4*>(slab)[i] = v;
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        for (size_t i = threadIdx.x; i < n; i += kThreads) {
+            float v = xs[i];
+            if (IN_SMEM) slab[i] = v;
+            s += v;
+        }
+    }
+    const float mean = block_total(s, red) / (float)(int)n;    // lib/norm.c:23
+    const float* src = IN_SMEM ? slab : xs;
+    float q = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += kThreads) {
+        float d = src[i] - mean;
+        q += d * d;
+    }
+    const float var = block_total(q, red) / (float)(int)n;     // lib/norm.c:36
+    // D5: the reference divides by the variance (+ an integer epsilon that is 0); quirks off = textbook
+    const float denom = p.quirk ? var : sqrtf(var + 1e-8f);
+    if (threadIdx.x == 0) {
+        means[(size_t)img * p.G + g] = mean;
+        vars[(size_t)img * p.G + g] = p.quirk ? var : denom;
+    }
+    if (vec) {
+        for (size_t i = threadIdx.x; i < n / 4; i += kThreads) {
+            float4 v = IN_SMEM ? reinterpret_cast<const float4*>(slab)[i] : reinterpret_cast<const float4*>(xs)[i];
+            v.x = (v.x - mean) / denom; v.y = (v.y - mean) / denom; v.z = (v.z - mean) / denom; v.w = (v.w - mean) / denom;
+            reinterpret_cast<float4*>(ys)[i] = v;
+        }
+    } else {
+        for (size_t i = threadIdx.x; i < n; i += kThreads) ys[i] = (src[i] - mean) / denom;
+    }
+}
+
+// dx = (dy - mean(dy) - w * mean(w*dy)) / s,  w = (x - mu)/s,  s = stored "stdev"   lib/norm.c:62-90
+template <bool IN_SMEM>
+__global__ void __launch_bounds__(kThreads) group_norm_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, const float* __restrict__ x,
+                                                                  const float* __restrict__ means, const float* __restrict__ stdevs, GnParams p) {
+    extern __shared__ __align__(16) float slab[];   // [0,n): w ; [n,2n): dy   (IN_SMEM only)
+    __shared__ float red[kThreads / 32];
+    const int g = blockIdx.x, img = blockIdx.y;
+    const int c0 = g * p.group_size;
+    const int nc = min(p.group_size, p.C - c0);
+    const size_t n = (size_t)nc * p.HW;
+    const size_t off = ((size_t)img * p.C + c0) * p.HW;
+    const float mu = means[(size_t)img * p.G + g], sd = stdevs[(size_t)img * p.G + g];
+    float gs = 0.f, gw = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += kThreads) {
+        float w = (x[off + i] - mu) / sd;
+        float d = dy[off + i];
+        if (IN_SMEM) { slab[i] = w; slab[n + i] = d; }
+        gs += d;
+        gw += w * d;
+    }
+    const float mean_g = block_total(gs, red) / (float)(int)n;
+    const float mean_gw = block_total(gw, red) / (float)(int)n;
+    for (size_t i = threadIdx.x; i < n; i += kThreads) {
+        float w = IN_SMEM ? slab[i] : (x[off + i] - mu) / sd;
+        float d = IN_SMEM ? slab[n + i] : dy[off + i];
+        dx[off + i] = (d - mean_g - w * mean_gw) / sd;
+    }
+}
+
+}  // namespace
+
+void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int images, int C, int HW, int group_size, int quirk,
+                      cudaStream_t s) {
+    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, quirk};
+    if (images <= 0 || C <= 0 || HW <= 0) return;
+    const size_t slab = (size_t)min(group_size, C) * HW;
+    dim3 grid(p.G, images);
+    if (slab <= kSmemSlabFloats) {
+        static bool attr = false;
+        if (!attr) {
+            BLA_CUDA(cudaFuncSetAttribute(group_norm_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemSlabFloats * 4)));
+            attr = true;
+        }
+        group_norm_fwd_kernel<true><<<grid, kThreads, slab * sizeof(float), s>>>(x, y, vars, means, p);
+    } else {
+        group_norm_fwd_kernel<false><<<grid, kThreads, 0, s>>>(x, y, vars, means, p);
+    }
+    BLA_LAUNCH_CHECK();
+    count_launch();
+}
+
+void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* means, const float* stdevs, int images, int C, int HW,
+                      int group_size, cudaStream_t s) {
+    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, 1};
+    if (images <= 0 || C <= 0 || HW <= 0) return;
+    const size_t slab = (size_t)min(group_size, C) * HW;
+    dim3 grid(p.G, images);
+    if (2 * slab <= kSmemSlabFloats) {
+        static bool attr = false;
+        if (!attr) {
+            BLA_CUDA(cudaFuncSetAttribute(group_norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemSlabFloats * 4)));
+            attr = true;
+        }
+        group_norm_bwd_kernel<true><<<grid, kThreads, 2 * slab * sizeof(float), s>>>(dy, dx, x, means, stdevs, p);
+    } else {
+        group_norm_bwd_kernel<false><<<grid, kThreads, 0, s>>>(dy, dx, x, means, stdevs, p);
+    }
+    BLA_LAUNCH_CHECK();
+    count_launch();
+}
+
+}  // namespace bla
+
+extern "C" {
+
+const int epsilon = 1e-8;   // lib/norm.c:3 -- an int, hence 0 (exported data symbol of the reference object)
+
+// lib/norm.c:5-50
+void group_norm(Matrix* in, Matrix* out, matrix_float_t* stdevs, matrix_float_t* means, int channels, int group_size) {
+    if (channels <= 0) return;
+    CallScope sc;
+    const int HW = in[0].rows * in[0].cols;
+    const int G = (channels + group_size - 1) / group_size;
+    PlaneSet xin(sc, in, channels, true);
+    PlaneSet yout(sc, out, channels, false);
+    float* dsd = sc.out(stdevs, G);
+    float* dmu = sc.out(means, G);
+    k_group_norm_fwd(xin.dev(), yout.dev(), dsd, dmu, 1, channels, HW, group_size, rt().quirks, sc.stream());
+    yout.write_back();
+}
+
+// lib/norm.c:52-93
+void group_norm_ddx(Matrix* source, Matrix* dest, Matrix* data, matrix_float_t* means, matrix_float_t* stdevs, int channels,
+                    int group_size) {
+    if (channels <= 0) return;
+    CallScope sc;
+    const int HW = source[0].rows * source[0].cols;
+    const int G = (channels + group_size - 1) / group_size;
+    PlaneSet dy(sc, source, channels, true);
+    PlaneSet x(sc, data, channels, true);
+    PlaneSet dx(sc, dest, channels, false);
+    const float* dmu = sc.in(means, G);
+    const float* dsd = sc.in(stdevs, G);
+    k_group_norm_bwd(dy.dev(), dx.dev(), x.dev(), dmu, dsd, 1, channels, HW, group_size, sc.stream());
+    dx.write_back();
+}
+
+// additive, batched, device-resident: x,y [images][C][HW]; vars/means [images][G]  (include/bla.h)
+void bla_group_norm(const float* x, float* y, float* vars, float* means, int images, int channels, int hw, int group_size) {
+    k_group_norm_fwd(x, y, vars, means, images, channels, hw, group_size, rt().quirks, rt().stream);
+}
+void bla_group_norm_ddx(const float* dy, float* dx, const float* x, const float* means, const float* vars, int images, int channels,
+                        int hw, int group_size) {
+    k_group_norm_bwd(dy, dx, x, means, vars, images, channels, hw, group_size, rt().stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// kernels.h -- launchers of the sm_100a kernels.  Every pointer is device-usable (device or
+// managed memory); all launches go to the given stream and return immediately.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+#include "../../include/bla.h"
+
+namespace bla {
+
+// ---- elementwise (ew.cu): 128-bit vectorised grid-stride kernels ---------------------------
+void k_scale(float* m, size_t n, float f, cudaStream_t s);                       // lib/matrix.c:59
+void k_add(float* a, const float* b, size_t n, cudaStream_t s);                  // lib/matrix.c:65
+void k_hadamard(float* a, const float* b, size_t n, cudaStream_t s);             // lib/matrix.c:95
+void k_copy(float* dst, const float* src, size_t n, cudaStream_t s);             // lib/matrix.c:14
+void k_axpy(float* y, const float* x, float alpha, size_t n, cudaStream_t s);    // y += alpha*x (scale+add, mnist_nn.c:303-315)
+void k_relu(float* d, size_t n, cudaStream_t s);                                 // lib/util.c:7
+void k_relu_ddx(float* d, size_t n, cudaStream_t s);                             // mnist_nn.c:47
+void k_relu_backward(const float* src, const float* relu_result, float* dst, size_t n, cudaStream_t s);  // cifar_unet.c:241
+void k_add_tile_columns(float* a, int rows, int cols, const float* b, int bcols, cudaStream_t s);        // lib/matrix.c:189
+void k_add_tile_rows(float* a, int rows, int cols, const float* b, cudaStream_t s);                      // lib/matrix.c:199
+void k_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t s);                      // lib/matrix.c:105
+void k_fill_uniform(float* dst, size_t n, unsigned long long seed, float lo, float hi, cudaStream_t s);
+void k_u8_to_float(float* dst, const unsigned char* src, size_t n, float scale, cudaStream_t s);
+
+// ---- reductions (reduce.cu): warp-shuffle trees, two deterministic stages ---------------------
+// `work` must hold reduce_workspace_bytes() bytes of device scratch.
+size_t reduce_workspace_bytes();
+void k_row_sum(const float* m, int rows, int cols, float* out, cudaStream_t s);                          // lib/matrix.c:123
+void k_col_sum(const float* m, int rows, int cols, float* out, int quirk, void* work, cudaStream_t s);   // lib/matrix.c:138
+void k_sum_squares(const float* m, size_t n, double* out1, void* work, cudaStream_t s);                  // lib/matrix.c:150
+void k_max(const float* m, size_t n, float* out1, void* work, cudaStream_t s);                           // lib/matrix.c:160
+void k_zscore(float* m, size_t n, void* work, cudaStream_t s);                                           // lib/matrix.c:170
+void k_softmax_cols(float* d, int rows, int cols, cudaStream_t s);                                       // lib/util.c:15
+void k_softmax_rows(float* d, int rows, int cols, cudaStream_t s);                                       // lib/util.c:36
+void k_softmax_xent(const float* logits, const float* expected, int classes, int batch, float* probs, float* grad,
+                    float grad_scale, double* stats, cudaStream_t s);                                    // mnist_nn.c:234-268
+
+// ---- GEMM (gemm_simt.cu / gemm_tc.cu) ---------------------------------------------------------
+struct GemmArgs {
+    bool ta, tb;          // A stored [k x m] / B stored [n x k]
+    int m, n, k;
+    const float* a; int lda;
+    const float* b; int ldb;
+    float* c; int ldc;
+    bla_epilogue epi;     // zero-initialised = plain store
+};
+// Dispatch on rt().gemm_path and the shape.
+void gemm(const GemmArgs& g, cudaStream_t s);
+void gemm_simt(const GemmArgs& g, cudaStream_t s);
+// returns false when the shape/alignment is not eligible for the tensor path
+bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s);
+
+}  // namespace bla

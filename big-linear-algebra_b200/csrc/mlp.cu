@@ -1,0 +1,293 @@
+// mlp.cu -- the data-parallel hot loop of the reference, model/mnist_nn.c:193-337, as one
+// device-resident step (include/bla.h "MNIST MLP trainer").
+//
+// What the reference does per mini-batch with 8 matrix_multiply, 10 materialised
+// matrix_transpose, 6 clone_matrix, ~25 elementwise passes and 17 malloc/free pairs becomes:
+//   3 forward GEMMs   (bias + ReLU fused in the epilogue; the 1/255 input scaling is the GEMM alpha)
+//   1 softmax / cross-entropy / argmax / (p - y)/784 kernel
+//   3 wgrad GEMMs     (NT form, split along the batch axis; no transposes)
+//   2 dgrad GEMMs     (TN form, relu' gate fused in the epilogue)
+//   3 bias-gradient window sums (the reference's matrix_col_sum, stride quirk D2 included)
+//   1 all-reduce of the flat gradient buffer (data-parallel only) and 1 fused SGD update.
+// Activations are features x batch (batch = columns), exactly the reference's layout, so a
+// data-parallel shard is a column range and gradients are plain sums over ranks.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.h"
+#include "runtime.h"
+
+namespace bla {
+bool comm_active();
+void comm_group_start();
+void comm_group_end();
+}  // namespace bla
+
+using namespace bla;
+
+struct bla_mlp {
+    int n[4];
+    int max_batch;
+    size_t off_w[3], off_b[3], nparams;   // offsets into the flat parameter / gradient buffers
+    float* params;                        // W1|b1|W2|b2|W3|b3
+    float* grads;                         // same layout
+    float *x, *y;                         // staging for host-side batches  [n0 x B], [n3 x B]
+    unsigned char* x_u8;
+    float *a1, *a2, *z3, *dz2, *dz1;      // [n1 x B] [n2 x B] [n3 x B] [n2 x B] [n1 x B]
+    double* stats;                        // {loss_sum, num_correct} on the device
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Bias gradient = the reference's matrix_col_sum(dZ) (lib/matrix.c:138-148) on the GLOBAL
+// [rows x Bg] matrix of which this process holds columns [c0, c0 + Bl).
+//   quirk: out[i] = sum of the Bg flat elements starting at i*rows  (two row segments)
+//   else : out[i] = sum of row i
+// One CTA per output element; elements of other shards contribute through the all-reduce.
+__global__ void __launch_bounds__(kThreads) bias_grad_kernel(const float* __restrict__ dz, int rows, int Bl, long long Bg, int c0,
+                                                             int quirk, float* out) {
+    __shared__ float sh[kThreads / 32];
+    const int i = blockIdx.x;
+    float acc = 0.f;
+    if (quirk) {
+        const long long start = (long long)i * rows;
+        const long long r0 = start / Bg, s = start % Bg;
+        // segment 1: row r0, global columns [s, Bg)      segment 2: row r0 + 1, global columns [0, s)
+        if (r0 < rows) {
+            long long lo = s > c0 ? s : c0;
+            for (long long c = lo + threadIdx.x; c < (long long)c0 + Bl; c += kThreads) acc += dz[r0 * Bl + (c - c0)];
+        }
+        if (r0 + 1 < rows) {
+            long long hi = s < (long long)c0 + Bl ? s : (long long)c0 + Bl;
+            for (long long c = c0 + threadIdx.x; c < hi; c += kThreads) acc += dz[(r0 + 1) * Bl + (c - c0)];
+        }
+    } else {
+        for (int c = threadIdx.x; c < Bl; c += kThreads) acc += dz[(size_t)i * Bl + c];
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) out[i] = t;
+    }
+}
+
+// He-uniform init of model/mnist_nn.c:97-121: range * u - range/2 with range = 2*sqrtf(6/fan_in)
+__global__ void he_uniform_kernel(float* w, size_t n, float range, unsigned long long seed) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+        w[i] = range * u - range / 2;
+    }
+}
+
+float* W(bla_mlp* m, int l) { return m->params + m->off_w[l]; }
+float* Bv(bla_mlp* m, int l) { return m->params + m->off_b[l]; }
+float* dW(bla_mlp* m, int l) { return m->grads + m->off_w[l]; }
+float* dB(bla_mlp* m, int l) { return m->grads + m->off_b[l]; }
+
+const float* resident(const float* p, float* staging, size_t n, cudaStream_t s) {
+    MemKind k = classify(p);
+    if (k == kDevice || k == kManaged) return p;
+    BLA_CUDA(cudaMemcpyAsync(staging, p, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rt().h2d_bytes += n * sizeof(float);
+    return staging;
+}
+
+void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s) {
+    // Z1 = W1.(X/255) + b1 ; A1 = relu(Z1)          model/mnist_nn.c:218-224
+    GemmArgs g{};
+    g.m = m->n[1]; g.n = B; g.k = m->n[0];
+    g.a = W(m, 0); g.lda = m->n[0]; g.b = x; g.ldb = B; g.c = m->a1; g.ldc = B;
+    g.epi.alpha = x_scale; g.epi.bias_rows = Bv(m, 0); g.epi.activation = BLA_ACT_RELU;
+    gemm(g, s);
+    // A2 = relu(W2.A1 + b2)                           :226-229
+    g = GemmArgs{};
+    g.m = m->n[2]; g.n = B; g.k = m->n[1];
+    g.a = W(m, 1); g.lda = m->n[1]; g.b = m->a1; g.ldb = B; g.c = m->a2; g.ldc = B;
+    g.epi.bias_rows = Bv(m, 1); g.epi.activation = BLA_ACT_RELU;
+    gemm(g, s);
+    // Z3 = W3.A2 + b3                                 :231-232
+    g = GemmArgs{};
+    g.m = m->n[3]; g.n = B; g.k = m->n[2];
+    g.a = W(m, 2); g.lda = m->n[2]; g.b = m->a2; g.ldb = B; g.c = m->z3; g.ldc = B;
+    g.epi.bias_rows = Bv(m, 2);
+    gemm(g, s);
+}
+
+void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, float lr_mult, double* stats_host) {
+    if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
+    cudaStream_t s = rt().stream;
+    const int quirk = rt().quirks;
+    forward(m, x, x_scale, B, s);
+    // A3 = softmax(Z3); loss / accuracy; dZ3 = (A3 - Y) / 784 (in place over Z3)      :234-268
+    k_softmax_xent(m->z3, y, m->n[3], B, nullptr, m->z3, (float)(1.0 / (double)m->n[0]), m->stats, s);
+    const float* dz3 = m->z3;
+
+    auto wgrad = [&](int l, const float* dz, const float* act_prev, float alpha) {   // dW_l = dZ_l . A_{l-1}^T
+        GemmArgs g{};
+        g.m = m->n[l + 1]; g.n = m->n[l]; g.k = B;
+        g.a = dz; g.lda = B; g.b = act_prev; g.ldb = B; g.tb = true;
+        g.c = dW(m, l); g.ldc = m->n[l];
+        g.epi.alpha = alpha;
+        gemm(g, s);
+        bias_grad_kernel<<<m->n[l + 1], kThreads, 0, s>>>(dz, m->n[l + 1], B, Bg, c0, quirk, dB(m, l));   // :271,:282,:293
+        BLA_LAUNCH_CHECK();
+        count_launch();
+    };
+    auto dgrad = [&](int l, const float* dz, const float* gate, float* out) {         // dZ_{l-1} = relu'(Z) (.) (W_l^T . dZ_l)
+        GemmArgs g{};
+        g.m = m->n[l]; g.n = B; g.k = m->n[l + 1];
+        g.a = W(m, l); g.lda = m->n[l]; g.ta = true;
+        g.b = dz; g.ldb = B; g.c = out; g.ldc = B;
+        g.epi.gate = gate;   // A > 0  <=>  Z > 0
+        gemm(g, s);
+    };
+    wgrad(2, dz3, m->a2, 0.f);            // :266-271
+    dgrad(2, dz3, m->a2, m->dz2);         // :273-278
+    wgrad(1, m->dz2, m->a1, 0.f);         // :279-282
+    dgrad(1, m->dz2, m->a1, m->dz1);      // :284-289
+    wgrad(0, m->dz1, x, x_scale);         // :290-293 (X/255 again folded into alpha)
+
+    if (comm_active()) {                  // sum over the data-parallel shards: ONE flat buffer
+        comm_group_start();
+        bla_allreduce_sum_f32(m->grads, m->nparams);
+        bla_allreduce_sum_f64(m->stats, 2);
+        comm_group_end();
+    }
+    // clip_gradient is a no-op (threshold INFINITY, :13,:296-301); scale by -lr and add  :303-315
+    k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, s);
+    if (stats_host) bla_mlp_read_stats(m, stats_host);
+}
+
+}  // namespace
+
+extern "C" {
+
+bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
+    rt();
+    bla_mlp* m = (bla_mlp*)calloc(1, sizeof(bla_mlp));
+    memcpy(m->n, dims, sizeof(m->n));
+    m->max_batch = max_batch;
+    size_t off = 0;
+    for (int l = 0; l < 3; ++l) {
+        m->off_w[l] = off; off += (size_t)dims[l + 1] * dims[l];
+        off = (off + 3) / 4 * 4;
+        m->off_b[l] = off; off += (size_t)dims[l + 1];
+        off = (off + 3) / 4 * 4;
+    }
+    m->nparams = off;
+    const size_t B = (size_t)max_batch;
+    m->params = (float*)pool_alloc(kDevice, off * sizeof(float));
+    m->grads = (float*)pool_alloc(kDevice, off * sizeof(float));
+    BLA_CUDA(cudaMemsetAsync(m->params, 0, off * sizeof(float), rt().stream));
+    BLA_CUDA(cudaMemsetAsync(m->grads, 0, off * sizeof(float), rt().stream));
+    m->x = (float*)pool_alloc(kDevice, dims[0] * B * sizeof(float));
+    m->x_u8 = (unsigned char*)pool_alloc(kDevice, dims[0] * B);
+    m->y = (float*)pool_alloc(kDevice, dims[3] * B * sizeof(float));
+    m->a1 = (float*)pool_alloc(kDevice, dims[1] * B * sizeof(float));
+    m->a2 = (float*)pool_alloc(kDevice, dims[2] * B * sizeof(float));
+    m->z3 = (float*)pool_alloc(kDevice, dims[3] * B * sizeof(float));
+    m->dz2 = (float*)pool_alloc(kDevice, dims[2] * B * sizeof(float));
+    m->dz1 = (float*)pool_alloc(kDevice, dims[1] * B * sizeof(float));
+    m->stats = (double*)pool_alloc(kDevice, 2 * sizeof(double));
+    BLA_CUDA(cudaMemsetAsync(m->stats, 0, 2 * sizeof(double), rt().stream));
+    return m;
+}
+
+void bla_mlp_destroy(bla_mlp* m) {
+    if (!m) return;
+    BLA_CUDA(cudaStreamSynchronize(rt().stream));
+    void* bufs[] = {m->params, m->grads, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats};
+    for (void* b : bufs) pool_free(b);
+    free(m);
+}
+
+void bla_mlp_set_params(bla_mlp* m, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3) {
+    const float* w[3] = {w1, w2, w3};
+    const float* b[3] = {b1, b2, b3};
+    for (int l = 0; l < 3; ++l) {
+        BLA_CUDA(cudaMemcpyAsync(W(m, l), w[l], (size_t)m->n[l + 1] * m->n[l] * sizeof(float), cudaMemcpyDefault, rt().stream));
+        BLA_CUDA(cudaMemcpyAsync(Bv(m, l), b[l], (size_t)m->n[l + 1] * sizeof(float), cudaMemcpyDefault, rt().stream));
+    }
+    BLA_CUDA(cudaStreamSynchronize(rt().stream));
+}
+
+void bla_mlp_get_params(bla_mlp* m, float* w1, float* b1, float* w2, float* b2, float* w3, float* b3) {
+    float* w[3] = {w1, w2, w3};
+    float* b[3] = {b1, b2, b3};
+    for (int l = 0; l < 3; ++l) {
+        if (w[l]) BLA_CUDA(cudaMemcpyAsync(w[l], W(m, l), (size_t)m->n[l + 1] * m->n[l] * sizeof(float), cudaMemcpyDefault, rt().stream));
+        if (b[l]) BLA_CUDA(cudaMemcpyAsync(b[l], Bv(m, l), (size_t)m->n[l + 1] * sizeof(float), cudaMemcpyDefault, rt().stream));
+    }
+    BLA_CUDA(cudaStreamSynchronize(rt().stream));
+}
+
+void bla_mlp_init_params(bla_mlp* m, unsigned long long seed) {
+    BLA_CUDA(cudaMemsetAsync(m->params, 0, m->nparams * sizeof(float), rt().stream));
+    for (int l = 0; l < 3; ++l) {
+        const size_t n = (size_t)m->n[l + 1] * m->n[l];
+        const float range = 2 * sqrtf(6.0f / (float)m->n[l]);
+        he_uniform_kernel<<<rt().num_sms, 256, 0, rt().stream>>>(W(m, l), n, range, seed + 1000003ull * (l + 1));
+        BLA_LAUNCH_CHECK();
+        count_launch();
+    }
+}
+
+void bla_mlp_read_stats(bla_mlp* m, double* stats_host) {
+    BLA_CUDA(cudaMemcpyAsync(stats_host, m->stats, 2 * sizeof(double), cudaMemcpyDeviceToHost, rt().stream));
+    rt().d2h_bytes += 2 * sizeof(double);
+    BLA_CUDA(cudaMemsetAsync(m->stats, 0, 2 * sizeof(double), rt().stream));
+    BLA_CUDA(cudaStreamSynchronize(rt().stream));
+}
+
+void bla_mlp_train_step(bla_mlp* m, const float* x, const float* y, int batch, int global_batch, int col_offset, float lr_mult,
+                        double* stats_host) {
+    cudaStream_t s = rt().stream;
+    const float* dx = resident(x, m->x, (size_t)m->n[0] * batch, s);
+    const float* dy = resident(y, m->y, (size_t)m->n[3] * batch, s);
+    step(m, dx, 1 / 255.0F, dy, batch, global_batch, col_offset, lr_mult, stats_host);
+}
+
+void bla_mlp_train_step_u8(bla_mlp* m, const unsigned char* x_u8, const float* y, int batch, int global_batch, int col_offset,
+                           float lr_mult, double* stats_host) {
+    cudaStream_t s = rt().stream;
+    const size_t n = (size_t)m->n[0] * batch;
+    const unsigned char* src = x_u8;
+    MemKind k = classify(x_u8);
+    if (k != kDevice && k != kManaged) {
+        BLA_CUDA(cudaMemcpyAsync(m->x_u8, x_u8, n, cudaMemcpyHostToDevice, s));
+        rt().h2d_bytes += n;
+        src = m->x_u8;
+    }
+    k_u8_to_float(m->x, src, n, 1.0f, s);   // exact: bytes -> the float pixel values the CSV loader would give
+    const float* dy = resident(y, m->y, (size_t)m->n[3] * batch, s);
+    step(m, m->x, 1 / 255.0F, dy, batch, global_batch, col_offset, lr_mult, stats_host);
+}
+
+void bla_mlp_forward(bla_mlp* m, const float* x, int batch, float* probs) {
+    if (batch > m->max_batch) die("bla: bla_mlp_forward batch %d exceeds max_batch %d, exiting", batch, m->max_batch);
+    CallScope sc;
+    cudaStream_t s = sc.stream();
+    const float* dx = resident(x, m->x, (size_t)m->n[0] * batch, s);
+    forward(m, dx, 1 / 255.0F, batch, s);
+    float* out = sc.out(probs, (size_t)m->n[3] * batch);
+    k_copy(out, m->z3, (size_t)m->n[3] * batch, s);
+    k_softmax_cols(out, m->n[3], batch, s);   // :463
+}
+
+}  // extern "C"

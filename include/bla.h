@@ -1,0 +1,169 @@
+/*
+ * bla.h -- additive C-ABI of libbla.so (big-linear-algebra on B200).
+ *
+ * The drop-in boundary is the reference's own link line: include/lib/{matrix,layer,conv,norm,util}.h
+ * declare exactly the symbols that the reference's lib/*.o export and model/*.c import
+ * (SURVEY.md section 8b).  This header adds what a *device-resident* caller needs on top of that,
+ * with plain pointers and sizes only (no C++ or torch types):
+ *   - device / pinned allocation and explicit transfers, so that a `struct Matrix` can live in HBM
+ *     and go through the unchanged matrix.h API without any staging (asynchronously);
+ *   - device versions of the loops that the reference keeps *inside its model programs*
+ *     (relu', softmax + cross-entropy + argmax, ...: model/mnist_nn.c:38-91,237-257);
+ *   - a fused MNIST-MLP trainer, the data-parallel workload of the benchmark
+ *     (model/mnist_nn.c:164-394), with its NCCL gradient all-reduce;
+ *   - GEMM with transposed operands and fused epilogues (what the reference spells as
+ *     matrix_transpose + matrix_multiply + matrix_add_tile_* + activation).
+ *
+ * Error convention = the reference's (lib/matrix.c:36-39): one line on stdout, then exit(1).
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef BLA_H
+#define BLA_H
+
+#include <stddef.h>
+#include "lib/matrix.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+
+/* Number of usable CUDA devices; 0 when there is none.  Never exits, never initialises a context. */
+int bla_device_count(void);
+/* Bind the library to a device (default: $LOCAL_RANK if set, else 0).  Must precede other calls. */
+void bla_init(int device);
+/* Block until everything queued on the library stream has finished. */
+void bla_sync(void);
+/* The library's cudaStream_t, as an opaque pointer (for CUDA events / graph capture by a host). */
+void* bla_stream(void);
+/* Adopt a caller's cudaStream_t as the library stream (NULL restores the private stream). */
+void bla_set_stream(void* cuda_stream);
+const char* bla_version(void);
+
+/* GEMM arithmetic path for every GEMM-shaped call (matrix_multiply*, conv, dense, MLP). */
+enum { BLA_GEMM_FP32 = 0,   /* FP32 FMA on the SIMT pipe: <= 1e-5 relative vs the reference */
+       BLA_GEMM_3XTF32 = 1, /* three TF32 tcgen05.mma per product, FP32 accumulate in TMEM: <= 1e-3 */
+       BLA_GEMM_AUTO = 2 }; /* 3xTF32 for tensor-core sized problems, FP32 otherwise (default; $BLA_PATH) */
+void bla_set_gemm_path(int path);
+int bla_get_gemm_path(void);
+/* 1 (default, $BLA_QUIRKS): reproduce reference defects D2 (matrix_col_sum stride) and D5 (group norm
+ * divides by the variance); 0: the mathematically intended results. */
+void bla_set_quirks(int on);
+int bla_get_quirks(void);
+/* Counters since load: kernels launched by this library, bytes staged host->device and back. */
+unsigned long long bla_launch_count(void);
+unsigned long long bla_h2d_bytes(void);
+unsigned long long bla_d2h_bytes(void);
+
+/* ---- memory ------------------------------------------------------------------------------- */
+
+void* bla_malloc_device(size_t bytes);
+void* bla_malloc_pinned(size_t bytes); /* page-locked host memory for fast transfers */
+void* bla_malloc_managed(size_t bytes); /* what the matrix.h API returns to host callers */
+void bla_free(void* p);                /* any of the three above */
+/* 0 = ordinary host, 1 = managed, 2 = device, 3 = pinned host */
+int bla_memory_kind(const void* p);
+/* A rows x cols matrix whose data lives in HBM (contents undefined).  Release with free_matrix(). */
+struct Matrix* bla_matrix_device(int rows, int cols);
+/* Asynchronous copies on the library stream; pair with bla_sync() before touching host memory. */
+void bla_copy_h2d(void* dst_device, const void* src_host, size_t bytes);
+void bla_copy_d2h(void* dst_host, const void* src_device, size_t bytes);
+void bla_copy_d2d(void* dst_device, const void* src_device, size_t bytes);
+void bla_memset_zero(void* dst_device, size_t bytes);
+/* Deterministic counter-based U[lo,hi) fill (same sequence on any grid; bla_host_uniform is the
+ * host twin used by tests and by the CPU baseline). */
+void bla_fill_uniform(float* dst_device, size_t n, unsigned long long seed, float lo, float hi);
+void bla_host_uniform(float* dst_host, size_t n, unsigned long long seed, float lo, float hi);
+/* bytes -> float pixels k (0..255) for MNIST-shaped inputs: dst[i] = (float)src[i] * scale */
+void bla_u8_to_float(float* dst_device, const unsigned char* src_device, size_t n, float scale);
+
+/* ---- GEMM --------------------------------------------------------------------------------- */
+
+enum { BLA_ACT_IDENTITY = 0, BLA_ACT_RELU = 1, BLA_ACT_SCALE = 2 };
+
+/* Fused epilogue of bla_gemm_ex.  All pointers may be NULL. */
+typedef struct bla_epilogue {
+	const float* bias_rows; /* + bias_rows[i]  (matrix_add_tile_columns with a column vector, lib/matrix.c:189) */
+	const float* bias_cols; /* + bias_cols[j]  (matrix_add_tile_rows, lib/matrix.c:199) */
+	float* pre_activation;  /* optional copy of the value before the activation (ldc layout) */
+	const float* gate;      /* result *= (gate[i][j] > 0)   (relu' (.) g, model/mnist_nn.c:276-278) */
+	int activation;         /* BLA_ACT_IDENTITY or BLA_ACT_RELU */
+	float alpha;            /* result = alpha * (a.b) before bias (0 is treated as 1) */
+} bla_epilogue;
+
+/* C[m x n] = op(A)[m x k] . op(B)[k x n], row-major with leading dimensions.
+ * trans_a: A is stored [k x m];  trans_b: B is stored [n x k].  Replaces the reference's
+ * matrix_transpose/matrix_multiply/matrix_transpose triples (model/mnist_nn.c:266-292). */
+void bla_gemm(int trans_a, int trans_b, int m, int n, int k, const float* a, int lda, const float* b, int ldb,
+              float* c, int ldc);
+void bla_gemm_ex(int trans_a, int trans_b, int m, int n, int k, const float* a, int lda, const float* b, int ldb,
+                 float* c, int ldc, const bla_epilogue* epi);
+
+/* ---- device twins of the model-local loops ------------------------------------------------ */
+
+/* model/mnist_nn.c:47-51   d[i] = d[i] > 0 */
+void bla_relu_ddx(matrix_float_t* data, int num);
+/* model/cifar_unet.c:241-253   dest = relu_result > 0 ? source : 0 */
+void bla_relu_backward(const matrix_float_t* source, const matrix_float_t* relu_result, matrix_float_t* dest, size_t n);
+/* model/mnist_nn.c:234-268: column softmax of logits[classes x batch], then per column the argmax
+ * hit count against one-hot `expected`, the reference's flat-slice cross-entropy (:249-252) summed
+ * into loss_sum (double), and grad = (probs - expected) * grad_scale.  probs/grad may alias
+ * logits or be NULL.  stats_device = {double loss_sum; double num_correct}, accumulated. */
+void bla_softmax_xent(const float* logits, const float* expected, int classes, int batch, float* probs, float* grad,
+                      float grad_scale, double* stats_device);
+
+/* ---- batched device-resident group norm (lib/norm.c on [images][C][H*W] tensors) ------------ */
+
+void bla_group_norm(const float* x, float* y, float* vars, float* means, int images, int channels, int hw, int group_size);
+void bla_group_norm_ddx(const float* dy, float* dx, const float* x, const float* means, const float* vars, int images,
+                        int channels, int hw, int group_size);
+
+/* ---- MNIST MLP trainer: model/mnist_nn.c:164-394 as one device-resident step ---------------- */
+
+typedef struct bla_mlp bla_mlp;
+/* dims = {inputs, hidden1, hidden2, classes} (784, 256, 128, 10 in the reference, :25-28);
+ * max_batch = the largest LOCAL batch (columns per GPU) a step will be given. */
+bla_mlp* bla_mlp_create(const int dims[4], int max_batch);
+void bla_mlp_destroy(bla_mlp* net);
+/* Parameters in the reference's layout: W_l [n_l x n_{l-1}] row-major, b_l [n_l] (:165-170).
+ * Pointers may be host or device memory. */
+void bla_mlp_set_params(bla_mlp* net, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                        const float* b3);
+void bla_mlp_get_params(bla_mlp* net, float* w1, float* b1, float* w2, float* b2, float* w3, float* b3);
+/* He-uniform weights / zero biases as model/mnist_nn.c:97-144 (`init`), from the counter-based generator. */
+void bla_mlp_init_params(bla_mlp* net, unsigned long long seed);
+/* One SGD step on x [inputs x batch] RAW pixel values (the 1/255.0F scaling of :218 is fused) and
+ * one-hot y [classes x batch]; x/y may be device memory (asynchronous) or host memory (staged).
+ * global_batch/col_offset describe the shard (global_batch == batch, col_offset == 0 on one GPU).
+ * lr_mult = SGD_LEARN_RATE_MULTIPLIER (0.02).  stats_host, if not NULL, receives {loss_sum, num_correct}
+ * of the GLOBAL batch and forces a synchronise; pass NULL to keep the step asynchronous. */
+void bla_mlp_train_step(bla_mlp* net, const float* x, const float* y, int batch, int global_batch, int col_offset,
+                        float lr_mult, double* stats_host);
+/* Same step from byte pixels (MNIST's native storage): x_u8 [inputs x batch]. */
+void bla_mlp_train_step_u8(bla_mlp* net, const unsigned char* x_u8, const float* y, int batch, int global_batch,
+                           int col_offset, float lr_mult, double* stats_host);
+/* Forward only (model/mnist_nn.c:446-463, `run`): probs [classes x batch] out. */
+void bla_mlp_forward(bla_mlp* net, const float* x, int batch, float* probs);
+/* {loss_sum, num_correct} accumulated on the device since the last call (then cleared). */
+void bla_mlp_read_stats(bla_mlp* net, double* stats_host);
+
+/* ---- NCCL over NVLink: one process per GPU -------------------------------------------------- */
+
+/* Rank 0 fills a 128-byte id (ncclGetUniqueId) that the launcher broadcasts out of band
+ * (torch.distributed store, MPI, a file ...); every rank then calls bla_comm_init with it. */
+void bla_comm_unique_id(void* id128);
+void bla_comm_init(const void* id128, int rank, int world);
+int bla_comm_world(void);
+int bla_comm_rank(void);
+/* In-place sum all-reduce of device buffers on the library stream. */
+void bla_allreduce_sum_f32(float* buf, size_t n);
+void bla_allreduce_sum_f64(double* buf, size_t n);
+/* Broadcast a device buffer from `root` (row-sharded GEMM: every rank needs all of B). */
+void bla_broadcast_f32(float* buf, size_t n, int root);
+void bla_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

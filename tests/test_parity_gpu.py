@@ -1,0 +1,430 @@
+"""-m gpu parity tests: the CUDA product (libbla.so) through its C-ABI against (1) the committed
+golden vectors generated from the reference's own compiled C and (2) the pinned CPU oracle on
+seeded inputs.  Tolerances (BASELINE.json north_star): FP32 path <= 1e-5 norm-wise relative vs the
+reference's double build, 3xTF32 path <= 1e-3; the lib/layer.c path is bit-exact vs the
+reference's float build."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_DIR, load_oracle, ptr, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+TF32X3_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def bla():
+    import bla_b200 as b
+    assert b.bla_device_count() >= 1
+    assert not b.MISSING
+    b.bla_set_gemm_path(b.GEMM_FP32)
+    b.bla_set_quirks(1)
+    return b
+
+
+@pytest.fixture(scope="module")
+def g64():
+    return np.load(os.path.join(GOLDEN_DIR, "ref_f64.npz"))
+
+
+def f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# lib/matrix.h on ordinary host memory (what an unchanged model program passes)
+# ------------------------------------------------------------------------------------------------
+def test_matrix_api_host_memory_vs_golden(bla, g64):
+    b = bla
+    a, bm = f32(g64["gemm_a"]), f32(g64["gemm_b"])
+    c = b.matrix_multiply(b.host_matrix(a), b.host_matrix(bm))
+    assert b.bla_memory_kind(C.cast(c.contents.data, C.c_void_p)) == b.KIND_MANAGED
+    got = b.to_numpy(c)
+    # managed result is host-dereferenceable, as model code requires (mnist_nn.c:242)
+    direct = np.ctypeslib.as_array(c.contents.data, shape=(got.size,)).reshape(got.shape)
+    assert np.array_equal(direct, got)
+    assert rel_err(got, g64["gemm_c"]) <= FP32_TOL
+    b.free_matrix(c)
+    ka, kb = f32(g64["kat_a"]), f32(g64["kat_b"])
+    kc = b.matrix_multiply(b.host_matrix(ka), b.host_matrix(kb))
+    np.testing.assert_allclose(b.to_numpy(kc), [[1.4, 8.5], [5.0, 19.0]], rtol=1e-6)   # main.c:20-41
+    b.free_matrix(kc)
+
+    x, y = f32(g64["ew_x"]), f32(g64["ew_y"])
+    R, Cc = x.shape
+
+    def run(fn, *extra):
+        t = x.copy()
+        m = b.host_matrix(t)
+        fn(C.byref(m), *extra)
+        return t, m
+
+    t, _ = run(b.matrix_scale, C.c_float(1 / np.float32(255.0))); assert rel_err(t, g64["scale"]) <= FP32_TOL
+    ym = b.host_matrix(y)
+    t, _ = run(b.matrix_add, C.byref(ym)); assert rel_err(t, g64["add"]) <= FP32_TOL
+    t, _ = run(b.matrix_multiply_elementwise, C.byref(ym)); assert rel_err(t, g64["hadamard"]) <= FP32_TOL
+    t, m = run(b.matrix_transpose)
+    assert (m.rows, m.cols) == (Cc, R) and np.array_equal(t.reshape(Cc, R), x.T)
+    assert rel_err(b.to_numpy(b.matrix_row_sum(b.host_matrix(x))), g64["row_sum"]) <= FP32_TOL
+    assert rel_err(b.to_numpy(b.matrix_col_sum(b.host_matrix(x))), g64["col_sum"]) <= FP32_TOL
+    assert abs(b.frobenius_norm(b.host_matrix(x)) - float(g64["frobenius"])) <= FP32_TOL * float(g64["frobenius"])
+    assert b.max_value(b.host_matrix(x)) == np.float32(g64["max_value"])
+    t, _ = run(b.matrix_z_score_normalize); assert rel_err(t, g64["zscore"]) <= FP32_TOL
+    bias = f32(g64["tile_cols_b"]); bmx = b.host_matrix(bias)
+    t, _ = run(b.matrix_add_tile_columns, C.byref(bmx)); assert rel_err(t, g64["tile_cols"]) <= FP32_TOL
+    bias3 = f32(g64["tile_cols3_b"]); bm3 = b.host_matrix(bias3)
+    t, _ = run(b.matrix_add_tile_columns, C.byref(bm3)); assert rel_err(t, g64["tile_cols3"]) <= FP32_TOL
+    rb = f32(g64["tile_rows_b"]); rbm = b.host_matrix(rb)
+    t, _ = run(b.matrix_add_tile_rows, C.byref(rbm)); assert rel_err(t, g64["tile_rows"]) <= FP32_TOL
+    t = x.copy(); b.relu(ptr(t), t.size); assert np.array_equal(t, f32(g64["relu"]))
+    t = f32(4 * x); b.softmax(ptr(t), R, Cc); assert rel_err(t, g64["softmax_cols"]) <= FP32_TOL
+    t = f32(4 * x); b.softmax_row_wise(ptr(t), R, Cc); assert rel_err(t, g64["softmax_rows"]) <= FP32_TOL
+
+
+def test_clone_and_interior_pointers(bla):
+    b = bla
+    rng = np.random.default_rng(0)
+    buf = rng.normal(size=(1, 785)).astype(np.float32)
+    # model/mnist_hinge.c:62 hands `buffer + 1` (not 16-byte aligned) to matrix_scale
+    view = buf[:, 1:]
+    m = b.Matrix(784, 1, C.cast(buf.ctypes.data + 4, b.c_float_p))
+    want = view.copy() * np.float32(1 / np.float32(255.0))
+    b.matrix_scale(C.byref(m), C.c_float(1 / np.float32(255.0)))
+    assert np.array_equal(buf[:, 1:], want) and buf[0, 0] == buf[0, 0]
+    cl = b.clone_matrix(m)
+    assert np.array_equal(b.to_numpy(cl).ravel(), buf[0, 1:])
+    b.free_matrix(cl)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM (FP32 SIMT path): shapes, transposes, epilogue, split-K, device residency
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,N", [(1, 1, 1), (5, 1, 7), (64, 96, 33), (10, 128, 200), (129, 130, 131), (256, 784, 512),
+                                   (300, 17, 300), (1, 784, 1), (3, 2, 1), (128, 128, 128)])
+def test_gemm_shapes_vs_oracle(bla, M, K, N):
+    b = bla
+    o = load_oracle(np.float64)
+    rng = np.random.default_rng(M * 1000 + K * 10 + N)
+    a = rng.uniform(-0.5, 0.5, (M, K)); bm = rng.uniform(-0.5, 0.5, (K, N))
+    want = np.empty((M, N))
+    o.orc_gemm(M, K, N, ptr(a), ptr(bm), ptr(want))
+    a32, b32 = f32(a), f32(bm)
+    c = b.matrix_multiply(b.host_matrix(a32), b.host_matrix(b32))
+    assert rel_err(b.to_numpy(c), want) <= FP32_TOL
+    b.free_matrix(c)
+    # in-place variant into caller storage (lib/matrix.c:47)
+    out = np.full((M, N), np.nan, np.float32)
+    am, bmm, cm = b.host_matrix(a32), b.host_matrix(b32), b.host_matrix(out)
+    b.matrix_multiply_inplace(C.byref(am), C.byref(bmm), C.byref(cm))
+    assert rel_err(out, want) <= FP32_TOL
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_transposes_and_epilogue(bla, ta, tb):
+    b = bla
+    rng = np.random.default_rng(7 + 2 * ta + tb)
+    M, N, K = 150, 203, 77
+    a = rng.normal(size=(M, K)); bm = rng.normal(size=(K, N))
+    bias_r = rng.normal(size=M); gate = rng.normal(size=(M, N))
+    a_st = f32(a.T if ta else a); b_st = f32(bm.T if tb else bm)
+    z = a_st.astype(np.float64).T @ (b_st.astype(np.float64).T if tb else b_st.astype(np.float64)) if ta else \
+        a_st.astype(np.float64) @ (b_st.astype(np.float64).T if tb else b_st.astype(np.float64))
+    out = np.empty((M, N), np.float32)
+    b.bla_gemm(ta, tb, M, N, K, ptr(a_st), a_st.shape[1], ptr(b_st), b_st.shape[1], ptr(out), N)
+    assert rel_err(out, z) <= FP32_TOL
+    # fused bias + relu + pre-activation copy + gate
+    br32, g32 = f32(bias_r), f32(gate)
+    pre = np.empty((M, N), np.float32)
+    epi = b.Epilogue(br32.ctypes.data, None, pre.ctypes.data, g32.ctypes.data, b.ACT_RELU, 0.5)
+    b.bla_gemm_ex(ta, tb, M, N, K, ptr(a_st), a_st.shape[1], ptr(b_st), b_st.shape[1], ptr(out), N, C.byref(epi))
+    zz = 0.5 * z + br32.astype(np.float64)[:, None]
+    assert rel_err(pre, zz) <= FP32_TOL
+    want = np.maximum(pre, 0) * (g32 > 0)
+    assert np.array_equal(out, want)
+
+
+def test_gemm_split_k_long_contraction(bla):
+    """wgrad-shaped: tiny output, K = 60000 (model/mnist_nn.c:290 at B = 60k)."""
+    b = bla
+    rng = np.random.default_rng(11)
+    M, N, K = 40, 56, 60000
+    a = f32(rng.uniform(-1, 1, (M, K))); bt = f32(rng.uniform(-1, 1, (N, K)))
+    want = a.astype(np.float64) @ bt.astype(np.float64).T
+    out = np.empty((M, N), np.float32)
+    b.bla_gemm(0, 1, M, N, K, ptr(a), K, ptr(bt), K, ptr(out), N)
+    assert rel_err(out, want) <= FP32_TOL
+
+
+def test_device_resident_matrices_stay_on_device(bla):
+    b = bla
+    rng = np.random.default_rng(5)
+    a = f32(rng.normal(size=(200, 300))); bm = f32(rng.normal(size=(300, 100)))
+    da, db = b.device_matrix_from(a), b.device_matrix_from(bm)
+    h2d0, d2h0 = b.bla_h2d_bytes(), b.bla_d2h_bytes()
+    dc = b.matrix_multiply(da.contents, db.contents)
+    b.matrix_scale(dc, C.c_float(2.0))
+    b.matrix_transpose(dc)
+    assert b.bla_memory_kind(C.cast(dc.contents.data, C.c_void_p)) == b.KIND_DEVICE
+    assert (b.bla_h2d_bytes(), b.bla_d2h_bytes()) == (h2d0, d2h0)       # nothing crossed PCIe
+    got = b.to_numpy(dc)
+    assert (dc.contents.rows, dc.contents.cols) == (100, 200)
+    assert rel_err(got, 2 * (a.astype(np.float64) @ bm.astype(np.float64)).T) <= FP32_TOL
+    for m in (da, db, dc):
+        b.free_matrix(m)
+
+
+def test_gemm_large_checksum_property(bla):
+    """Size-independent check at a sweep size the CPU oracle cannot finish: (A.B).1 == A.(B.1)."""
+    b = bla
+    n = 4096
+    A = b.bla_matrix_device(n, n); B = b.bla_matrix_device(n, n)
+    b.bla_fill_uniform(C.cast(A.contents.data, C.c_void_p), n * n, 1, -0.5, 0.5)
+    b.bla_fill_uniform(C.cast(B.contents.data, C.c_void_p), n * n, 2, -0.5, 0.5)
+    Cm = b.matrix_multiply(A.contents, B.contents)
+    ones = b.device_matrix_from(np.ones((n, 1), np.float32))
+    lhs = b.matrix_multiply(Cm.contents, ones.contents)
+    b1 = b.matrix_multiply(B.contents, ones.contents)
+    rhs = b.matrix_multiply(A.contents, b1.contents)
+    assert rel_err(b.to_numpy(lhs), b.to_numpy(rhs)) <= 1e-4
+    # and a row of C against float64 numpy on the host twin of the generator
+    ha = np.empty(n * n, np.float32); hb = np.empty(n * n, np.float32)
+    b.bla_host_uniform(ptr(ha), n * n, 1, -0.5, 0.5); b.bla_host_uniform(ptr(hb), n * n, 2, -0.5, 0.5)
+    assert np.array_equal(b.to_numpy(A).ravel(), ha)
+    row = ha.reshape(n, n)[17].astype(np.float64) @ hb.reshape(n, n).astype(np.float64)
+    assert rel_err(b.to_numpy(Cm)[17], row) <= FP32_TOL
+    for m in (A, B, Cm, ones, lhs, b1, rhs):
+        b.free_matrix(m)
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise + reductions at awkward sizes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (257, 1023), (1024, 1031), (10, 60000)])
+def test_elementwise_and_reductions_vs_oracle(bla, shape):
+    b = bla
+    o = load_oracle(np.float64)
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    x = rng.normal(0.1, 1, shape); y = rng.normal(0, 1, shape)
+    x32, y32 = f32(x), f32(y)
+    x64, y64 = x32.astype(np.float64), y32.astype(np.float64)
+    R, Cc = shape
+    t = x32.copy(); m = b.host_matrix(t); ym = b.host_matrix(y32)
+    b.matrix_add(C.byref(m), C.byref(ym)); assert np.array_equal(t, x32 + y32)
+    b.matrix_multiply_elementwise(C.byref(m), C.byref(ym)); assert np.array_equal(t, (x32 + y32) * y32)
+    t = x32.copy(); m = b.host_matrix(t); b.matrix_transpose(C.byref(m)); assert np.array_equal(t.reshape(Cc, R), x32.T)
+    # D2 quirk, including the cols < rows contract (out-of-range elements count as 0)
+    want = np.empty((R, 1)); o.orc_col_sum(R, Cc, ptr(x64), ptr(want), 1)
+    assert rel_err(b.to_numpy(b.matrix_col_sum(b.host_matrix(x32))), want) <= FP32_TOL
+    want = np.empty((1, Cc)); o.orc_row_sum(R, Cc, ptr(x64), ptr(want))
+    assert rel_err(b.to_numpy(b.matrix_row_sum(b.host_matrix(x32))), want) <= FP32_TOL
+    o.orc_frobenius.restype = C.c_double
+    fro = o.orc_frobenius(R, Cc, ptr(x64))
+    assert abs(b.frobenius_norm(b.host_matrix(x32)) - fro) <= FP32_TOL * fro
+    assert b.max_value(b.host_matrix(x32)) == x32.max()
+    if x.size > 1:
+        t = x32.copy(); m = b.host_matrix(t); b.matrix_z_score_normalize(C.byref(m))
+        w = x64.copy(); o.orc_zscore(C.c_size_t(w.size), ptr(w))
+        assert rel_err(t, w) <= FP32_TOL
+    t = x32.copy(); b.softmax(ptr(t), R, Cc); w = x64.copy(); o.orc_softmax_cols(R, Cc, ptr(w)); assert rel_err(t, w) <= FP32_TOL
+    t = x32.copy(); b.softmax_row_wise(ptr(t), R, Cc); w = x64.copy(); o.orc_softmax_rows(R, Cc, ptr(w)); assert rel_err(t, w) <= FP32_TOL
+    t = x32.copy(); b.bla_relu_ddx(ptr(t), t.size); assert np.array_equal(t, (x32 > 0).astype(np.float32))
+
+
+def test_quirks_off_gives_row_totals(bla):
+    b = bla
+    x = f32(np.random.default_rng(2).normal(size=(37, 11)))
+    b.bla_set_quirks(0)
+    try:
+        got = b.to_numpy(b.matrix_col_sum(b.host_matrix(x)))
+    finally:
+        b.bla_set_quirks(1)
+    assert rel_err(got.ravel(), x.astype(np.float64).sum(axis=1)) <= FP32_TOL
+
+
+def test_softmax_xent_matches_mlp_tail(bla):
+    """model/mnist_nn.c:234-268 fused on the device, against the oracle's restatement of the same lines."""
+    b = bla
+    rng = np.random.default_rng(3)
+    classes, batch = 10, 777
+    logits = f32(rng.normal(0, 3, (classes, batch)))
+    labels = rng.integers(0, classes, batch)
+    Y = np.zeros((classes, batch), np.float32); Y[labels, np.arange(batch)] = 1
+    probs = np.empty_like(logits); grad = np.empty_like(logits)
+    stats = b.bla_malloc_device(16); b.bla_memset_zero(stats, 16)
+    b.bla_softmax_xent(ptr(logits), ptr(Y), classes, batch, ptr(probs), ptr(grad), 1 / 784.0, stats)
+    hs = np.zeros(2); b.bla_copy_d2h(ptr(hs), stats, 16); b.bla_sync(); b.bla_free(stats)
+    p64 = logits.astype(np.float64); load_oracle(np.float64).orc_softmax_cols(classes, batch, ptr(p64))
+    assert rel_err(probs, p64) <= FP32_TOL
+    assert rel_err(grad, (p64 - Y) / 784.0) <= FP32_TOL
+    flatp, flaty = p64.ravel(), Y.astype(np.float64).ravel()
+    want_loss = float(-(flaty * np.log(flatp + 1e-15)).sum())        # flat-slice quirk sums to this
+    assert abs(hs[0] - want_loss) <= 1e-5 * abs(want_loss)
+    pred = np.where(p64.max(axis=0) > 0, p64.argmax(axis=0), 0)
+    assert int(hs[1]) == int((pred == labels).sum())
+
+
+# ------------------------------------------------------------------------------------------------
+# lib/layer.h: bit-exact against the reference's float build (golden from main.c and a 2-3-2 net)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,sizes,kind", [("main", [3, 2, 2], "scale"), ("mfm", [2, 3, 2], "relu")])
+def test_layer_api_bit_exact_vs_reference(bla, tag, sizes, kind):
+    b = bla
+    g = np.load(os.path.join(GOLDEN_DIR, "ref_layer_f32.npz"))
+    libc = C.CDLL(None); libc.malloc.restype = C.c_void_p
+
+    def heap(arr):
+        arr = f32(arr)
+        p = libc.malloc(C.c_size_t(max(arr.nbytes, 4)))
+        C.memmove(p, arr.ctypes.data, arr.nbytes)
+        return p
+
+    if kind == "scale":        # main.c:7-17: unrecognised slope callback -> runs on the host
+        def act(d, n):
+            for i in range(n):
+                d[i] = np.float32(np.float64(d[i]) * 0.1)
+
+        def ddx(d, n):
+            for i in range(n):
+                d[i] = 0.1
+    else:                      # my_first_model.c:8-20: recognised and fused on the device
+        def act(d, n):
+            for i in range(n):
+                if d[i] < 0:
+                    d[i] = 0
+
+        def ddx(d, n):
+            for i in range(n):
+                d[i] = 1.0 if d[i] > 0 else 0.0
+    fa, fd = b.ACT_FN(act), b.ACT_FN(ddx)
+    layers = [b.Layer() for _ in sizes]
+    layers[0].num_nodes = sizes[0]
+    layers[0].nodes = b.make_matrix(sizes[0], 1, heap(g[f"{tag}_x"]))
+    layers[0].has_nodes = b"\x01"; layers[0].has_previous_layer = b"\x00"
+    for i in range(1, len(sizes)):
+        L = layers[i]
+        L.num_nodes = sizes[i]
+        L.weights = b.make_matrix(sizes[i], sizes[i - 1], heap(g[f"{tag}_W{i}_in"]))
+        L.biases = b.make_matrix(sizes[i], 1, heap(g[f"{tag}_b{i}_in"]))
+        L.previous_layer = C.pointer(layers[i - 1])
+        L.activation, L.activation_ddx = fa, fd
+        L.has_previous_layer = b"\x01"; L.has_nodes = b"\x00"
+    for i in range(1, len(sizes)):
+        b.feed_forward(C.byref(layers[i]))
+    for i in range(1, len(sizes)):
+        assert np.array_equal(b.to_numpy(layers[i].raw_nodes), g[f"{tag}_raw{i}"])
+        assert np.array_equal(b.to_numpy(layers[i].nodes), g[f"{tag}_nodes{i}"])
+    t = f32(g[f"{tag}_target"])
+    b.back_propagate_errors(C.byref(layers[-1]), t.ctypes.data_as(b.c_float_p), C.c_float(float(g[f"{tag}_lr"])))
+    for i in range(1, len(sizes)):
+        assert np.array_equal(b.to_numpy(layers[i].weights), g[f"{tag}_W{i}_out"])
+        assert np.array_equal(b.to_numpy(layers[i].biases), g[f"{tag}_b{i}_out"])
+    # a second forward pass must recycle the previous results without leaking or crashing
+    for i in range(1, len(sizes)):
+        b.feed_forward(C.byref(layers[i]))
+    for i in range(len(sizes) - 1, 0, -1):
+        b.free_layer_data(layers[i])
+    b.free_matrix(layers[0].nodes)
+
+
+# ------------------------------------------------------------------------------------------------
+# lib/conv.h and lib/norm.h on channel planes
+# ------------------------------------------------------------------------------------------------
+def _conv_buffers(b, Cin, H, W, F, k, s):
+    Ho, Wo = -(-H // s), -(-W // s)
+    bufs = dict(im2col=np.zeros((Ho * Wo, k * k * Cin), np.float32), kernel_matrix=np.zeros((k * k * Cin, F), np.float32),
+                product=np.zeros((Ho * Wo, F), np.float32), output=np.full((F, Ho, Wo), -999, np.float32))
+    mats = {n: b.host_matrix(v) for n, v in bufs.items() if n != "output"}
+    outp = b.planes(bufs["output"])
+    cd = b.ConvData(C.pointer(mats["im2col"]), C.pointer(mats["kernel_matrix"]), C.pointer(mats["product"]), C.cast(outp, b.MatrixP))
+    cd._keep = (bufs, mats, outp)
+    return cd, bufs
+
+
+@pytest.mark.parametrize("case", ["s1k3", "s2k3", "s1k1", "s1k3_ragged"])
+def test_conv_api_vs_golden(bla, g64, case):
+    b = bla
+    Cin, H, W, F, k, s = [int(v) for v in g64[f"conv_{case}_meta"]]
+    x, kr = f32(g64[f"conv_{case}_x"]), f32(g64[f"conv_{case}_k"])
+    cd, bufs = _conv_buffers(b, Cin, H, W, F, k, s)
+    xp, kt = b.planes(x), b.kernel_table(kr)
+    b.conv(C.cast(xp, b.MatrixP), kt, C.byref(cd), Cin, F, s)
+    assert rel_err(bufs["output"], g64[f"conv_{case}_y"]) <= FP32_TOL
+    assert np.array_equal(bufs["im2col"], f32(g64[f"conv_{case}_im2col"]))
+    assert np.array_equal(bufs["kernel_matrix"], kr.reshape(F, -1).T)
+    assert rel_err(bufs["product"], g64[f"conv_{case}_y"].reshape(F, -1).T) <= FP32_TOL
+    if f"conv_{case}_dy" in g64.files:
+        dy = f32(g64[f"conv_{case}_dy"])
+        gcd, gbufs = _conv_buffers(b, Cin, H, W, F, k, s)
+        dk = np.zeros_like(kr); dx = np.zeros_like(x)
+        dyp, dkt, dxp = b.planes(dy), b.kernel_table(dk), b.planes(dx)
+        b.conv_ddx(C.cast(dyp, b.MatrixP), C.byref(cd), C.byref(gcd), dkt, C.cast(dxp, b.MatrixP), Cin, s)
+        assert rel_err(dk, g64[f"conv_{case}_dk"]) <= FP32_TOL
+        assert rel_err(dx, g64[f"conv_{case}_dx"]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("Cin,H,W,F,k,s", [(128, 32, 32, 128, 3, 1), (128, 32, 32, 256, 3, 2), (3, 32, 32, 128, 3, 1),
+                                           (256, 8, 8, 256, 1, 1), (256, 4, 4, 256, 3, 1)])
+def test_conv_unet_shapes_vs_oracle(bla, Cin, H, W, F, k, s):
+    """The U-Net's own conv shapes, forward and backward, against the f64 oracle
+    (whose stride-2 dgrad is the validated adjoint)."""
+    b = bla
+    o = load_oracle(np.float64)
+    rng = np.random.default_rng(Cin + H + F + k + s)
+    x = rng.normal(size=(Cin, H, W)); kr = rng.normal(0, 0.05, (F, Cin, k, k))
+    Ho, Wo = -(-H // s), -(-W // s)
+    dy = rng.normal(size=(F, Ho, Wo))
+    y = np.empty((F, Ho, Wo)); dk = np.empty_like(kr); dx = np.empty_like(x)
+    o.orc_conv(Cin, H, W, F, k, s, ptr(x), ptr(kr), ptr(y))
+    o.orc_conv_ddx(Cin, H, W, F, k, s, ptr(x), ptr(kr), ptr(dy), ptr(dk), ptr(dx))
+    x32, k32, dy32 = f32(x), f32(kr), f32(dy)
+    cd, bufs = _conv_buffers(b, Cin, H, W, F, k, s)
+    b.conv(C.cast(b.planes(x32), b.MatrixP), b.kernel_table(k32), C.byref(cd), Cin, F, s)
+    assert rel_err(bufs["output"], y) <= FP32_TOL
+    gcd, _ = _conv_buffers(b, Cin, H, W, F, k, s)
+    dk32 = np.zeros_like(k32); dx32 = np.zeros_like(x32)
+    dkt = b.kernel_table(dk32); dxp = b.planes(dx32)
+    b.conv_ddx(C.cast(b.planes(dy32), b.MatrixP), C.byref(cd), C.byref(gcd), dkt, C.cast(dxp, b.MatrixP), Cin, s)
+    assert rel_err(dk32, dk) <= FP32_TOL
+    assert rel_err(dx32, dx) <= FP32_TOL
+
+
+@pytest.mark.parametrize("case", ["even", "ragged", "rgb"])
+def test_group_norm_api_vs_golden(bla, g64, case):
+    b = bla
+    Cn, H, W, gs = [int(v) for v in g64[f"gn_{case}_meta"]]
+    G = -(-Cn // gs)
+    x = f32(g64[f"gn_{case}_x"])
+    y = np.zeros_like(x); var = np.zeros(G, np.float32); mu = np.zeros(G, np.float32)
+    b.group_norm(C.cast(b.planes(x), b.MatrixP), C.cast(b.planes(y), b.MatrixP), ptr(var), ptr(mu), Cn, gs)
+    assert rel_err(y, g64[f"gn_{case}_y"]) <= FP32_TOL
+    assert rel_err(var, g64[f"gn_{case}_var"]) <= FP32_TOL and rel_err(mu, g64[f"gn_{case}_mean"]) <= FP32_TOL
+    dy = f32(g64[f"gn_{case}_dy"]); dx = np.zeros_like(x)
+    var64, mu64 = f32(g64[f"gn_{case}_var"]), f32(g64[f"gn_{case}_mean"])
+    b.group_norm_ddx(C.cast(b.planes(dy), b.MatrixP), C.cast(b.planes(dx), b.MatrixP), C.cast(b.planes(x), b.MatrixP),
+                     ptr(mu64), ptr(var64), Cn, gs)
+    assert rel_err(dx, g64[f"gn_{case}_dx"]) <= 5 * FP32_TOL   # divides twice by a small variance
+
+
+@pytest.mark.parametrize("Cn,HW", [(128, 1024), (256, 256), (512, 64), (256, 16)])
+def test_group_norm_unet_shapes_vs_oracle(bla, Cn, HW):
+    b = bla
+    o = load_oracle(np.float64)
+    rng = np.random.default_rng(Cn + HW)
+    side = int(round(HW ** 0.5))
+    x = rng.normal(0.2, 1.3, (Cn, side, side)); dy = rng.normal(size=x.shape)
+    G = Cn // 32
+    y = np.empty_like(x); var = np.empty(G); mu = np.empty(G); dx = np.empty_like(x)
+    o.orc_group_norm(Cn, HW, 32, ptr(x), ptr(y), ptr(var), ptr(mu), 1)
+    o.orc_group_norm_ddx(Cn, HW, 32, ptr(dy), ptr(dx), ptr(x), ptr(mu), ptr(var))
+    x32, dy32 = f32(x), f32(dy)
+    y32 = np.zeros_like(x32); v32 = np.zeros(G, np.float32); m32 = np.zeros(G, np.float32); dx32 = np.zeros_like(x32)
+    b.group_norm(C.cast(b.planes(x32), b.MatrixP), C.cast(b.planes(y32), b.MatrixP), ptr(v32), ptr(m32), Cn, 32)
+    assert rel_err(y32, y) <= FP32_TOL and rel_err(v32, var) <= FP32_TOL
+    b.group_norm_ddx(C.cast(b.planes(dy32), b.MatrixP), C.cast(b.planes(dx32), b.MatrixP), C.cast(b.planes(x32), b.MatrixP),
+                     ptr(m32), ptr(v32), Cn, 32)
+    assert rel_err(dx32, dx) <= 5 * FP32_TOL
