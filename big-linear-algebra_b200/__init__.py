@@ -20,7 +20,7 @@ if not os.path.exists(LIB_PATH):
         f"{LIB_PATH} is missing: build it with `make -C {_HERE}` (nvcc, sm_100a). "
         "There is no CPU or PyTorch fallback for the big-linear-algebra hot path.")
 
-lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+lib = C.CDLL(LIB_PATH)   # RTLD_LOCAL: the test-only reference build exports the same names
 
 c_float_p = C.POINTER(C.c_float)
 

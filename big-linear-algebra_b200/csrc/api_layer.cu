@@ -4,14 +4,13 @@
 // the arithmetic inside a kernel keeps the reference's order and rounding (separate IEEE multiply
 // and add, k ascending) so results are bit-identical to the reference's float build.
 //
-// Activations are host function pointers (lib/layer.h:11-12).  A callback is probed once on a
+// Activations are host function pointers (lib/layer.h:11-12).  A callback is probed on each call on a
 // fixed host vector; ReLU, ReLU' (0/1 step) and constant-valued derivatives are recognised exactly
 // and fused into the kernels; any other callback is applied on the host to the host-visible
 // (managed) result, exactly as the reference would.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <unordered_map>
 
 #include "../../include/lib/layer.h"
 #include "../../include/lib/matrix.h"
@@ -28,9 +27,8 @@ enum ActKind { kActHost = 0, kActIdentity = 1, kActRelu = 2, kActStep = 3, kActC
 struct ActInfo { int kind; float c; };
 
 ActInfo probe(void (*fn)(float*, int)) {
-    static std::unordered_map<void*, ActInfo> cache;
-    auto it = cache.find((void*)fn);
-    if (it != cache.end()) return it->second;
+    // Probed on every call (13 floats): a cache keyed by address would go stale when a host
+    // runtime recycles callback trampolines (ctypes, JITs, dlclose).
     const float in[13] = {-1e30f, -100.f, -2.f, -0.5f, -1e-30f, -0.0f, 0.f, 1e-30f, 0.5f, 1.f, 3.f, 100.f, 1e30f};
     float out[13];
     memcpy(out, in, sizeof(in));
@@ -49,7 +47,6 @@ ActInfo probe(void (*fn)(float*, int)) {
     else if (relu) a.kind = kActRelu;
     else if (step) a.kind = kActStep;
     else if (cst) { a.kind = kActConst; a.c = out[0]; }
-    cache[(void*)fn] = a;
     return a;
 }
 

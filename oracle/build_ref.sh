@@ -50,7 +50,7 @@ build_lib() {          # $1 = variant, $2 = with layer.c? (0/1)
   local t="$GEN/$1"
   local srcs="$t/lib/matrix.c $t/lib/conv.c $t/lib/norm.c $t/lib/util.c $t/lib/csv.c"
   if [ "$2" = 1 ]; then srcs="$srcs $t/lib/layer.c"; fi
-  $CC $CFLAGS -shared -o "$OUT/libref_$1.so" $srcs -lm
+  $CC $CFLAGS -shared -Wl,-Bsymbolic -o "$OUT/libref_$1.so" $srcs -lm
 }
 
 mk_tree f64 double 0;          build_lib f64 0
