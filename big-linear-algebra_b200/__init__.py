@@ -116,6 +116,8 @@ PROTOTYPES = {
     "bla_version": (C.c_char_p, []),
     "bla_set_gemm_path": (None, [C.c_int]),
     "bla_get_gemm_path": (C.c_int, []),
+    "bla_tc_available": (C.c_int, []),
+    "bla_tc_launch_count": (C.c_ulonglong, []),
     "bla_set_quirks": (None, [C.c_int]),
     "bla_get_quirks": (C.c_int, []),
     "bla_launch_count": (C.c_ulonglong, []),

@@ -1,5 +1,493 @@
-// gemm_tc.cu -- placeholder until the tcgen05 3xTF32 kernel lands (next commit).
+// gemm_tc.cu -- the 3xTF32 tensor-core GEMM path: C = op(A).op(B) with FP32-class
+// accuracy from TF32 tcgen05.mma instructions, accumulating in FP32 in tensor memory (TMEM).
+//
+// Arithmetic.  Each fp32 operand x is split as x = hi + lo with hi = x truncated to TF32 (the
+// tensor core itself ignores the low 13 mantissa bits of a 32-bit operand, so the RAW fp32 tile is
+// the hi tile) and lo = tf32_rna(x - hi) (exact subtraction, 13 significant bits, rounded to 11).
+// Every product is issued three times, a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, into one TMEM
+// accumulator; the dropped lo.lo term and the rounding of lo are O(2^-21) relative.
+//
+// Dataflow per CTA (persistent, one CTA per SM, 10 warps):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles of raw A (128 x 32) and B (32 x 256) fp32
+//               into 128B-swizzled shared memory, 2-stage ring, mbarrier complete_tx.
+//   warps 6-9   splitters: read the raw tile from shared memory, write the lo tile next to it
+//               (same swizzled positions, so the split is a flat elementwise pass), then
+//               fence.proxy.async and arrive on the stage's "split" barrier.
+//   warp 1      MMA issuer (one lane): 12 tcgen05.mma.kind::tf32 128x256x8 per stage
+//               (4 k-steps x 3 products), tcgen05.commit -> frees the stage / publishes the tile.
+//   warps 2-5   epilogue: tcgen05.ld the 128 x 256 fp32 accumulator (TMEM is double-buffered, so
+//               the next tile's MMAs overlap), transpose through swizzled shared memory so that
+//               global stores / gate loads are full 128-byte rows, fused alpha / bias / ReLU /
+//               pre-activation copy / relu' gate, or raw partials for split-K.
+// Operand layouts are expressed only through the TMA box and the UMMA descriptor: K-major
+// (A row-major, B stored [n][k]) and MN-major (A stored [k][m], B row-major) -- no transposes.
+#include <cuda.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
 #include "kernels.h"
+#include "runtime.h"
+
 namespace bla {
-bool gemm_3xtf32(const GemmArgs&, cudaStream_t) { return false; }
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 32;
+constexpr int kStages = 2;
+constexpr int kAccStages = 2;
+constexpr int kThreads = 320;
+constexpr uint32_t kABytes = BM * BK * 4;               // 16 KB
+constexpr uint32_t kBBytes = BN * BK * 4;               // 32 KB
+constexpr uint32_t kRawBytes = kABytes + kBBytes;       // 48 KB  (lo tiles mirror it at +kRawBytes)
+constexpr uint32_t kStageBytes = 2 * kRawBytes;         // 96 KB
+constexpr uint32_t kStagingBytes = 4 * 32 * 32 * 4;     // 16 KB: one 32x32 fp32 tile per epilogue warp
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;   // + barriers + alignment slack
+
+struct TcParams {
+    int m, n, k;
+    int m_tiles, n_tiles, splits, kblocks_per_split, kblocks;
+    bool a_kmajor, b_kmajor;
+    float* c; int ldc;
+    float* partial;          // [splits][m][n] when splits > 1
+    bla_epilogue epi;
+    bool c_vec;              // 16-byte aligned rows
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride
+// byte offsets (all >> 4), version 1 (Blackwell), SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // version
+    d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, FP32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_major) {
+    return (1u << 4)                       // c_format  = F32
+           | (2u << 7)                     // a_format  = TF32
+           | (2u << 10)                    // b_format  = TF32
+           | ((a_mn_major ? 1u : 0u) << 15)
+           | ((b_mn_major ? 1u : 0u) << 16)
+           | ((uint32_t)(BN >> 3) << 17)   // n_dim
+           | ((uint32_t)(BM >> 4) << 24);  // m_dim
+}
+
+__device__ __forceinline__ float epilogue_value(float acc, int i, int j, const TcParams& p) {
+    float v = acc;
+    if (p.epi.alpha != 0.f) v *= p.epi.alpha;
+    if (p.epi.bias_rows) v += p.epi.bias_rows[i];
+    if (p.epi.bias_cols) v += p.epi.bias_cols[j];
+    if (p.epi.pre_activation) p.epi.pre_activation[(size_t)i * p.ldc + j] = v;
+    if (p.epi.activation == BLA_ACT_RELU) v = v < 0.f ? 0.f : v;
+    if (p.epi.gate) v = p.epi.gate[(size_t)i * p.ldc + j] > 0.f ? v : 0.f;
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t staging_base = smem_base + kStages * kStageBytes;
+    const uint32_t bar_base = staging_base + kStagingBytes;
+    // barrier slots (8 bytes each)
+    auto bar_full = [&](int s) { return bar_base + 8u * s; };
+    auto bar_split = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto bar_empty = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto bar_acc_full = [&](int a) { return bar_base + 8u * (3 * kStages + a); };
+    auto bar_acc_empty = [&](int a) { return bar_base + 8u * (3 * kStages + kAccStages + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * kStages + 2 * kAccStages);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_split(s), 4);      // one arrival per splitter warp
+            mbar_init(bar_empty(s), 1);      // tcgen05.commit
+        }
+        for (int a = 0; a < kAccStages; ++a) {
+            mbar_init(bar_acc_full(a), 1);   // tcgen05.commit
+            mbar_init(bar_acc_empty(a), 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // whole warp: allocate all 512 TMEM columns (2 accumulator stages x 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int split = tile / (p.m_tiles * p.n_tiles);
+                const int mn = tile % (p.m_tiles * p.n_tiles);
+                const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
+                const int kb0 = split * p.kblocks_per_split;
+                const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(bar_empty(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                    mbar_arrive_expect_tx(bar_full(stage), kRawBytes);
+                    const int k0 = kb * BK;
+                    if (p.a_kmajor) {
+                        tma_load_2d(sa, &tma_a, k0, m0, bar_full(stage));                              // box {32 k, 128 m}
+                    } else {
+#pragma unroll
+                        for (int at = 0; at < BM / 32; ++at)                                            // box {32 m, 32 k} per atom
+                            tma_load_2d(sa + at * (BK * 128), &tma_a, m0 + 32 * at, k0, bar_full(stage));
+                    }
+                    if (p.b_kmajor) {
+                        tma_load_2d(sb, &tma_b, k0, n0, bar_full(stage));                              // box {32 k, 256 n}
+                    } else {
+#pragma unroll
+                        for (int at = 0; at < BN / 32; ++at)
+                            tma_load_2d(sb + at * (BK * 128), &tma_b, n0 + 32 * at, k0, bar_full(stage));
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(!p.a_kmajor, !p.b_kmajor);
+            // K-major: 8-row groups 1024 B apart, k-step = 32 B inside the swizzle row.
+            // MN-major: 32-wide atoms BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO), k-step = 1024 B.
+            const uint32_t a_lbo = p.a_kmajor ? 16u : BK * 128u, b_lbo = p.b_kmajor ? 16u : BK * 128u;
+            const uint32_t a_kstep = p.a_kmajor ? 32u : 1024u, b_kstep = p.b_kmajor ? 32u : 1024u;
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int split = tile / (p.m_tiles * p.n_tiles);
+                const int kb0 = split * p.kblocks_per_split;
+                const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
+                mbar_wait(bar_acc_empty(acc), acc_phase ^ 1);      // epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                uint32_t accumulate = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(bar_split(stage), phase);            // raw tile landed AND lo tile written
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t a_hi = make_desc(sa + ks * a_kstep, a_lbo, 1024u);
+                        const uint64_t b_hi = make_desc(sb + ks * b_kstep, b_lbo, 1024u);
+                        const uint64_t a_lo = make_desc(sa + kRawBytes + ks * a_kstep, a_lbo, 1024u);
+                        const uint64_t b_lo = make_desc(sb + kRawBytes + ks * b_kstep, b_lbo, 1024u);
+                        umma_tf32(tmem_d, a_lo, b_hi, idesc, accumulate);
+                        umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+                        umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
+                        accumulate = 1u;
+                    }
+                    tcgen05_commit(bar_empty(stage));              // stage reusable once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(bar_acc_full(acc));                 // accumulator complete -> epilogue
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 6) {
+        // ===================================== splitters ========================================
+        const int t = threadIdx.x - 6 * 32;   // 0..127
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int split = tile / (p.m_tiles * p.n_tiles);
+            const int kb0 = split * p.kblocks_per_split;
+            const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(bar_full(stage), phase);
+                float4* raw = reinterpret_cast<float4*>(smem_gen + stage * kStageBytes);
+                float4* lo = reinterpret_cast<float4*>(smem_gen + stage * kStageBytes + kRawBytes);
+#pragma unroll 4
+                for (int i = t; i < (int)(kRawBytes / 16); i += 128) {
+                    const float4 v = raw[i];
+                    float4 r;
+                    uint32_t u;
+                    // lo = rna_tf32(x - trunc_tf32(x)); the tensor core reads trunc_tf32(x) from the raw tile
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u))); r.x = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u))); r.y = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u))); r.z = __uint_as_float(u);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u))); r.w = __uint_as_float(u);
+                    lo[i] = r;
+                }
+                fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_split(stage));
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================== epilogue (warps 2-5) =============================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        float* stg = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + (warp - 2) * 4096);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int split = tile / (p.m_tiles * p.n_tiles);
+            const int mn = tile % (p.m_tiles * p.n_tiles);
+            const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
+            mbar_wait(bar_acc_full(acc), acc_phase);
+            tcgen05_fence_after();
+            const int row_base = m0 + 32 * q;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                const int col0 = n0 + 32 * ch;
+                if (col0 >= p.n) break;              // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + 32 * ch), v);
+                // lane r holds row r, columns col0..col0+31: park it in shared memory with the 16-byte
+                // chunks XOR-swizzled by the row so that both the column-wise writes here and the
+                // row-wise reads below are bank-conflict free
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float4 f = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]),
+                                           __uint_as_float(v[4 * c4 + 3]));
+                    *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = f;
+                }
+                __syncwarp();
+                // now 8 lanes cover one 128-byte row: 4 rows per pass, 8 passes
+                const int c4 = lane & 7;
+#pragma unroll
+                for (int pass = 0; pass < 8; ++pass) {
+                    const int r = pass * 4 + (lane >> 3);
+                    float4 f = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
+                    const int i = row_base + r, j = col0 + 4 * c4;
+                    if (i < p.m && j < p.n) {
+                        float o[4] = {f.x, f.y, f.z, f.w};
+                        if (p.partial) {
+                            float* dst = p.partial + ((size_t)split * p.m + i) * p.n + j;
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj)
+                                if (j + jj < p.n) dst[jj] = o[jj];
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj)
+                                if (j + jj < p.n) o[jj] = epilogue_value(o[jj], i, j + jj, p);
+                            float* dst = p.c + (size_t)i * p.ldc + j;
+                            if (p.c_vec && j + 3 < p.n) {
+                                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                            } else {
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj)
+                                    if (j + jj < p.n) dst[jj] = o[jj];
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// sums split-K partials in a fixed order and applies the epilogue
+__global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p) {
+    const size_t total = (size_t)p.m * p.n;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        float s = 0.f;
+        for (int z = 0; z < p.splits; ++z) s += p.partial[(size_t)z * total + e];
+        const int i = (int)(e / p.n), j = (int)(e % p.n);
+        p.c[(size_t)i * p.ldc + j] = epilogue_value(s, i, j, p);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map over a row-major [rows][cols] array with leading dimension ld; box = {32 cols, box_rows}
+bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t elem[2] = {1u, 1u};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+bool g_tc_broken = false;
+unsigned long long g_tc_launches = 0;
+
+}  // namespace
+
+bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
+    if (g_tc_broken || !encode_fn()) return false;
+    if (g.m <= 0 || g.n <= 0 || g.k <= 0) return false;
+    // TMA needs 16-byte aligned bases and row pitches
+    if (((uintptr_t)g.a & 15) || ((uintptr_t)g.b & 15) || (g.lda & 3) || (g.ldb & 3)) return false;
+
+    TcParams p{};
+    p.m = g.m; p.n = g.n; p.k = g.k;
+    p.a_kmajor = !g.ta;           // A row-major [m][k]  -> K-major;  stored [k][m] -> MN-major
+    p.b_kmajor = g.tb;            // B stored [n][k]     -> K-major;  row-major [k][n] -> MN-major
+    p.c = g.c; p.ldc = g.ldc; p.epi = g.epi;
+    p.c_vec = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 4 == 0);
+    p.m_tiles = ceil_div(g.m, BM);
+    p.n_tiles = ceil_div(g.n, BN);
+    p.kblocks = ceil_div(g.k, BK);
+
+    CUtensorMap ma, mb;
+    bool ok = p.a_kmajor ? make_map(&ma, g.a, g.m, g.k, g.lda, BM) : make_map(&ma, g.a, g.k, g.m, g.lda, BK);
+    ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, BN) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK));
+    if (!ok) return false;
+
+    const int sms = rt().num_sms;
+    const long long tiles = (long long)p.m_tiles * p.n_tiles;
+    int splits = 1;
+    if (tiles < sms && p.kblocks >= 16) {
+        long long want = (sms + tiles - 1) / tiles;
+        long long maxs = p.kblocks / 8;
+        splits = (int)(want < maxs ? want : maxs);
+        if (splits < 1) splits = 1;
+        if (splits > 64) splits = 64;
+    }
+    p.kblocks_per_split = ceil_div(p.kblocks, splits);
+    splits = ceil_div(p.kblocks, p.kblocks_per_split);
+    p.splits = splits;
+    float* ws = nullptr;
+    if (splits > 1) {
+        ws = (float*)pool_alloc(kDevice, (size_t)splits * g.m * g.n * sizeof(float));
+        p.partial = ws;
+    }
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            g_tc_broken = true;
+            if (ws) pool_free(ws);
+            return false;
+        }
+        attr_set = true;
+    }
+    const long long total = tiles * splits;
+    const int grid = (int)(total < sms ? total : sms);
+    gemm_3xtf32_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, p);
+    BLA_LAUNCH_CHECK();
+    count_launch();
+    ++g_tc_launches;
+    if (ws) {
+        size_t totalc = (size_t)g.m * g.n;
+        size_t blocks = (totalc + 255) / 256;
+        size_t cap = (size_t)sms * 8;
+        if (blocks > cap) blocks = cap;
+        tc_splitk_reduce_kernel<<<(int)blocks, 256, 0, s>>>(p);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+        pool_free(ws);
+    }
+    return true;
+}
+
+}  // namespace bla
+
+extern "C" int bla_tc_available(void) {
+    bla::rt();
+    return bla::encode_fn() != nullptr && !bla::g_tc_broken;
+}
+extern "C" unsigned long long bla_tc_launch_count(void) { return bla::g_tc_launches; }

@@ -47,6 +47,10 @@ enum { BLA_GEMM_FP32 = 0,   /* FP32 FMA on the SIMT pipe: <= 1e-5 relative vs th
        BLA_GEMM_AUTO = 2 }; /* 3xTF32 for tensor-core sized problems, FP32 otherwise (default; $BLA_PATH) */
 void bla_set_gemm_path(int path);
 int bla_get_gemm_path(void);
+/* 1 when the tcgen05/TMA path is usable on this device+driver; launches of the tensor kernel so far.
+ * A GEMM whose operands are not 16-byte aligned (base or row pitch) runs on the FP32 path instead. */
+int bla_tc_available(void);
+unsigned long long bla_tc_launch_count(void);
 /* 1 (default, $BLA_QUIRKS): reproduce reference defects D2 (matrix_col_sum stride) and D5 (group norm
  * divides by the variance); 0: the mathematically intended results. */
 void bla_set_quirks(int on);

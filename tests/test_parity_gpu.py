@@ -428,3 +428,115 @@ def test_group_norm_unet_shapes_vs_oracle(bla, Cn, HW):
     b.group_norm_ddx(C.cast(b.planes(dy32), b.MatrixP), C.cast(b.planes(dx32), b.MatrixP), C.cast(b.planes(x32), b.MatrixP),
                      ptr(m32), ptr(v32), Cn, 32)
     assert rel_err(dx32, dx) <= 5 * FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# 3xTF32 tensor path (tcgen05 + TMA + TMEM): same GEMM contract, tolerance 1e-3 (north_star);
+# the measured error is asserted much tighter so that a silent 1xTF32 regression cannot hide.
+# ------------------------------------------------------------------------------------------------
+TC_TIGHT = 2e-5
+
+
+@pytest.fixture()
+def tc(bla):
+    assert bla.bla_tc_available() == 1, "tcgen05/TMA path unavailable on this device"
+    bla.bla_set_gemm_path(bla.GEMM_3XTF32)
+    yield bla
+    bla.bla_set_gemm_path(bla.GEMM_FP32)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (152, 204, 76), (256, 512, 784), (384, 1000, 256), (8, 16, 8)])
+def test_tc_gemm_layouts_vs_float64(tc, ta, tb, M, N, K):
+    b = tc
+    rng = np.random.default_rng(M + N + K + 2 * ta + tb)
+    a = rng.uniform(-0.5, 0.5, (M, K)); bm = rng.uniform(-0.5, 0.5, (K, N))
+    a_st = f32(a.T if ta else a); b_st = f32(bm.T if tb else bm)
+    want = (a_st.astype(np.float64).T if ta else a_st.astype(np.float64)) @ (b_st.astype(np.float64).T if tb else b_st.astype(np.float64))
+    out = np.full((M, N), np.nan, np.float32)
+    n0 = b.bla_tc_launch_count()
+    b.bla_gemm(ta, tb, M, N, K, ptr(a_st), a_st.shape[1], ptr(b_st), b_st.shape[1], ptr(out), N)
+    assert b.bla_tc_launch_count() == n0 + 1, "GEMM did not run on the tensor path"
+    err = rel_err(out, want)
+    assert err <= TF32X3_TOL and err <= TC_TIGHT, err
+
+
+def test_tc_gemm_epilogue_and_split_k(tc):
+    b = tc
+    rng = np.random.default_rng(21)
+    M, N, K = 136, 260, 96
+    a = f32(rng.normal(size=(M, K))); bm = f32(rng.normal(size=(K, N)))
+    bias_r = f32(rng.normal(size=M)); gate = f32(rng.normal(size=(M, N)))
+    out = np.empty((M, N), np.float32); pre = np.empty((M, N), np.float32)
+    epi = b.Epilogue(bias_r.ctypes.data, None, pre.ctypes.data, gate.ctypes.data, b.ACT_RELU, 0.5)
+    n0 = b.bla_tc_launch_count()
+    b.bla_gemm_ex(0, 0, M, N, K, ptr(a), K, ptr(bm), N, ptr(out), N, C.byref(epi))
+    assert b.bla_tc_launch_count() == n0 + 1
+    zz = 0.5 * (a.astype(np.float64) @ bm.astype(np.float64)) + bias_r.astype(np.float64)[:, None]
+    assert rel_err(pre, zz) <= TC_TIGHT
+    assert np.array_equal(out, np.maximum(pre, 0) * (gate > 0))
+    # wgrad-shaped: few tiles, long K -> split-K partials + reduce (model/mnist_nn.c:279 at B = 60k)
+    M, N, K = 128, 256, 60000
+    a = f32(rng.uniform(-1, 1, (M, K))); bt = f32(rng.uniform(-1, 1, (N, K)))
+    out = np.empty((M, N), np.float32)
+    b.bla_gemm(0, 1, M, N, K, ptr(a), K, ptr(bt), K, ptr(out), N)
+    assert rel_err(out, a.astype(np.float64) @ bt.astype(np.float64).T) <= TC_TIGHT
+
+
+def test_tc_gemm_many_tiles_persistent_loop(tc):
+    """More tiles than SMs so every CTA walks several tiles (both TMEM accumulator stages, barrier
+    phase wrap-around), device-resident, checked against the FP32 path."""
+    b = tc
+    M, N, K = 1024, 8192, 512
+    A = b.bla_matrix_device(M, K); B = b.bla_matrix_device(K, N)
+    b.bla_fill_uniform(C.cast(A.contents.data, C.c_void_p), M * K, 11, -0.5, 0.5)
+    b.bla_fill_uniform(C.cast(B.contents.data, C.c_void_p), K * N, 12, -0.5, 0.5)
+    c_tc = b.matrix_multiply(A.contents, B.contents)
+    b.bla_set_gemm_path(b.GEMM_FP32)
+    c_ref = b.matrix_multiply(A.contents, B.contents)
+    err = rel_err(b.to_numpy(c_tc), b.to_numpy(c_ref))
+    for m in (A, B, c_tc, c_ref):
+        b.free_matrix(m)
+    assert err <= TC_TIGHT, err
+
+
+def test_mlp_step_tensor_path_vs_oracle(tc):
+    """One SGD step of the MLP (model/mnist_nn.c:218-315) with every eligible GEMM on the tensor path."""
+    _mlp_step_check(tc, 2048, 1e-4)
+
+
+def test_mlp_step_fp32_path_vs_oracle(bla):
+    _mlp_step_check(bla, 1000, 1e-5)
+
+
+def _mlp_step_check(b, B, tol):
+    o64 = load_oracle(np.float64)
+    rng = np.random.default_rng(B)
+    dims = (C.c_int * 4)(784, 256, 128, 10)
+    net = b.bla_mlp_create(dims, B)
+    p32 = [f32(rng.uniform(-0.08, 0.08, s)) for s in ((256, 784), (256,), (128, 256), (128,), (10, 128), (10,))]
+    b.bla_mlp_set_params(net, *[ptr(p) for p in p32])
+    X = rng.integers(0, 256, (784, B)).astype(np.float32)
+    labels = rng.integers(0, 10, B)
+    Y = np.zeros((10, B), np.float32); Y[labels, np.arange(B)] = 1
+    stats = np.zeros(2)
+    b.bla_mlp_train_step(net, ptr(X), ptr(Y), B, B, 0, 0.02, ptr(stats))
+    got = [np.empty_like(p) for p in p32]
+    b.bla_mlp_get_params(net, *[ptr(g) for g in got])
+    probs = np.empty((10, B), np.float32)
+    b.bla_mlp_forward(net, ptr(X), B, ptr(probs))
+    b.bla_mlp_destroy(net)
+    p64 = [p.astype(np.float64) for p in p32]
+    loss = C.c_double(); correct = C.c_int()
+    o64.orc_mlp_step(dims, B, *[ptr(p) for p in p64], ptr(X.astype(np.float64)), ptr(Y.astype(np.float64)), 0.02, 1,
+                     C.byref(loss), C.byref(correct), None, 1)
+    assert abs(stats[0] - loss.value) <= 1e-4 * abs(loss.value)
+    assert int(stats[1]) == correct.value
+    for g, w in zip(got, p64):
+        assert rel_err(g, w) <= tol, rel_err(g, w)
+    # forward with the UPDATED parameters == the oracle's next forward (same argmax per sample)
+    want = np.empty((10, B))
+    o64.orc_mlp_step(dims, B, *[ptr(p) for p in p64], ptr(X.astype(np.float64)), ptr(Y.astype(np.float64)), 0.02, 1,
+                     None, None, ptr(want), 0)
+    assert rel_err(probs, want) <= 10 * tol
+    assert np.array_equal(probs.argmax(axis=0), want.argmax(axis=0))
