@@ -113,13 +113,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride
 // byte offsets (all >> 4), version 1 (Blackwell), SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B -- the only layout the tensor
+// core accepts for MN-major 32-bit operands (32-byte swizzle atoms, 4-row groups).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;   // version
-    d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 
@@ -226,9 +228,12 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         // ===================================== MMA issuer =======================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(!p.a_kmajor, !p.b_kmajor);
-            // K-major: 8-row groups 1024 B apart, k-step = 32 B inside the swizzle row.
-            // MN-major: 32-wide atoms BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO), k-step = 1024 B.
+            // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), k-step = 32 B inside the swizzle row.
+            // MN-major (SWIZZLE_128B_BASE32B): 32-wide atoms BK*128 B apart (LBO), 4-k groups 512 B apart
+            // (SBO), k-step of 8 = 1024 B.
             const uint32_t a_lbo = p.a_kmajor ? 16u : BK * 128u, b_lbo = p.b_kmajor ? 16u : BK * 128u;
+            const uint32_t a_sbo = p.a_kmajor ? 1024u : 512u, b_sbo = p.b_kmajor ? 1024u : 512u;
+            const uint32_t a_lt = p.a_kmajor ? 2u : 1u, b_lt = p.b_kmajor ? 2u : 1u;
             const uint32_t a_kstep = p.a_kmajor ? 32u : 1024u, b_kstep = p.b_kmajor ? 32u : 1024u;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -246,10 +251,10 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint64_t a_hi = make_desc(sa + ks * a_kstep, a_lbo, 1024u);
-                        const uint64_t b_hi = make_desc(sb + ks * b_kstep, b_lbo, 1024u);
-                        const uint64_t a_lo = make_desc(sa + kRawBytes + ks * a_kstep, a_lbo, 1024u);
-                        const uint64_t b_lo = make_desc(sb + kRawBytes + ks * b_kstep, b_lbo, 1024u);
+                        const uint64_t a_hi = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lt);
+                        const uint64_t b_hi = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lt);
+                        const uint64_t a_lo = make_desc(sa + kRawBytes + ks * a_kstep, a_lbo, a_sbo, a_lt);
+                        const uint64_t b_lo = make_desc(sb + kRawBytes + ks * b_kstep, b_lbo, b_sbo, b_lt);
                         umma_tf32(tmem_d, a_lo, b_hi, idesc, accumulate);
                         umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
                         umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
@@ -399,13 +404,13 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor map over a row-major [rows][cols] array with leading dimension ld; box = {32 cols, box_rows}
-bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows, bool mn_major) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
     cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     cuuint32_t elem[2] = {1u, 1u};
     CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -431,8 +436,8 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     p.kblocks = ceil_div(g.k, BK);
 
     CUtensorMap ma, mb;
-    bool ok = p.a_kmajor ? make_map(&ma, g.a, g.m, g.k, g.lda, BM) : make_map(&ma, g.a, g.k, g.m, g.lda, BK);
-    ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, BN) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK));
+    bool ok = p.a_kmajor ? make_map(&ma, g.a, g.m, g.k, g.lda, BM, false) : make_map(&ma, g.a, g.k, g.m, g.lda, BK, true);
+    ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, BN, false) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
     if (!ok) return false;
 
     const int sms = rt().num_sms;
