@@ -244,6 +244,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default=os.environ.get("BLA_BENCH_PATH", "auto"), choices=["auto", "fp32", "3xtf32"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
 
@@ -391,7 +392,7 @@ def main():
         extras = run_extras(b, torch, stream, pk)
 
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         try:
             r = time_cpu_reference(2, 1, args.cpu_budget)
             cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"], "sample": r["sample"]}
