@@ -8,13 +8,13 @@
 // accumulator; the dropped lo.lo term and the rounding of lo are O(2^-21) relative.
 //
 // Dataflow per CTA (persistent, one CTA per SM, 10 warps):
-//   warp 0      TMA producer: cp.async.bulk.tensor tiles of raw A (128 x 32) and B (32 x 256) fp32
-//               into 128B-swizzled shared memory, 2-stage ring, mbarrier complete_tx.
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles of raw A (128 x 16) and B (16 x 256) fp32
+//               into swizzled shared memory, 4-stage ring, mbarrier complete_tx.
 //   warps 6-9   splitters: read the raw tile from shared memory, write the lo tile next to it
 //               (same swizzled positions, so the split is a flat elementwise pass), then
 //               fence.proxy.async and arrive on the stage's "split" barrier.
-//   warp 1      MMA issuer (one lane): 12 tcgen05.mma.kind::tf32 128x256x8 per stage
-//               (4 k-steps x 3 products), tcgen05.commit -> frees the stage / publishes the tile.
+//   warp 1      MMA issuer (one lane): 6 tcgen05.mma.kind::tf32 128x256x8 per stage
+//               (2 k-steps x 3 products), tcgen05.commit -> frees the stage / publishes the tile.
 //   warps 2-5   epilogue: tcgen05.ld the 128 x 256 fp32 accumulator (TMEM is double-buffered, so
 //               the next tile's MMAs overlap), transpose through swizzled shared memory so that
 //               global stores / gate loads are full 128-byte rows, fused alpha / bias / ReLU /
@@ -34,20 +34,22 @@ namespace bla {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32;
-constexpr int kStages = 2;
+constexpr int BM = 128, BN = 256, BK = 16;   // BN = widest tile (TMEM stage); the tile width actually used is p.bn
+constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kThreads = 320;
-constexpr uint32_t kABytes = BM * BK * 4;               // 16 KB
-constexpr uint32_t kBBytes = BN * BK * 4;               // 32 KB
-constexpr uint32_t kRawBytes = kABytes + kBBytes;       // 48 KB  (lo tiles mirror it at +kRawBytes)
-constexpr uint32_t kStageBytes = 2 * kRawBytes;         // 96 KB
+constexpr uint32_t kABytes = BM * BK * 4;               // 8 KB
+constexpr uint32_t kBBytes = BN * BK * 4;               // 16 KB
+constexpr uint32_t kRawBytes = kABytes + kBBytes;       // 24 KB  (lo tiles mirror it at +kRawBytes)
+constexpr uint32_t kStageBytes = 2 * kRawBytes;         // 48 KB
 constexpr uint32_t kStagingBytes = 4 * 32 * 32 * 4;     // 16 KB: one 32x32 fp32 tile per epilogue warp
 constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;   // + barriers + alignment slack
 
 struct TcParams {
     int m, n, k;
     int m_tiles, n_tiles, splits, kblocks_per_split, kblocks;
+    int bn;                  // tile width: multiple of 16 (B K-major) or 32 (B MN-major), <= 256
+    uint32_t stage_tx_bytes; // bytes TMA delivers per stage
     bool a_kmajor, b_kmajor;
     float* c; int ldc;
     float* partial;          // [splits][m][n] when splits > 1
@@ -126,13 +128,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, FP32 accumulate.
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_major) {
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_major, int bn) {
     return (1u << 4)                       // c_format  = F32
            | (2u << 7)                     // a_format  = TF32
            | (2u << 10)                    // b_format  = TF32
            | ((a_mn_major ? 1u : 0u) << 15)
            | ((b_mn_major ? 1u : 0u) << 16)
-           | ((uint32_t)(BN >> 3) << 17)   // n_dim
+           | ((uint32_t)(bn >> 3) << 17)   // n_dim
            | ((uint32_t)(BM >> 4) << 24);  // m_dim
 }
 
@@ -198,26 +200,25 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int split = tile / (p.m_tiles * p.n_tiles);
                 const int mn = tile % (p.m_tiles * p.n_tiles);
-                const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
+                const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * p.bn;
                 const int kb0 = split * p.kblocks_per_split;
                 const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(bar_empty(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-                    mbar_arrive_expect_tx(bar_full(stage), kRawBytes);
+                    mbar_arrive_expect_tx(bar_full(stage), p.stage_tx_bytes);
                     const int k0 = kb * BK;
                     if (p.a_kmajor) {
-                        tma_load_2d(sa, &tma_a, k0, m0, bar_full(stage));                              // box {32 k, 128 m}
+                        tma_load_2d(sa, &tma_a, k0, m0, bar_full(stage));                              // box {16 k, 128 m}
                     } else {
 #pragma unroll
-                        for (int at = 0; at < BM / 32; ++at)                                            // box {32 m, 32 k} per atom
+                        for (int at = 0; at < BM / 32; ++at)                                            // box {32 m, 16 k} per atom
                             tma_load_2d(sa + at * (BK * 128), &tma_a, m0 + 32 * at, k0, bar_full(stage));
                     }
                     if (p.b_kmajor) {
-                        tma_load_2d(sb, &tma_b, k0, n0, bar_full(stage));                              // box {32 k, 256 n}
+                        tma_load_2d(sb, &tma_b, k0, n0, bar_full(stage));                              // box {16 k, bn n}
                     } else {
-#pragma unroll
-                        for (int at = 0; at < BN / 32; ++at)
+                        for (int at = 0; at < p.bn / 32; ++at)
                             tma_load_2d(sb + at * (BK * 128), &tma_b, n0 + 32 * at, k0, bar_full(stage));
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -227,13 +228,14 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(!p.a_kmajor, !p.b_kmajor);
-            // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), k-step = 32 B inside the swizzle row.
+            const uint32_t idesc = make_idesc(!p.a_kmajor, !p.b_kmajor, p.bn);
+            // K-major (rows of BK floats = 64 B, SWIZZLE_64B): 8-row groups 512 B apart (SBO), k-step = 32 B
+            // inside the swizzle row.
             // MN-major (SWIZZLE_128B_BASE32B): 32-wide atoms BK*128 B apart (LBO), 4-k groups 512 B apart
             // (SBO), k-step of 8 = 1024 B.
             const uint32_t a_lbo = p.a_kmajor ? 16u : BK * 128u, b_lbo = p.b_kmajor ? 16u : BK * 128u;
-            const uint32_t a_sbo = p.a_kmajor ? 1024u : 512u, b_sbo = p.b_kmajor ? 1024u : 512u;
-            const uint32_t a_lt = p.a_kmajor ? 2u : 1u, b_lt = p.b_kmajor ? 2u : 1u;
+            const uint32_t a_sbo = 512u, b_sbo = 512u;
+            const uint32_t a_lt = p.a_kmajor ? 4u : 1u, b_lt = p.b_kmajor ? 4u : 1u;
             const uint32_t a_kstep = p.a_kmajor ? 32u : 1024u, b_kstep = p.b_kmajor ? 32u : 1024u;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -305,14 +307,15 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int split = tile / (p.m_tiles * p.n_tiles);
             const int mn = tile % (p.m_tiles * p.n_tiles);
-            const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
+            const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * p.bn;
+            const int n_end = min(p.n, n0 + p.bn);
             mbar_wait(bar_acc_full(acc), acc_phase);
             tcgen05_fence_after();
             const int row_base = m0 + 32 * q;
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 const int col0 = n0 + 32 * ch;
-                if (col0 >= p.n) break;              // warp-uniform
+                if (col0 >= n_end) break;            // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + 32 * ch), v);
                 // lane r holds row r, columns col0..col0+31: park it in shared memory with the 16-byte
@@ -332,24 +335,24 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     const int r = pass * 4 + (lane >> 3);
                     float4 f = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
                     const int i = row_base + r, j = col0 + 4 * c4;
-                    if (i < p.m && j < p.n) {
+                    if (i < p.m && j < n_end) {
                         float o[4] = {f.x, f.y, f.z, f.w};
                         if (p.partial) {
                             float* dst = p.partial + ((size_t)split * p.m + i) * p.n + j;
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj)
-                                if (j + jj < p.n) dst[jj] = o[jj];
+                                if (j + jj < n_end) dst[jj] = o[jj];
                         } else {
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj)
-                                if (j + jj < p.n) o[jj] = epilogue_value(o[jj], i, j + jj, p);
+                                if (j + jj < n_end) o[jj] = epilogue_value(o[jj], i, j + jj, p);
                             float* dst = p.c + (size_t)i * p.ldc + j;
-                            if (p.c_vec && j + 3 < p.n) {
+                            if (p.c_vec && j + 3 < n_end) {
                                 *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                             } else {
 #pragma unroll
                                 for (int jj = 0; jj < 4; ++jj)
-                                    if (j + jj < p.n) dst[jj] = o[jj];
+                                    if (j + jj < n_end) dst[jj] = o[jj];
                             }
                         }
                     }
@@ -403,14 +406,16 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp32 tensor map over a row-major [rows][cols] array with leading dimension ld; box = {32 cols, box_rows}
+// 2-D fp32 tensor map over a row-major [rows][cols] array with leading dimension ld.
+//   K-major operand : box = {BK cols (64 B), box_rows}, SWIZZLE_64B
+//   MN-major operand: box = {32 cols (128 B), BK rows}, SWIZZLE_128B with 32-byte atoms
 bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows, bool mn_major) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {mn_major ? 32u : (cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t elem[2] = {1u, 1u};
     CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -434,18 +439,23 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     p.m_tiles = ceil_div(g.m, BM);
     p.n_tiles = ceil_div(g.n, BN);
     p.kblocks = ceil_div(g.k, BK);
+    // narrowest tile that still covers n with the same tile count (784 -> 4 x 208 instead of 4 x 256)
+    const int gran = p.b_kmajor ? 16 : 32;
+    p.bn = (ceil_div(g.n, p.n_tiles) + gran - 1) / gran * gran;
+    if (p.bn > BN) p.bn = BN;
+    p.stage_tx_bytes = kABytes + (uint32_t)p.bn * BK * 4;
 
     CUtensorMap ma, mb;
     bool ok = p.a_kmajor ? make_map(&ma, g.a, g.m, g.k, g.lda, BM, false) : make_map(&ma, g.a, g.k, g.m, g.lda, BK, true);
-    ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, BN, false) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
+    ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, p.bn, false) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
     if (!ok) return false;
 
     const int sms = rt().num_sms;
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     int splits = 1;
-    if (tiles < sms && p.kblocks >= 16) {
-        long long want = (sms + tiles - 1) / tiles;
-        long long maxs = p.kblocks / 8;
+    if (tiles * 2 <= sms && p.kblocks >= 32) {
+        long long want = sms / tiles;          // one wave: tiles * splits <= SMs
+        long long maxs = p.kblocks / 16;
         splits = (int)(want < maxs ? want : maxs);
         if (splits < 1) splits = 1;
         if (splits > 64) splits = 64;
