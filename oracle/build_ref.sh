@@ -72,5 +72,31 @@ $CC $CFLAGS -o "$OUT/bin/ref_mnist_nn_f64"       "$t/model/mnist_nn.c" "$t/lib/m
 sed 's/^#define SGD_BATCH_SIZE 64/#define SGD_BATCH_SIZE 512/' "$REF/model/mnist_nn.c" > "$t/model/mnist_nn_b512.c"
 $CC $CFLAGS -o "$OUT/bin/ref_mnist_nn_f64_b512"  "$t/model/mnist_nn_b512.c" "$t/lib/matrix.c" "$t/lib/csv.c" "$t/lib/mnist_csv2.c" -lm
 
+# ---- the same UNCHANGED model sources relinked against libbla.so (the drop-in demonstration) ----
+# lib/{matrix,layer,conv,norm,util}.h come from include/lib (this repo); every other header and the
+# host-I/O objects (csv, mnist_csv*, cifar10, bmp) are the reference's own.  See INTEGRATION.md.
+BLA_DIR="$HERE/../big-linear-algebra_b200"
+if [ -f "$BLA_DIR/libbla.so" ]; then
+  t="$GEN/bla"
+  mkdir -p "$t/lib" "$t/model"
+  for f in "$REF"/lib/*; do ln -s "$f" "$t/lib/$(basename "$f")"; done
+  for h in matrix.h layer.h conv.h norm.h util.h; do ln -sf "$HERE/../include/lib/$h" "$t/lib/$h"; done
+  for f in "$REF"/model/*.c "$REF"/main.c; do ln -s "$f" "$t/model/$(basename "$f")"; done
+  LINK="-L$BLA_DIR -lbla -Wl,-rpath,\$ORIGIN/../../../big-linear-algebra_b200 -lm"
+  HOSTFLAGS="-O2 -std=c99 -w"
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_main"           "$t/model/main.c" "$t/lib/csv.c" -I"$t" $LINK
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_my_first_model" "$t/model/my_first_model.c" "$t/lib/csv.c" $LINK
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_mnist_hinge"    "$t/model/mnist_hinge.c" "$t/lib/csv.c" "$t/lib/mnist_csv.c" $LINK
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_mnist_nn"       "$t/model/mnist_nn.c" "$t/lib/csv.c" "$t/lib/mnist_csv2.c" $LINK
+  sed 's/^#define SGD_BATCH_SIZE 64/#define SGD_BATCH_SIZE 512/' "$REF/model/mnist_nn.c" > "$t/model/mnist_nn_b512.c"
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_mnist_nn_b512"  "$t/model/mnist_nn_b512.c" "$t/lib/csv.c" "$t/lib/mnist_csv2.c" $LINK
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_cifar_unet"     "$t/model/cifar_unet.c" "$t/lib/csv.c" "$t/lib/cifar10.c" "$t/lib/bmp.c" $LINK
+  # the reference's own U-Net build (double, as shipped) for comparison runs
+  $CC $CFLAGS -o "$OUT/bin/ref_cifar_unet_f64" "$GEN/f64/model/cifar_unet.c" "$GEN/f64/lib/matrix.c" "$GEN/f64/lib/csv.c" \
+      "$GEN/f64/lib/cifar10.c" "$GEN/f64/lib/bmp.c" "$GEN/f64/lib/conv.c" "$GEN/f64/lib/norm.c" "$GEN/f64/lib/util.c" -lm
+else
+  echo "build_ref: $BLA_DIR/libbla.so not built yet -- skipping the relinked programs" >&2
+fi
+
 rm -rf "$GEN"
 echo "build_ref: built $(ls "$OUT"/*.so | wc -l) oracle libraries and $(ls "$OUT/bin" | wc -l) reference programs in $OUT"
