@@ -258,8 +258,10 @@ def main():
         raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
     args.warmup = max(args.warmup, 3)
 
+    import importlib
     import torch
     import bla_b200 as b
+    dp = importlib.import_module("big-linear-algebra_b200.dp")
     if b.bla_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the big-linear-algebra B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -273,15 +275,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        idbuf = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            raw = (C.c_ubyte * 128)()
-            b.bla_comm_unique_id(raw)
-            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
-        idbuf = idbuf.cuda()
-        dist.broadcast(idbuf, 0)
-        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
-        b.bla_comm_init(raw, rank, world)
+        b.bla_comm_init(dp.exchange_unique_id(b, dist, rank, device="cuda"), rank, world)
 
     def barrier():
         if dist:
@@ -289,10 +283,7 @@ def main():
         torch.cuda.synchronize()
 
     Bg = GLOBAL_BATCH
-    Bl = Bg // world
-    c0 = rank * Bl
-    if rank == world - 1:
-        Bl = Bg - c0
+    c0, Bl = dp.shard_columns(Bg, world, rank)
     dims = (C.c_int * 4)(*DIMS)
     net = b.bla_mlp_create(dims, Bl)
     b.bla_mlp_init_params(net, 42)

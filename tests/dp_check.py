@@ -1,0 +1,68 @@
+"""Run under torchrun with >= 2 GPUs: 3 data-parallel SGD steps of the MLP (one process per GPU, NCCL all-reduce
+inside bla_mlp_train_step) against the f64 oracle's full-batch steps.  Prints DP_CHECK_OK on rank 0."""
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import bla_b200 as b
+    from helpers import load_oracle, ptr, rel_err
+    dp = importlib.import_module("big-linear-algebra_b200.dp")
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    b.bla_init(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    b.bla_comm_init(dp.exchange_unique_id(b, dist, rank, device="cuda"), rank, world)
+    path = {"fp32": b.GEMM_FP32, "3xtf32": b.GEMM_3XTF32}[os.environ.get("DP_PATH", "fp32")]
+    b.bla_set_gemm_path(path)
+    B, steps = int(os.environ.get("DP_BATCH", "2000")), 3
+    dims = (C.c_int * 4)(784, 256, 128, 10)
+    rng = np.random.default_rng(5)                             # identical on every rank
+    p32 = [np.ascontiguousarray(rng.uniform(-0.08, 0.08, s), np.float32) for s in ((256, 784), (256,), (128, 256), (128,), (10, 128), (10,))]
+    off, cnt = dp.shard_columns(B, world, rank)
+    net = b.bla_mlp_create(dims, cnt)
+    b.bla_mlp_set_params(net, *[ptr(p) for p in p32])
+    p64 = [p.astype(np.float64) for p in p32]
+    o64 = load_oracle(np.float64)
+    ok = True
+    for s in range(steps):
+        X = rng.integers(0, 256, (784, B)).astype(np.float32)
+        labels = rng.integers(0, 10, B)
+        Y = np.zeros((10, B), np.float32); Y[labels, np.arange(B)] = 1
+        Xl, Yl = np.ascontiguousarray(X[:, off:off + cnt]), np.ascontiguousarray(Y[:, off:off + cnt])
+        stats = np.zeros(2)
+        b.bla_mlp_train_step(net, ptr(Xl), ptr(Yl), cnt, B, off, 0.02, ptr(stats))
+        if rank == 0:
+            loss = C.c_double(); correct = C.c_int()
+            o64.orc_mlp_step(dims, B, *[ptr(p) for p in p64], ptr(X.astype(np.float64)), ptr(Y.astype(np.float64)), 0.02, 1,
+                             C.byref(loss), C.byref(correct), None, 1)
+            ok &= abs(stats[0] - loss.value) <= 1e-4 * abs(loss.value) and int(stats[1]) == correct.value
+    got = [np.empty_like(p) for p in p32]
+    b.bla_mlp_get_params(net, *[ptr(g) for g in got])
+    # every rank must hold identical parameters (same all-reduced gradient, same update)
+    flat = torch.from_numpy(np.concatenate([g.ravel() for g in got])).cuda()
+    ref = flat.clone(); dist.broadcast(ref, 0)
+    same = bool(torch.equal(flat, ref))
+    gathered = [torch.zeros(1, device="cuda") for _ in range(world)]
+    dist.all_gather(gathered, torch.tensor([1.0 if same else 0.0], device="cuda"))
+    if rank == 0:
+        tol = 1e-5 if path == b.GEMM_FP32 else 1e-4
+        errs = [rel_err(g, w) for g, w in zip(got, p64)]
+        ok &= all(e <= tol * steps for e in errs) and all(t.item() == 1.0 for t in gathered)
+        print("DP_CHECK_OK" if ok else "DP_CHECK_FAIL", "world", world, "errs", ["%.2e" % e for e in errs], flush=True)
+    b.bla_mlp_destroy(net)
+    b.bla_comm_destroy()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
