@@ -137,7 +137,10 @@ def test_mnist_nn_loss_curve_and_checkpoint_match(tmp_path):
     for f in ("weights_1", "weights_2", "weights_3", "biases_1", "biases_2", "biases_3"):
         p = f"data/mnist_nn/{f}.csv"
         # the checkpoint is "%f" text (lib/csv.c:62): one unit of the 6th decimal is the resolution
-        assert np.allclose(read_csv(os.path.join(rb, p)), read_csv(os.path.join(ra, p)), rtol=1e-4, atol=2.5e-6), f
+        got_v, want_v = read_csv(os.path.join(rb, p)), read_csv(os.path.join(ra, p))
+        # final weights norm-wise <= 1e-5 * steps (9 SGD steps here); element-wise a few units of
+        # the "%f" text resolution
+        assert rel_err(got_v, want_v) <= 9e-5 and np.abs(got_v - want_v).max() <= 1e-5, (f, float(np.abs(got_v - want_v).max()), rel_err(got_v, want_v))
     hits = lambda s: re.findall(r"Got (\d+) correct", s)
     assert hits(run("bla_mnist_nn", rb, "run", "200")) == hits(run("ref_mnist_nn_f64", ra, "run", "200"))
     # the shipped B = 64 build must also train to completion behind the unchanged API
