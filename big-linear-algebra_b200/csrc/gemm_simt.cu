@@ -174,6 +174,31 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_simt_kernel(const SimtParams
     }
 
     // ---- store ----
+    // The relu' gate is read for the whole micro-tile before the first store: the output may alias
+    // the gate as far as the compiler knows, and interleaved load/store pairs would each wait a
+    // full DRAM round trip.
+    const bool early_gate = p.epi.gate && !p.partial && !p.epi.bias_rows && !p.epi.bias_cols && !p.epi.pre_activation &&
+                            p.epi.activation == BLA_ACT_IDENTITY;   // the dgrad case: gate commutes with alpha
+    if (early_gate) {
+#pragma unroll
+        for (int gi = 0; gi < GM; ++gi)
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                const int i = m0 + gi * (BM / GM) + ty * 4 + ii;
+#pragma unroll
+                for (int gj = 0; gj < GN; ++gj) {
+                    const int j = n0 + gj * (BN / GN) + tx * 4;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        float gv = 1.f;
+                        if (i < p.m && j + jj < p.n) gv = __ldg(p.epi.gate + (size_t)i * p.ldc + j + jj);
+                        if (!(gv > 0.f)) acc[4 * gi + ii][4 * gj + jj] = 0.f;
+                    }
+                }
+            }
+    }
+    SimtParams q = p;
+    if (early_gate) q.epi.gate = nullptr;   // already applied: a zeroed accumulator stays zero through alpha
 #pragma unroll
     for (int gi = 0; gi < GM; ++gi)
 #pragma unroll
@@ -195,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_simt_kernel(const SimtParams
                 } else {
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj)
-                        if (j + jj < p.n) v[jj] = epilogue_value(v[jj], i, j + jj, p);
+                        if (j + jj < p.n) v[jj] = epilogue_value(v[jj], i, j + jj, q);
                     float* dst = p.c + (size_t)i * p.ldc + j;
                     if (p.c_vec && j + 3 < p.n) {
                         *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);

@@ -84,6 +84,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
+// L2 prefetch of a tile that the TMA will load a few k-blocks later: turns the DRAM latency of
+// streaming operands into an L2 hit for the shared-memory pipeline.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -196,33 +201,58 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0) {
+            // two cursors over this CTA's (tile, k-block) sequence: `cur` feeds shared memory, `ahead`
+            // runs kPrefetchDistance k-blocks in front of it and only warms L2
+            struct Cursor { int tile, kb, kb1, m0, n0; bool valid; };
+            auto open_tile = [&](Cursor& c) {
+                c.valid = c.tile < total_tiles;
+                if (!c.valid) return;
+                const int split = c.tile / (p.m_tiles * p.n_tiles);
+                const int mn = c.tile % (p.m_tiles * p.n_tiles);
+                c.m0 = (mn % p.m_tiles) * BM;
+                c.n0 = (mn / p.m_tiles) * p.bn;
+                c.kb = split * p.kblocks_per_split;
+                c.kb1 = min(p.kblocks, c.kb + p.kblocks_per_split);
+            };
+            auto advance = [&](Cursor& c) {
+                if (++c.kb >= c.kb1) { c.tile += gridDim.x; open_tile(c); }
+            };
+            auto prefetch = [&](const Cursor& c) {
+                const int k0 = c.kb * BK;
+                if (p.a_kmajor) tma_prefetch_2d(&tma_a, k0, c.m0);
+                else
+                    for (int at = 0; at < BM / 32; ++at) tma_prefetch_2d(&tma_a, c.m0 + 32 * at, k0);
+                if (p.b_kmajor) tma_prefetch_2d(&tma_b, k0, c.n0);
+                else
+                    for (int at = 0; at < p.bn / 32; ++at) tma_prefetch_2d(&tma_b, c.n0 + 32 * at, k0);
+            };
+            constexpr int kPrefetchDistance = 12;
+            Cursor cur{(int)blockIdx.x, 0, 0, 0, 0, false}, ahead{(int)blockIdx.x, 0, 0, 0, 0, false};
+            open_tile(cur);
+            open_tile(ahead);
+            for (int i = 0; i < kPrefetchDistance && ahead.valid; ++i) { prefetch(ahead); advance(ahead); }
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int split = tile / (p.m_tiles * p.n_tiles);
-                const int mn = tile % (p.m_tiles * p.n_tiles);
-                const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * p.bn;
-                const int kb0 = split * p.kblocks_per_split;
-                const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(bar_empty(stage), phase ^ 1);
-                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-                    mbar_arrive_expect_tx(bar_full(stage), p.stage_tx_bytes);
-                    const int k0 = kb * BK;
-                    if (p.a_kmajor) {
-                        tma_load_2d(sa, &tma_a, k0, m0, bar_full(stage));                              // box {16 k, 128 m}
-                    } else {
+            while (cur.valid) {
+                mbar_wait(bar_empty(stage), phase ^ 1);
+                const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                mbar_arrive_expect_tx(bar_full(stage), p.stage_tx_bytes);
+                const int k0 = cur.kb * BK, m0 = cur.m0, n0 = cur.n0;
+                if (p.a_kmajor) {
+                    tma_load_2d(sa, &tma_a, k0, m0, bar_full(stage));                              // box {16 k, 128 m}
+                } else {
 #pragma unroll
-                        for (int at = 0; at < BM / 32; ++at)                                            // box {32 m, 16 k} per atom
-                            tma_load_2d(sa + at * (BK * 128), &tma_a, m0 + 32 * at, k0, bar_full(stage));
-                    }
-                    if (p.b_kmajor) {
-                        tma_load_2d(sb, &tma_b, k0, n0, bar_full(stage));                              // box {16 k, bn n}
-                    } else {
-                        for (int at = 0; at < p.bn / 32; ++at)
-                            tma_load_2d(sb + at * (BK * 128), &tma_b, n0 + 32 * at, k0, bar_full(stage));
-                    }
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    for (int at = 0; at < BM / 32; ++at)                                            // box {32 m, 16 k} per atom
+                        tma_load_2d(sa + at * (BK * 128), &tma_a, m0 + 32 * at, k0, bar_full(stage));
                 }
+                if (p.b_kmajor) {
+                    tma_load_2d(sb, &tma_b, k0, n0, bar_full(stage));                              // box {16 k, bn n}
+                } else {
+                    for (int at = 0; at < p.bn / 32; ++at)
+                        tma_load_2d(sb + at * (BK * 128), &tma_b, n0 + 32 * at, k0, bar_full(stage));
+                }
+                if (ahead.valid) { prefetch(ahead); advance(ahead); }
+                advance(cur);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -328,26 +358,62 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = f;
                 }
                 __syncwarp();
-                // now 8 lanes cover one 128-byte row: 4 rows per pass, 8 passes
+                // now 8 lanes cover one 128-byte row: 4 rows per pass, 8 passes.  All shared-memory reads
+                // and all gate loads are issued before the first global store: the output may alias the
+                // gate as far as the compiler knows, and interleaving would serialise on DRAM latency.
                 const int c4 = lane & 7;
+                const int j = col0 + 4 * c4;
+                float4 f[8], gt[8];
 #pragma unroll
                 for (int pass = 0; pass < 8; ++pass) {
                     const int r = pass * 4 + (lane >> 3);
-                    float4 f = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
-                    const int i = row_base + r, j = col0 + 4 * c4;
+                    f[pass] = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
+                }
+                const bool full4 = j + 3 < n_end;
+                if (p.epi.gate && !p.partial) {
+#pragma unroll
+                    for (int pass = 0; pass < 8; ++pass) {
+                        const int i = row_base + pass * 4 + (lane >> 3);
+                        gt[pass] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (i < p.m && j < n_end) {
+                            const float* gp = p.epi.gate + (size_t)i * p.ldc + j;
+                            if (p.c_vec && full4) {
+                                gt[pass] = __ldg(reinterpret_cast<const float4*>(gp));
+                            } else {
+                                gt[pass].x = gp[0];
+                                if (j + 1 < n_end) gt[pass].y = gp[1];
+                                if (j + 2 < n_end) gt[pass].z = gp[2];
+                                if (j + 3 < n_end) gt[pass].w = gp[3];
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int pass = 0; pass < 8; ++pass) {
+                    const int i = row_base + pass * 4 + (lane >> 3);
                     if (i < p.m && j < n_end) {
-                        float o[4] = {f.x, f.y, f.z, f.w};
+                        float o[4] = {f[pass].x, f[pass].y, f[pass].z, f[pass].w};
                         if (p.partial) {
                             float* dst = p.partial + ((size_t)split * p.m + i) * p.n + j;
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj)
                                 if (j + jj < n_end) dst[jj] = o[jj];
                         } else {
+                            const float g4[4] = {gt[pass].x, gt[pass].y, gt[pass].z, gt[pass].w};
+                            const float brow = p.epi.bias_rows ? p.epi.bias_rows[i] : 0.f;
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj)
-                                if (j + jj < n_end) o[jj] = epilogue_value(o[jj], i, j + jj, p);
+                            for (int jj = 0; jj < 4; ++jj) {
+                                float v = o[jj];
+                                if (p.epi.alpha != 0.f) v *= p.epi.alpha;
+                                v += brow;
+                                if (p.epi.bias_cols && j + jj < n_end) v += p.epi.bias_cols[j + jj];
+                                if (p.epi.pre_activation && j + jj < n_end) p.epi.pre_activation[(size_t)i * p.ldc + j + jj] = v;
+                                if (p.epi.activation == BLA_ACT_RELU) v = v < 0.f ? 0.f : v;
+                                if (p.epi.gate) v = g4[jj] > 0.f ? v : 0.f;
+                                o[jj] = v;
+                            }
                             float* dst = p.c + (size_t)i * p.ldc + j;
-                            if (p.c_vec && j + 3 < n_end) {
+                            if (p.c_vec && full4) {
                                 *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                             } else {
 #pragma unroll
@@ -439,10 +505,25 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     p.m_tiles = ceil_div(g.m, BM);
     p.n_tiles = ceil_div(g.n, BN);
     p.kblocks = ceil_div(g.k, BK);
-    // narrowest tile that still covers n with the same tile count (784 -> 4 x 208 instead of 4 x 256)
+    // Tile width: among the legal UMMA widths pick the one with the least (waves x width) so that the
+    // last wave of the persistent grid is not mostly idle (470 tiles on 148 SMs = 4 waves at width 256,
+    // but also 4 waves at width 224), then shrink it to the narrowest width with the same tile count
+    // (784 columns -> 4 x 208 instead of 4 x 256).
     const int gran = p.b_kmajor ? 16 : 32;
-    p.bn = (ceil_div(g.n, p.n_tiles) + gran - 1) / gran * gran;
-    if (p.bn > BN) p.bn = BN;
+    {
+        const int sms_ = rt().num_sms;
+        long long best_cost = -1;
+        int best_bn = BN;
+        for (int bn = BN; bn >= 128; bn -= gran) {
+            const long long tiles_ = (long long)p.m_tiles * ceil_div(g.n, bn);
+            const long long waves = (tiles_ + sms_ - 1) / sms_;
+            const long long cost = waves * (bn + 24);     // + ~24 columns' worth of per-tile fixed cost
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
+        }
+        p.n_tiles = ceil_div(g.n, best_bn);
+        p.bn = (ceil_div(g.n, p.n_tiles) + gran - 1) / gran * gran;
+        if (p.bn > BN) p.bn = BN;
+    }
     p.stage_tx_bytes = kABytes + (uint32_t)p.bn * BK * 4;
 
     CUtensorMap ma, mb;

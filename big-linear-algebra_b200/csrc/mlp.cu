@@ -36,6 +36,8 @@ struct bla_mlp {
     unsigned char* x_u8;
     float *a1, *a2, *z3, *dz2, *dz1;      // [n1 x B] [n2 x B] [n3 x B] [n2 x B] [n1 x B]
     double* stats;                        // {loss_sum, num_correct} on the device
+    float* head_partial;                  // [ctas][n3][n2] partial dW3 of the skinny output layer
+    int head_ctas;
 };
 
 namespace {
@@ -52,10 +54,23 @@ __device__ __forceinline__ float warp_sum(float v) {
 // [rows x Bg] matrix of which this process holds columns [c0, c0 + Bl).
 //   quirk: out[i] = sum of the Bg flat elements starting at i*rows  (two row segments)
 //   else : out[i] = sum of row i
-// One CTA per output element; elements of other shards contribute through the all-reduce.
-__global__ void __launch_bounds__(kThreads) bias_grad_kernel(const float* __restrict__ dz, int rows, int Bl, long long Bg, int c0,
-                                                             int quirk, float* out) {
-    __shared__ float sh[kThreads / 32];
+// One 1024-thread CTA per output element, 4 independent loads in flight per thread; elements of
+// other shards contribute through the all-reduce.
+constexpr int kBiasThreads = 1024;
+
+__device__ __forceinline__ float segment_sum(const float* __restrict__ p, long long n) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    long long c = threadIdx.x;
+    for (; c + 3 * kBiasThreads < n; c += 4 * kBiasThreads) {
+        a0 += p[c]; a1 += p[c + kBiasThreads]; a2 += p[c + 2 * kBiasThreads]; a3 += p[c + 3 * kBiasThreads];
+    }
+    for (; c < n; c += kBiasThreads) a0 += p[c];
+    return (a0 + a1) + (a2 + a3);
+}
+
+__global__ void __launch_bounds__(kBiasThreads) bias_grad_kernel(const float* __restrict__ dz, int rows, int Bl, long long Bg, int c0,
+                                                                 int quirk, float* out) {
+    __shared__ float sh[kBiasThreads / 32];
     const int i = blockIdx.x;
     float acc = 0.f;
     if (quirk) {
@@ -63,23 +78,186 @@ __global__ void __launch_bounds__(kThreads) bias_grad_kernel(const float* __rest
         const long long r0 = start / Bg, s = start % Bg;
         // segment 1: row r0, global columns [s, Bg)      segment 2: row r0 + 1, global columns [0, s)
         if (r0 < rows) {
-            long long lo = s > c0 ? s : c0;
-            for (long long c = lo + threadIdx.x; c < (long long)c0 + Bl; c += kThreads) acc += dz[r0 * Bl + (c - c0)];
+            const long long lo = s > c0 ? s : c0, hi = (long long)c0 + Bl;
+            if (lo < hi) acc += segment_sum(dz + r0 * Bl + (lo - c0), hi - lo);
         }
         if (r0 + 1 < rows) {
-            long long hi = s < (long long)c0 + Bl ? s : (long long)c0 + Bl;
-            for (long long c = c0 + threadIdx.x; c < hi; c += kThreads) acc += dz[(r0 + 1) * Bl + (c - c0)];
+            const long long hi = s < (long long)c0 + Bl ? s : (long long)c0 + Bl;
+            if (c0 < hi) acc += segment_sum(dz + (r0 + 1) * Bl, hi - c0);
         }
     } else {
-        for (int c = threadIdx.x; c < Bl; c += kThreads) acc += dz[(size_t)i * Bl + c];
+        acc = segment_sum(dz + (size_t)i * Bl, Bl);
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x < 32) {
-        float t = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.f;
+        float t = threadIdx.x < kBiasThreads / 32 ? sh[threadIdx.x] : 0.f;
         t = warp_sum(t);
         if (threadIdx.x == 0) out[i] = t;
+    }
+}
+
+// ---- the skinny output layer (classes <= 16): three fused kernels instead of three padded GEMMs -------
+// All three stream the [hidden x B] activation matrix once with coalesced rows; the tiny weight
+// matrix lives in shared memory and is read as broadcasts.
+constexpr int kMaxClasses = 16;
+
+// logits = W3 . A2 + b3 (model/mnist_nn.c:231-232), then per column softmax, argmax hit, the reference's
+// flat-slice cross-entropy and dZ3 = (p - y) * scale (:234-268) -- one thread per sample column.
+template <int NC>
+__global__ void __launch_bounds__(256) head_forward_kernel(const float* __restrict__ W3, const float* __restrict__ b3,
+                                                           const float* __restrict__ A2, const float* __restrict__ Y, int hidden, int B,
+                                                           float* dz, float* probs, float scale, double* stats) {
+    extern __shared__ float w_s[];   // [hidden][NC]  (transposed so one k gives NC consecutive floats)
+    for (int e = threadIdx.x; e < hidden * NC; e += 256) {
+        const int k = e / NC, r = e % NC;
+        w_s[e] = W3[(size_t)r * hidden + k];
+    }
+    __syncthreads();
+    double loss = 0.0;
+    int correct = 0;
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < B; c += gridDim.x * 256) {
+        float acc[NC];
+#pragma unroll
+        for (int r = 0; r < NC; ++r) acc[r] = 0.f;
+        int k = 0;
+        for (; k + 8 <= hidden; k += 8) {
+            float a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = A2[(size_t)(k + u) * B + c];     // 8 coalesced rows in flight
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int r = 0; r < NC; ++r) acc[r] = fmaf(w_s[(k + u) * NC + r], a[u], acc[r]);
+        }
+        for (; k < hidden; ++k) {
+            const float a = A2[(size_t)k * B + c];
+#pragma unroll
+            for (int r = 0; r < NC; ++r) acc[r] = fmaf(w_s[k * NC + r], a, acc[r]);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) { acc[r] += b3[r]; mx = fmaxf(mx, acc[r]); }
+        float tot = 0.f;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) { acc[r] = expf(acc[r] - mx); tot += acc[r]; }
+        int pred = 0;
+        float best = 0.f, l = 0.f;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+            const size_t at = (size_t)r * B + c;
+            const float pr = acc[r] / tot;
+            if (probs) probs[at] = pr;
+            if (Y) {
+                const float y = Y[at];
+                if (pr > best) { best = pr; pred = r; }
+                l += -1.f * (y * logf(pr + 1e-15f));
+                dz[at] = (pr + (-1.0f) * y) * scale;
+            }
+        }
+        if (Y && Y[(size_t)pred * B + c] == 1.f) ++correct;
+        loss += (double)l;
+    }
+    // block reduction of the two statistics
+    __shared__ double red[2][8];
+    double cv = (double)correct;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { loss += __shfl_xor_sync(0xffffffffu, loss, o); cv += __shfl_xor_sync(0xffffffffu, cv, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = loss; red[1][threadIdx.x >> 5] = cv; }
+    __syncthreads();
+    if (threadIdx.x == 0 && stats) {
+        double tl = 0.0, tc = 0.0;
+        for (int w = 0; w < 8; ++w) { tl += red[0][w]; tc += red[1][w]; }
+        atomicAdd(&stats[0], tl);
+        atomicAdd(&stats[1], tc);
+    }
+}
+
+// dW3 partials: each CTA owns a contiguous range of sample columns and produces a full [NC x hidden]
+// partial sum (thread k = one hidden unit); a second launch adds the partials in a fixed order.
+template <int NC>
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ A2, int hidden, int B,
+                                                         int cols_per_cta, float* partial) {
+    __shared__ float a_s[256][33];          // [hidden unit][column in step]
+    __shared__ __align__(16) float d_s[32][NC];   // [column in step][class]
+    const int k = threadIdx.x;
+    const int cbeg = blockIdx.x * cols_per_cta;
+    const int cend = min(B, cbeg + cols_per_cta);
+    float acc[NC];
+#pragma unroll
+    for (int r = 0; r < NC; ++r) acc[r] = 0.f;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        // rows of A2 (hidden units) are read 32 columns = 128 bytes at a time by one warp each
+        for (int row = wrp; row < hidden; row += 8) {
+            const int c = c0 + lane;
+            a_s[row][lane] = c < cend ? A2[(size_t)row * B + c] : 0.f;
+        }
+        for (int e = threadIdx.x; e < 32 * NC; e += 256) {
+            const int cc = e % 32, r = e / 32;
+            const int c = c0 + cc;
+            d_s[cc][r] = c < cend ? dz[(size_t)r * B + c] : 0.f;
+        }
+        __syncthreads();
+        if (k < hidden) {
+#pragma unroll 8
+            for (int cc = 0; cc < 32; ++cc) {
+                const float a = a_s[k][cc];
+#pragma unroll
+                for (int r = 0; r < NC; ++r) acc[r] = fmaf(d_s[cc][r], a, acc[r]);
+            }
+        }
+        __syncthreads();
+    }
+    if (k < hidden) {
+#pragma unroll
+        for (int r = 0; r < NC; ++r) partial[((size_t)blockIdx.x * NC + r) * hidden + k] = acc[r];
+    }
+}
+
+__global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int count, float* out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * count + e];
+    out[e] = s;
+}
+
+// dZ2 = (A2 > 0) (.) (W3^T . dZ3)  (model/mnist_nn.c:273-278): a thread owns 4 sample columns (float4) and
+// walks the hidden units; W3 is read from shared memory as broadcasts.
+template <int NC>
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ W3, const float* __restrict__ dz,
+                                                         const float* __restrict__ A2, int hidden, int B, float* out) {
+    extern __shared__ float w_s[];   // [hidden][NC]
+    for (int e = threadIdx.x; e < hidden * NC; e += 256) {
+        const int k = e / NC, r = e % NC;
+        w_s[e] = W3[(size_t)r * hidden + k];
+    }
+    __syncthreads();
+    const int B4 = B >> 2;
+    for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < B4; c4 += gridDim.x * 256) {
+        float4 d[NC];
+#pragma unroll
+        for (int r = 0; r < NC; ++r) d[r] = *reinterpret_cast<const float4*>(dz + (size_t)r * B + 4 * c4);
+        for (int k0 = 0; k0 < hidden; k0 += 4) {
+            float4 g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g[u] = *reinterpret_cast<const float4*>(A2 + (size_t)(k0 + u) * B + 4 * c4);   // hidden % 4 == 0
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < NC; ++r) {
+                    const float w = w_s[(k0 + u) * NC + r];
+                    acc.x = fmaf(w, d[r].x, acc.x); acc.y = fmaf(w, d[r].y, acc.y);
+                    acc.z = fmaf(w, d[r].z, acc.z); acc.w = fmaf(w, d[r].w, acc.w);
+                }
+                acc.x = g[u].x > 0.f ? acc.x : 0.f; acc.y = g[u].y > 0.f ? acc.y : 0.f;
+                acc.z = g[u].z > 0.f ? acc.z : 0.f; acc.w = g[u].w > 0.f ? acc.w : 0.f;
+                *reinterpret_cast<float4*>(out + (size_t)(k0 + u) * B + 4 * c4) = acc;
+            }
+        }
     }
 }
 
@@ -108,7 +286,36 @@ const float* resident(const float* p, float* staging, size_t n, cudaStream_t s) 
     return staging;
 }
 
-void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s) {
+bool skinny_head(const bla_mlp* m, int B) {
+    return m->n[3] <= kMaxClasses && m->n[2] <= 256 && m->n[2] % 4 == 0 && B % 4 == 0;
+}
+
+#define BLA_DISPATCH_NC(nc, ...)                                                        \
+    switch (nc) {                                                                       \
+        case 1: { constexpr int NC = 1; __VA_ARGS__; } break;   case 2: { constexpr int NC = 2; __VA_ARGS__; } break;     \
+        case 3: { constexpr int NC = 3; __VA_ARGS__; } break;   case 4: { constexpr int NC = 4; __VA_ARGS__; } break;     \
+        case 5: { constexpr int NC = 5; __VA_ARGS__; } break;   case 6: { constexpr int NC = 6; __VA_ARGS__; } break;     \
+        case 7: { constexpr int NC = 7; __VA_ARGS__; } break;   case 8: { constexpr int NC = 8; __VA_ARGS__; } break;     \
+        case 9: { constexpr int NC = 9; __VA_ARGS__; } break;   case 10: { constexpr int NC = 10; __VA_ARGS__; } break;   \
+        case 11: { constexpr int NC = 11; __VA_ARGS__; } break; case 12: { constexpr int NC = 12; __VA_ARGS__; } break;   \
+        case 13: { constexpr int NC = 13; __VA_ARGS__; } break; case 14: { constexpr int NC = 14; __VA_ARGS__; } break;   \
+        case 15: { constexpr int NC = 15; __VA_ARGS__; } break; default: { constexpr int NC = 16; __VA_ARGS__; } break;   \
+    }
+
+// output layer + softmax (+ loss / accuracy / dZ3 when y is given), one kernel
+void head_forward(bla_mlp* m, const float* y, int B, float* dz, float* probs, cudaStream_t s) {
+    int blocks = ceil_div(B, 256);
+    const int cap = rt().num_sms * 4;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (size_t)m->n[2] * m->n[3] * sizeof(float);
+    BLA_DISPATCH_NC(m->n[3], head_forward_kernel<NC><<<blocks, 256, smem, s>>>(m->params + m->off_w[2], m->params + m->off_b[2], m->a2, y,
+                                                                                  m->n[2], B, dz, probs, (float)(1.0 / (double)m->n[0]),
+                                                                                  y ? m->stats : nullptr));
+    BLA_LAUNCH_CHECK();
+    count_launch();
+}
+
+void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s, bool with_head = true) {
     // Z1 = W1.(X/255) + b1 ; A1 = relu(Z1)          model/mnist_nn.c:218-224
     GemmArgs g{};
     g.m = m->n[1]; g.n = B; g.k = m->n[0];
@@ -121,6 +328,7 @@ void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s) {
     g.a = W(m, 1); g.lda = m->n[1]; g.b = m->a1; g.ldb = B; g.c = m->a2; g.ldc = B;
     g.epi.bias_rows = Bv(m, 1); g.epi.activation = BLA_ACT_RELU;
     gemm(g, s);
+    if (!with_head) return;
     // Z3 = W3.A2 + b3                                 :231-232
     g = GemmArgs{};
     g.m = m->n[3]; g.n = B; g.k = m->n[2];
@@ -133,9 +341,11 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
     if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
     cudaStream_t s = rt().stream;
     const int quirk = rt().quirks;
-    forward(m, x, x_scale, B, s);
+    const bool skinny = skinny_head(m, B);
+    forward(m, x, x_scale, B, s, !skinny);
     // A3 = softmax(Z3); loss / accuracy; dZ3 = (A3 - Y) / 784 (in place over Z3)      :234-268
-    k_softmax_xent(m->z3, y, m->n[3], B, nullptr, m->z3, (float)(1.0 / (double)m->n[0]), m->stats, s);
+    if (skinny) head_forward(m, y, B, m->z3, nullptr, s);
+    else k_softmax_xent(m->z3, y, m->n[3], B, nullptr, m->z3, (float)(1.0 / (double)m->n[0]), m->stats, s);
     const float* dz3 = m->z3;
 
     auto wgrad = [&](int l, const float* dz, const float* act_prev, float alpha) {   // dW_l = dZ_l . A_{l-1}^T
@@ -145,7 +355,7 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
         g.c = dW(m, l); g.ldc = m->n[l];
         g.epi.alpha = alpha;
         gemm(g, s);
-        bias_grad_kernel<<<m->n[l + 1], kThreads, 0, s>>>(dz, m->n[l + 1], B, Bg, c0, quirk, dB(m, l));   // :271,:282,:293
+        bias_grad_kernel<<<m->n[l + 1], kBiasThreads, 0, s>>>(dz, m->n[l + 1], B, Bg, c0, quirk, dB(m, l));   // :271,:282,:293
         BLA_LAUNCH_CHECK();
         count_launch();
     };
@@ -157,8 +367,28 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
         g.epi.gate = gate;   // A > 0  <=>  Z > 0
         gemm(g, s);
     };
-    wgrad(2, dz3, m->a2, 0.f);            // :266-271
-    dgrad(2, dz3, m->a2, m->dz2);         // :273-278
+    if (skinny) {
+        const int n2 = m->n[2], n3 = m->n[3];
+        int ctas = m->head_ctas;
+        int cols = (ceil_div(B, ctas) + 31) / 32 * 32;
+        ctas = ceil_div(B, cols);
+        BLA_DISPATCH_NC(n3, head_wgrad_kernel<NC><<<ctas, 256, 0, s>>>(dz3, m->a2, n2, B, cols, m->head_partial));       // :266-270
+        BLA_LAUNCH_CHECK();
+        head_wgrad_reduce_kernel<<<ceil_div(n3 * n2, 256), 256, 0, s>>>(m->head_partial, ctas, n3 * n2, dW(m, 2));
+        BLA_LAUNCH_CHECK();
+        bias_grad_kernel<<<n3, kBiasThreads, 0, s>>>(dz3, n3, B, Bg, c0, quirk, dB(m, 2));                               // :271
+        BLA_LAUNCH_CHECK();
+        int blocks = ceil_div(B / 4, 256);
+        const int cap = rt().num_sms * 4;
+        if (blocks > cap) blocks = cap;
+        const size_t smem = (size_t)n2 * n3 * sizeof(float);
+        BLA_DISPATCH_NC(n3, head_dgrad_kernel<NC><<<blocks, 256, smem, s>>>(W(m, 2), dz3, m->a2, n2, B, m->dz2));        // :273-278
+        BLA_LAUNCH_CHECK();
+        count_launch(4);
+    } else {
+        wgrad(2, dz3, m->a2, 0.f);            // :266-271
+        dgrad(2, dz3, m->a2, m->dz2);         // :273-278
+    }
     wgrad(1, m->dz2, m->a1, 0.f);         // :279-282
     dgrad(1, m->dz2, m->a1, m->dz1);      // :284-289
     wgrad(0, m->dz1, x, x_scale);         // :290-293 (X/255 again folded into alpha)
@@ -206,13 +436,15 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     m->dz1 = (float*)pool_alloc(kDevice, dims[1] * B * sizeof(float));
     m->stats = (double*)pool_alloc(kDevice, 2 * sizeof(double));
     BLA_CUDA(cudaMemsetAsync(m->stats, 0, 2 * sizeof(double), rt().stream));
+    m->head_ctas = rt().num_sms * 2;
+    m->head_partial = (float*)pool_alloc(kDevice, (size_t)(m->head_ctas + 1) * kMaxClasses * 256 * sizeof(float));
     return m;
 }
 
 void bla_mlp_destroy(bla_mlp* m) {
     if (!m) return;
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
-    void* bufs[] = {m->params, m->grads, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats};
+    void* bufs[] = {m->params, m->grads, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
     for (void* b : bufs) pool_free(b);
     free(m);
 }
@@ -284,10 +516,15 @@ void bla_mlp_forward(bla_mlp* m, const float* x, int batch, float* probs) {
     CallScope sc;
     cudaStream_t s = sc.stream();
     const float* dx = resident(x, m->x, (size_t)m->n[0] * batch, s);
-    forward(m, dx, 1 / 255.0F, batch, s);
     float* out = sc.out(probs, (size_t)m->n[3] * batch);
-    k_copy(out, m->z3, (size_t)m->n[3] * batch, s);
-    k_softmax_cols(out, m->n[3], batch, s);   // :463
+    if (skinny_head(m, batch)) {
+        forward(m, dx, 1 / 255.0F, batch, s, false);
+        head_forward(m, nullptr, batch, nullptr, out, s);
+    } else {
+        forward(m, dx, 1 / 255.0F, batch, s);
+        k_copy(out, m->z3, (size_t)m->n[3] * batch, s);
+        k_softmax_cols(out, m->n[3], batch, s);   // :463
+    }
 }
 
 }  // extern "C"

@@ -140,7 +140,9 @@ def test_mnist_nn_loss_curve_and_checkpoint_match(tmp_path):
         got_v, want_v = read_csv(os.path.join(rb, p)), read_csv(os.path.join(ra, p))
         # final weights norm-wise <= 1e-5 * steps (9 SGD steps here); element-wise a few units of
         # the "%f" text resolution
-        assert rel_err(got_v, want_v) <= 9e-5 and np.abs(got_v - want_v).max() <= 1e-5, (f, float(np.abs(got_v - want_v).max()), rel_err(got_v, want_v))
+        assert np.abs(got_v - want_v).max() <= 1e-5, (f, float(np.abs(got_v - want_v).max()))
+        if f.startswith("weights"):      # the biases (~1e-4) sit at the text resolution, a relative bound is meaningless there
+            assert rel_err(got_v, want_v) <= 9e-5, (f, rel_err(got_v, want_v))
     hits = lambda s: re.findall(r"Got (\d+) correct", s)
     assert hits(run("bla_mnist_nn", rb, "run", "200")) == hits(run("ref_mnist_nn_f64", ra, "run", "200"))
     # the shipped B = 64 build must also train to completion behind the unchanged API
