@@ -42,7 +42,7 @@ constexpr uint32_t kABytes = BM * BK * 4;               // 8 KB
 constexpr uint32_t kBBytes = BN * BK * 4;               // 16 KB
 constexpr uint32_t kRawBytes = kABytes + kBBytes;       // 24 KB  (lo tiles mirror it at +kRawBytes)
 constexpr uint32_t kStageBytes = 2 * kRawBytes;         // 48 KB
-constexpr uint32_t kStagingBytes = 4 * 32 * 32 * 4;     // 16 KB: one 32x32 fp32 tile per epilogue warp
+constexpr uint32_t kStagingBytes = 4 * 2 * 32 * 32 * 4; // 32 KB: two 32x32 fp32 tiles per epilogue warp
 constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;   // + barriers + alignment slack
 
 struct TcParams {
@@ -55,6 +55,7 @@ struct TcParams {
     float* partial;          // [splits][m][n] when splits > 1
     bla_epilogue epi;
     bool c_vec;              // 16-byte aligned rows
+    bool tma_store;          // epilogue writes C (or the split-K partials) with cp.async.bulk.tensor stores
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -89,6 +90,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y), "r"(src)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -155,7 +163,8 @@ __device__ __forceinline__ float epilogue_value(float acc, int i, int j, const T
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   const __grid_constant__ CUtensorMap tma_c, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -176,6 +185,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+        if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_split(s), 4);      // one arrival per splitter warp
@@ -226,7 +236,9 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 else
                     for (int at = 0; at < p.bn / 32; ++at) tma_prefetch_2d(&tma_b, c.n0 + 32 * at, k0);
             };
-            constexpr int kPrefetchDistance = 12;
+            // Measured on B200: lookahead prefetch LOSES 8-20 % (extra TMA traffic competes with the loads, L2-resident
+            // operands gain nothing) -- kept as a switch, disabled.
+            constexpr int kPrefetchDistance = 0;
             Cursor cur{(int)blockIdx.x, 0, 0, 0, 0, false}, ahead{(int)blockIdx.x, 0, 0, 0, 0, false};
             open_tile(cur);
             open_tile(ahead);
@@ -250,7 +262,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     for (int at = 0; at < p.bn / 32; ++at)
                         tma_load_2d(sb + at * (BK * 128), &tma_b, n0 + 32 * at, k0, bar_full(stage));
                 }
-                if (ahead.valid) { prefetch(ahead); advance(ahead); }
+                if (kPrefetchDistance > 0 && ahead.valid) { prefetch(ahead); advance(ahead); }
                 advance(cur);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -332,7 +344,9 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     } else {
         // ===================================== epilogue (warps 2-5) =============================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        float* stg = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + (warp - 2) * 4096);
+        float* stg = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + (warp - 2) * 8192);
+        const uint32_t stg_u32 = staging_base + (warp - 2) * 8192;
+        int sbuf = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int split = tile / (p.m_tiles * p.n_tiles);
@@ -348,6 +362,61 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 if (col0 >= n_end) break;            // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + 32 * ch), v);
+                if (p.tma_store) {
+                    // Fast path: the epilogue runs on the accumulator row each lane already holds (its bias is a
+                    // per-lane constant, its gate row is 128 contiguous bytes), the 32x32 tile is parked in
+                    // shared memory in the SWIZZLE_128B pattern and ONE bulk tensor store writes it out
+                    // (clipped at the matrix edge by the tensor map).  Two staging tiles per warp.
+                    const int i = row_base + lane;
+                    const bool row_ok = i < p.m;
+                    float o[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) o[e] = __uint_as_float(v[e]);
+                    if (!p.partial) {
+                        if (p.epi.alpha != 0.f) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) o[e] *= p.epi.alpha;
+                        }
+                        if (p.epi.bias_rows) {
+                            const float brow = row_ok ? __ldg(p.epi.bias_rows + i) : 0.f;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) o[e] += brow;
+                        }
+                        if (p.epi.activation == BLA_ACT_RELU) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) o[e] = o[e] < 0.f ? 0.f : o[e];
+                        }
+                        if (p.epi.gate && row_ok) {
+                            const float* gp = p.epi.gate + (size_t)i * p.ldc + col0;
+                            if (col0 + 31 < p.n) {
+                                float4 g4[8];
+#pragma unroll
+                                for (int c4 = 0; c4 < 8; ++c4) g4[c4] = __ldg(reinterpret_cast<const float4*>(gp) + c4);
+#pragma unroll
+                                for (int c4 = 0; c4 < 8; ++c4) {
+                                    o[4 * c4 + 0] = g4[c4].x > 0.f ? o[4 * c4 + 0] : 0.f; o[4 * c4 + 1] = g4[c4].y > 0.f ? o[4 * c4 + 1] : 0.f;
+                                    o[4 * c4 + 2] = g4[c4].z > 0.f ? o[4 * c4 + 2] : 0.f; o[4 * c4 + 3] = g4[c4].w > 0.f ? o[4 * c4 + 3] : 0.f;
+                                }
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 32; ++e)
+                                    if (col0 + e < p.n) o[e] = __ldg(gp + e) > 0.f ? o[e] : 0.f;
+                            }
+                        }
+                    }
+                    if (lane == 0) tma_store_wait_read1();     // the store that last used this staging tile has been read
+                    __syncwarp();
+                    float* sb = stg + sbuf * 1024;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        *reinterpret_cast<float4*>(sb + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+                            make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tma_c, col0, (p.partial ? split * p.m : 0) + row_base, stg_u32 + sbuf * 4096);
+                    sbuf ^= 1;
+                    continue;
+                }
                 // lane r holds row r, columns col0..col0+31: park it in shared memory with the 16-byte
                 // chunks XOR-swizzled by the row so that both the column-wise writes here and the
                 // row-wise reads below are bank-conflict free
@@ -430,6 +499,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             if (lane == 0) mbar_arrive(bar_acc_empty(acc));
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.tma_store && lane == 0) tma_store_wait_all();
     }
 
     tcgen05_fence_before();
@@ -485,6 +555,17 @@ bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, i
     return r == CUDA_SUCCESS;
 }
 
+// fp32 tensor map for the epilogue's 32x32 tile stores (SWIZZLE_128B, clipped at the matrix edge)
+bool make_map_c(CUtensorMap* map, float* base, long long rows, int cols, int ld) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t elem[2] = {1u, 1u};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 bool g_tc_broken = false;
 unsigned long long g_tc_launches = 0;
 
@@ -509,15 +590,17 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     // last wave of the persistent grid is not mostly idle (470 tiles on 148 SMs = 4 waves at width 256,
     // but also 4 waves at width 224), then shrink it to the narrowest width with the same tile count
     // (784 columns -> 4 x 208 instead of 4 x 256).
-    const int gran = p.b_kmajor ? 16 : 32;
+    const int gran = 32;   // whole 32-column epilogue chunks (and whole MN-major atoms)
     {
         const int sms_ = rt().num_sms;
-        long long best_cost = -1;
+        double best_cost = -1.0;
         int best_bn = BN;
-        for (int bn = BN; bn >= 128; bn -= gran) {
+        for (int bn = BN; bn >= 192; bn -= gran) {
             const long long tiles_ = (long long)p.m_tiles * ceil_div(g.n, bn);
             const long long waves = (tiles_ + sms_ - 1) / sms_;
-            const long long cost = waves * (bn + 24);     // + ~24 columns' worth of per-tile fixed cost
+            // measured on B200 (square 4096): a 192-wide tile costs 1.33x more per column than a 256-wide one
+            // (the A tile and its split are amortised over fewer columns)
+            const double cost = (double)waves * bn * (1.0 + 0.33 * (BN - bn) / 64.0);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
         }
         p.n_tiles = ceil_div(g.n, best_bn);
@@ -550,6 +633,14 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         p.partial = ws;
     }
 
+    CUtensorMap mc;
+    memset(&mc, 0, sizeof(mc));
+    p.tma_store = p.c_vec && !g.epi.pre_activation && !g.epi.bias_cols &&
+                  (splits == 1 || (g.m % BM == 0 && g.n % 4 == 0));
+    if (p.tma_store) {
+        p.tma_store = splits == 1 ? make_map_c(&mc, g.c, g.m, g.n, g.ldc) : make_map_c(&mc, ws, (long long)splits * g.m, g.n, g.n);
+    }
+
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
@@ -563,7 +654,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     }
     const long long total = tiles * splits;
     const int grid = (int)(total < sms ? total : sms);
-    gemm_3xtf32_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, p);
+    gemm_3xtf32_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, mc, p);
     BLA_LAUNCH_CHECK();
     count_launch();
     ++g_tc_launches;
