@@ -295,7 +295,13 @@ def main():
     rng = np.random.default_rng(1234 + rank)
     for i in range(nbuf):
         xd = b.bla_malloc_device(x_bytes)
-        b.bla_fill_uniform(xd, DIMS[0] * Bl, 1000 + 17 * i + 131 * rank, 0.0, 255.0)
+        # MNIST-shaped pixels: integers 0..255 stored as float32 (what the CSV loader hands the reference, mnist_csv2.c:28)
+        px = rng.integers(0, 256, DIMS[0] * Bl, dtype=np.uint8)
+        pd = b.bla_malloc_device(px.nbytes)
+        b.bla_copy_h2d(pd, px.ctypes.data_as(C.c_void_p), px.nbytes)
+        b.bla_u8_to_float(xd, pd, px.size, 1.0)
+        b.bla_sync()
+        b.bla_free(pd)
         labels = rng.integers(0, DIMS[3], Bl)
         Y = np.zeros((DIMS[3], Bl), np.float32); Y[labels, np.arange(Bl)] = 1
         yd = b.bla_malloc_device(Y.nbytes)
