@@ -7,10 +7,10 @@
 // Every product is issued three times, a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, into one TMEM
 // accumulator; the dropped lo.lo term and the rounding of lo are O(2^-21) relative.
 //
-// Dataflow per CTA (persistent, one CTA per SM, 10 warps):
+// Dataflow per CTA (persistent, one CTA per SM, 14 warps):
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles of raw A (128 x 16) and B (16 x 256) fp32
 //               into swizzled shared memory, 4-stage ring, mbarrier complete_tx.
-//   warps 6-9   splitters: read the raw tile from shared memory, write the lo tile next to it
+//   warps 6-13  splitters: read the raw tile from shared memory, write the lo tile next to it
 //               (same swizzled positions, so the split is a flat elementwise pass), then
 //               fence.proxy.async and arrive on the stage's "split" barrier.
 //   warp 1      MMA issuer (one lane): 6 tcgen05.mma.kind::tf32 128x256x8 per stage
@@ -37,7 +37,8 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 16;   // BN = widest tile (TMEM stage); the tile width actually used is p.bn
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
-constexpr int kThreads = 320;
+constexpr int kSplitWarps = 8;   // 4 warps needed ~700 cycles per 24 KB stage, as long as its MMAs: the split was co-critical
+constexpr int kThreads = 32 * (6 + kSplitWarps);   // TMA, MMA, 4 epilogue, kSplitWarps splitters
 constexpr uint32_t kABytes = BM * BK * 4;               // 8 KB
 constexpr uint32_t kBBytes = BN * BK * 4;               // 16 KB
 constexpr uint32_t kRawBytes = kABytes + kBBytes;       // 24 KB  (lo tiles mirror it at +kRawBytes)
@@ -190,7 +191,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_split(s), 4);      // one arrival per splitter warp
+            mbar_init(bar_split(s), kSplitWarps);   // one arrival per splitter warp
             mbar_init(bar_empty(s), 1);      // tcgen05.commit
         }
         for (int a = 0; a < kAccStages; ++a) {
@@ -297,7 +298,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
                     uint32_t a_lo_nz = 0, b_lo_nz = 0;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) { a_lo_nz |= lo_flags[(stage * 4 + w) * 2]; b_lo_nz |= lo_flags[(stage * 4 + w) * 2 + 1]; }
+                    for (int w = 0; w < kSplitWarps; ++w) { a_lo_nz |= lo_flags[(stage * kSplitWarps + w) * 2]; b_lo_nz |= lo_flags[(stage * kSplitWarps + w) * 2 + 1]; }
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
                         const uint64_t a_hi = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lt);
@@ -318,7 +319,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         }
     } else if (warp >= 6) {
         // ===================================== splitters ========================================
-        const int t = threadIdx.x - 6 * 32;   // 0..127
+        const int t = threadIdx.x - 6 * 32;   // 0 .. 32*kSplitWarps-1
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int split = tile / (p.m_tiles * p.n_tiles);
@@ -330,7 +331,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 float4* lo = reinterpret_cast<float4*>(smem_gen + stage * kStageBytes + kRawBytes);
                 uint32_t nz_a = 0, nz_b = 0;
 #pragma unroll 4
-                for (int i = t; i < (int)(kRawBytes / 16); i += 128) {
+                for (int i = t; i < (int)(kRawBytes / 16); i += 32 * kSplitWarps) {
                     const float4 v = raw[i];
                     float4 r;
                     uint32_t u, any;
@@ -347,8 +348,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 // all-zero lo tile: the MMA issuer skips the product with it -- bit-identical result, a third less work.
                 const bool wa = __any_sync(0xffffffffu, nz_a != 0), wb = __any_sync(0xffffffffu, nz_b != 0);
                 if (lane == 0) {
-                    lo_flags[(stage * 4 + (warp - 6)) * 2 + 0] = wa;
-                    lo_flags[(stage * 4 + (warp - 6)) * 2 + 1] = wb;
+                    lo_flags[(stage * kSplitWarps + (warp - 6)) * 2 + 0] = wa;
+                    lo_flags[(stage * kSplitWarps + (warp - 6)) * 2 + 1] = wb;
                 }
                 fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
