@@ -143,6 +143,9 @@ PROTOTYPES = {
     "bla_relu_ddx": (None, [C.c_void_p, C.c_int]),
     "bla_relu_backward": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "bla_softmax_xent": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "bla_conv2d_forward": (None, [C.c_void_p] * 3 + [C.c_int] * 7),
+    "bla_conv2d_wgrad": (None, [C.c_void_p] * 3 + [C.c_int] * 7),
+    "bla_conv2d_dgrad": (None, [C.c_void_p] * 3 + [C.c_int] * 7),
     "bla_group_norm": (None, [C.c_void_p] * 4 + [C.c_int] * 4),
     "bla_group_norm_ddx": (None, [C.c_void_p] * 5 + [C.c_int] * 4),
     # include/bla.h -- MNIST MLP trainer

@@ -130,6 +130,111 @@ __global__ void __launch_bounds__(kThreads) group_norm_bwd_kernel(const float* _
     }
 }
 
+
+// ---- fast paths: 1024-thread CTAs, two per SM, 128-bit accesses -------------------------------------
+constexpr int kFastThreads = 1024;
+constexpr int kFastF4 = 8;   // float4 per thread held in registers: slabs up to 1024*8*4 = 32768 elements (32 ch x 32 x 32)
+
+__device__ __forceinline__ float block_total_1024(float v, float* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = threadIdx.x < 32 ? sh[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32) {
+        t = warp_sum(t);
+        if (threadIdx.x == 0) sh[0] = t;
+    }
+    __syncthreads();
+    t = sh[0];
+    return t;
+}
+
+// forward: the group's slab is read from HBM exactly once into REGISTERS (8 x 128-bit loads per thread issued
+// back to back = 128 KB in flight per SM, no shared-memory round trip), reduced twice, and written out.
+__global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_regs(const float* __restrict__ x, float* __restrict__ y, float* vars,
+                                                                       float* means, GnParams p) {
+    __shared__ float red[32];
+    const int g = blockIdx.x, img = blockIdx.y;
+    const int c0 = g * p.group_size;
+    const int nc = min(p.group_size, p.C - c0);
+    const int n4 = (nc * p.HW) >> 2;
+    const size_t off = ((size_t)img * p.C + c0) * p.HW;
+    const float4* xs = reinterpret_cast<const float4*>(x + off);
+    float4* ys = reinterpret_cast<float4*>(y + off);
+    float4 v[kFastF4];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < kFastF4; ++u) {
+        const int i = threadIdx.x + u * kFastThreads;
+        v[u] = i < n4 ? xs[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    }
+    const float inv_n = 1.f / (float)(4 * n4);
+    const float mean = block_total_1024(s, red) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < kFastF4; ++u) {
+        const int i = threadIdx.x + u * kFastThreads;
+        if (i < n4) {
+            const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float var = block_total_1024(q, red) * inv_n;
+    const float denom = p.quirk ? var : sqrtf(var + 1e-8f);
+    if (threadIdx.x == 0) {
+        means[(size_t)img * p.G + g] = mean;
+        vars[(size_t)img * p.G + g] = p.quirk ? var : denom;
+    }
+#pragma unroll
+    for (int u = 0; u < kFastF4; ++u) {
+        const int i = threadIdx.x + u * kFastThreads;
+        if (i < n4) {
+            float4 o;
+            o.x = (v[u].x - mean) / denom; o.y = (v[u].y - mean) / denom; o.z = (v[u].z - mean) / denom; o.w = (v[u].w - mean) / denom;
+            ys[i] = o;
+        }
+    }
+}
+
+// backward: pass 1 reads x and dy (HBM) for the two group sums, pass 2 re-reads them (the CTA's 2 x 128 KB were
+// just touched, they come from L2) and writes dx -- 12 B/elem of DRAM traffic, 128-bit accesses throughout.
+__global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_vec(const float* __restrict__ dy, float* __restrict__ dx,
+                                                                      const float* __restrict__ x, const float* __restrict__ means,
+                                                                      const float* __restrict__ stdevs, GnParams p) {
+    __shared__ float red[32];
+    const int g = blockIdx.x, img = blockIdx.y;
+    const int c0 = g * p.group_size;
+    const int nc = min(p.group_size, p.C - c0);
+    const int n4 = (nc * p.HW) >> 2;
+    const size_t off = ((size_t)img * p.C + c0) * p.HW;
+    const float4* xs = reinterpret_cast<const float4*>(x + off);
+    const float4* gs4 = reinterpret_cast<const float4*>(dy + off);
+    float4* ds = reinterpret_cast<float4*>(dx + off);
+    const float mu = means[(size_t)img * p.G + g], sd = stdevs[(size_t)img * p.G + g];
+    float gs = 0.f, gw = 0.f;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += kFastThreads) {
+        const float4 a = xs[i], d = gs4[i];
+        gs += (d.x + d.y) + (d.z + d.w);
+        gw += ((a.x - mu) / sd * d.x + (a.y - mu) / sd * d.y) + ((a.z - mu) / sd * d.z + (a.w - mu) / sd * d.w);
+    }
+    const float inv_n = 1.f / (float)(4 * n4);
+    const float mean_g = block_total_1024(gs, red) * inv_n;
+    const float mean_gw = block_total_1024(gw, red) * inv_n;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += kFastThreads) {
+        const float4 a = xs[i], d = gs4[i];
+        float4 o;
+        o.x = (d.x - mean_g - (a.x - mu) / sd * mean_gw) / sd; o.y = (d.y - mean_g - (a.y - mu) / sd * mean_gw) / sd;
+        o.z = (d.z - mean_g - (a.z - mu) / sd * mean_gw) / sd; o.w = (d.w - mean_g - (a.w - mu) / sd * mean_gw) / sd;
+        ds[i] = o;
+    }
+}
+
+inline bool al16(const void* q) { return ((uintptr_t)q & 15) == 0; }
+
 }  // namespace
 
 void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int images, int C, int HW, int group_size, int quirk,
@@ -138,7 +243,11 @@ void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int i
     if (images <= 0 || C <= 0 || HW <= 0) return;
     const size_t slab = (size_t)min(group_size, C) * HW;
     dim3 grid(p.G, images);
-    if (slab <= kSmemSlabFloats) {
+    // every group slab starts 16-byte aligned and has a multiple of 4 elements?
+    const bool vec_ok = al16(x) && al16(y) && (HW % 4 == 0) && (C % group_size == 0 || ((size_t)(C % group_size) * HW) % 4 == 0);
+    if (vec_ok && slab <= (size_t)kFastThreads * kFastF4 * 4) {
+        group_norm_fwd_regs<<<grid, kFastThreads, 0, s>>>(x, y, vars, means, p);
+    } else if (slab <= kSmemSlabFloats) {
         static bool attr = false;
         if (!attr) {
             BLA_CUDA(cudaFuncSetAttribute(group_norm_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemSlabFloats * 4)));
@@ -158,7 +267,10 @@ void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* m
     if (images <= 0 || C <= 0 || HW <= 0) return;
     const size_t slab = (size_t)min(group_size, C) * HW;
     dim3 grid(p.G, images);
-    if (2 * slab <= kSmemSlabFloats) {
+    const bool vec_ok = al16(dy) && al16(dx) && al16(x) && (HW % 4 == 0);
+    if (vec_ok) {
+        group_norm_bwd_vec<<<grid, kFastThreads, 0, s>>>(dy, dx, x, means, stdevs, p);
+    } else if (2 * slab <= kSmemSlabFloats) {
         static bool attr = false;
         if (!attr) {
             BLA_CUDA(cudaFuncSetAttribute(group_norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemSlabFloats * 4)));

@@ -123,6 +123,19 @@ void bla_group_norm(const float* x, float* y, float* vars, float* means, int ima
 void bla_group_norm_ddx(const float* dy, float* dx, const float* x, const float* means, const float* vars, int images,
                         int channels, int hw, int group_size);
 
+/* ---- batched device-resident conv2d as implicit GEMM (lib/conv.c on NCHW tensors) ------------ */
+
+/* x [imgs][C][H][W], w [F][C][k][k], y / dy [imgs][F][Ho][Wo] with Ho = ceil(H/stride); SAME padding
+ * as lib/conv.c:12-24.  The im2col matrix is never materialised.  conv (lib/conv.c:205-212): */
+void bla_conv2d_forward(const float* x, const float* w, float* y, int imgs, int channels, int height, int width,
+                        int filters, int kernel_size, int stride);
+/* conv_ddx (lib/conv.c:214-229), the two halves: dw [F][C][k][k] summed over the images ... */
+void bla_conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int channels, int height, int width,
+                      int filters, int kernel_size, int stride);
+/* ... and dx [imgs][C][H][W], the exact adjoint for any stride (the reference's is stride-1 only). */
+void bla_conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int channels, int height, int width,
+                      int filters, int kernel_size, int stride);
+
 /* ---- MNIST MLP trainer: model/mnist_nn.c:164-394 as one device-resident step ---------------- */
 
 typedef struct bla_mlp bla_mlp;

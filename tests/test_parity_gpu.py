@@ -540,3 +540,71 @@ def _mlp_step_check(b, B, tol):
                      None, None, ptr(want), 0)
     assert rel_err(probs, want) <= 10 * tol
     assert np.array_equal(probs.argmax(axis=0), want.argmax(axis=0))
+
+
+# ------------------------------------------------------------------------------------------------
+# batched, device-resident implicit-GEMM conv2d (include/bla.h) vs the f64 oracle, image by image
+# ------------------------------------------------------------------------------------------------
+def _dev(b, arr):
+    arr = f32(arr)
+    d = b.bla_malloc_device(max(arr.nbytes, 4))
+    b.bla_copy_h2d(d, ptr(arr), arr.nbytes)
+    return d
+
+
+def _host(b, d, shape):
+    out = np.empty(shape, np.float32)
+    b.bla_copy_d2h(ptr(out), d, out.nbytes)
+    b.bla_sync()
+    return out
+
+
+@pytest.mark.parametrize("imgs,Cin,H,W,F,k,s", [(3, 128, 32, 32, 128, 3, 1), (2, 128, 32, 32, 256, 3, 2), (4, 3, 32, 32, 128, 3, 1),
+                                                (5, 256, 8, 8, 256, 1, 1), (7, 256, 4, 4, 256, 3, 1), (2, 5, 9, 7, 6, 3, 2),
+                                                (1, 128, 32, 32, 3, 3, 1)])
+def test_implicit_conv_batched_vs_oracle(bla, imgs, Cin, H, W, F, k, s):
+    b = bla
+    o = load_oracle(np.float64)
+    rng = np.random.default_rng(imgs + Cin + H + F + k + s)
+    Ho, Wo = -(-H // s), -(-W // s)
+    x = rng.normal(size=(imgs, Cin, H, W)); kr = rng.normal(0, 0.05, (F, Cin, k, k)); dy = rng.normal(size=(imgs, F, Ho, Wo))
+    y = np.empty((imgs, F, Ho, Wo)); dk = np.zeros_like(kr); dx = np.empty_like(x)
+    for n in range(imgs):
+        dkn = np.empty_like(kr)
+        o.orc_conv(Cin, H, W, F, k, s, ptr(x[n]), ptr(kr), ptr(y[n]))
+        o.orc_conv_ddx(Cin, H, W, F, k, s, ptr(x[n]), ptr(kr), ptr(dy[n]), ptr(dkn), ptr(dx[n]))
+        dk += dkn
+    dxd, dwd, dyd = _dev(b, x), _dev(b, kr), _dev(b, dy)
+    yd = b.bla_malloc_device(y.size * 4); dkd = b.bla_malloc_device(kr.size * 4); dxo = b.bla_malloc_device(x.size * 4)
+    h2d0 = b.bla_h2d_bytes()
+    b.bla_conv2d_forward(dxd, dwd, yd, imgs, Cin, H, W, F, k, s)
+    b.bla_conv2d_wgrad(dxd, dyd, dkd, imgs, Cin, H, W, F, k, s)
+    b.bla_conv2d_dgrad(dyd, dwd, dxo, imgs, Cin, H, W, F, k, s)
+    assert b.bla_h2d_bytes() == h2d0                       # device-resident: nothing staged
+    assert rel_err(_host(b, yd, y.shape), y) <= FP32_TOL
+    assert rel_err(_host(b, dkd, kr.shape), dk) <= FP32_TOL
+    assert rel_err(_host(b, dxo, x.shape), dx) <= FP32_TOL
+    for d in (dxd, dwd, dyd, yd, dkd, dxo):
+        b.bla_free(d)
+
+
+def test_group_norm_batched_device_vs_oracle(bla):
+    b = bla
+    o = load_oracle(np.float64)
+    rng = np.random.default_rng(8)
+    imgs, Cn, HW, gs = 5, 128, 256, 32
+    G = Cn // gs
+    x = rng.normal(0.2, 1.3, (imgs, Cn, HW)); dy = rng.normal(size=x.shape)
+    y = np.empty_like(x); var = np.empty((imgs, G)); mu = np.empty((imgs, G)); dx = np.empty_like(x)
+    for n in range(imgs):
+        o.orc_group_norm(Cn, HW, gs, ptr(x[n]), ptr(y[n]), ptr(var[n]), ptr(mu[n]), 1)
+        o.orc_group_norm_ddx(Cn, HW, gs, ptr(dy[n]), ptr(dx[n]), ptr(x[n]), ptr(mu[n]), ptr(var[n]))
+    xd, dyd = _dev(b, x), _dev(b, dy)
+    yd = b.bla_malloc_device(x.size * 4); dxd = b.bla_malloc_device(x.size * 4)
+    vd = b.bla_malloc_device(imgs * G * 4); md = b.bla_malloc_device(imgs * G * 4)
+    b.bla_group_norm(xd, yd, vd, md, imgs, Cn, HW, gs)
+    b.bla_group_norm_ddx(dyd, dxd, xd, md, vd, imgs, Cn, HW, gs)
+    assert rel_err(_host(b, yd, x.shape), y) <= FP32_TOL and rel_err(_host(b, vd, var.shape), var) <= FP32_TOL
+    assert rel_err(_host(b, dxd, x.shape), dx) <= 5 * FP32_TOL
+    for d in (xd, dyd, yd, dxd, vd, md):
+        b.bla_free(d)
