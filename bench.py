@@ -487,6 +487,30 @@ def run_extras(b, torch, stream, pk):
     out["elementwise"].append({"op": "group_norm bwd 256x128x32x32", "bytes_per_elem": 12, "gbs": 12 * ne / (ms * 1e-3) / 1e9,
                                "frac_hbm": 12 * ne / (ms * 1e-3) / 1e9 / pk["hbm"]})
     out["hbm_peak_gbs"] = pk["hbm"]
+    for p_ in (gx, gy, gd, gv, gm):
+        b.bla_free(p_)
+    for m_ in (X, Y, bias):
+        b.free_matrix(m_)
+    # implicit-GEMM conv2d at the U-Net's shapes, batch of 64 images, FP32 path: 2*M*N*K flop
+    out["conv"] = []
+    imgs = 64
+    for (Cn, H, F, k, st) in ((128, 32, 128, 3, 1), (128, 32, 256, 3, 2), (256, 16, 256, 3, 1), (256, 8, 256, 3, 1), (256, 16, 256, 1, 1)):
+        Ho = -(-H // st)
+        nx, nw, ny = imgs * Cn * H * H, F * Cn * k * k, imgs * F * Ho * Ho
+        dxp = b.bla_malloc_device(nx * 4); dwp = b.bla_malloc_device(nw * 4); dyp = b.bla_malloc_device(ny * 4)
+        gxp = b.bla_malloc_device(nx * 4); gwp = b.bla_malloc_device(nw * 4)
+        b.bla_fill_uniform(dxp, nx, 8, -1, 1); b.bla_fill_uniform(dwp, nw, 9, -0.05, 0.05); b.bla_fill_uniform(dyp, ny, 10, -1, 1)
+        flop = 2.0 * F * (imgs * Ho * Ho) * (Cn * k * k)
+        row = {"shape": f"{imgs}x{Cn}x{H}x{H} -> {F}, k{k} s{st}", "gflop": flop / 1e9}
+        for name, fn in (("fprop", lambda: b.bla_conv2d_forward(dxp, dwp, dyp, imgs, Cn, H, H, F, k, st)),
+                         ("wgrad", lambda: b.bla_conv2d_wgrad(dxp, dyp, gwp, imgs, Cn, H, H, F, k, st)),
+                         ("dgrad", lambda: b.bla_conv2d_dgrad(dyp, dwp, gxp, imgs, Cn, H, H, F, k, st))):
+            ms = t(fn, 5)
+            row[name + "_tflops"] = flop / (ms * 1e-3) / 1e12
+            row[name + "_frac_fp32"] = row[name + "_tflops"] / fp32_peak
+        out["conv"].append(row)
+        for p_ in (dxp, dwp, dyp, gxp, gwp):
+            b.bla_free(p_)
     return out
 
 

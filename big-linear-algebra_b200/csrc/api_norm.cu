@@ -5,6 +5,8 @@
 // centred second moment are reduced there (two passes over shared memory, like the reference's two
 // passes over DRAM, lib/norm.c:13-37), and the normalised values are written straight out.  Slabs
 // larger than shared memory fall back to re-reading global memory (L2-resident at these sizes).
+#include <cooperative_groups.h>
+
 #include <cstdint>
 
 #include "../../include/lib/norm.h"
@@ -235,6 +237,246 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_vec(const floa
 
 inline bool al16(const void* q) { return ((uintptr_t)q & 15) == 0; }
 
+// ---- cluster paths: one thread-block CLUSTER per (image, group) --------------------------------------------
+// The slab is split over the CTAs of a cluster; every CTA keeps its share in registers (read from HBM exactly
+// once) and the partial sums are exchanged through distributed shared memory.  Small CTAs (512 threads, <= 48
+// registers) mean two or more clusters' CTAs are resident per SM, so one group's loads overlap another's
+// reductions and stores -- which a single 1024-thread CTA per SM cannot do.
+namespace cg = cooperative_groups;
+constexpr int kClThreads = 512;
+
+template <int CL>
+__device__ __forceinline__ float cluster_total(float v, float* slot /* one float of this CTA's smem, 2 slots alternate */,
+                                               float* red) {
+    // CTA total
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < kClThreads / 32 ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) *slot = t;
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();                                   // partials visible cluster-wide
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < CL; ++r) tot += *cluster.map_shared_rank(slot, r);   // same order in every CTA -> identical totals
+    return tot;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(kClThreads, 2) group_norm_fwd_cluster(const float* __restrict__ x, float* __restrict__ y, float* vars,
+                                                                        float* means, GnParams p) {
+    constexpr int F4 = 8;
+    __shared__ float red[kClThreads / 32];
+    __shared__ float slots[2];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int g = blockIdx.x / CL, img = blockIdx.y;
+    const int c0 = g * p.group_size;
+    const int nc = min(p.group_size, p.C - c0);
+    const int n4 = (nc * p.HW) >> 2;
+    const int per = (n4 + CL - 1) / CL;                // float4 per CTA
+    const int beg = rank * per, end = min(n4, beg + per);
+    const size_t off = ((size_t)img * p.C + c0) * p.HW;
+    const float4* xs = reinterpret_cast<const float4*>(x + off);
+    float4* ys = reinterpret_cast<float4*>(y + off);
+    float4 v[F4];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = beg + threadIdx.x + u * kClThreads;
+        v[u] = i < end ? xs[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    }
+    const float inv_n = 1.f / (float)(4 * n4);
+    const float mean = cluster_total<CL>(s, &slots[0], red) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = beg + threadIdx.x + u * kClThreads;
+        if (i < end) {
+            const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float var = cluster_total<CL>(q, &slots[1], red) * inv_n;
+    const float denom = p.quirk ? var : sqrtf(var + 1e-8f);
+    if (rank == 0 && threadIdx.x == 0) {
+        means[(size_t)img * p.G + g] = mean;
+        vars[(size_t)img * p.G + g] = p.quirk ? var : denom;
+    }
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = beg + threadIdx.x + u * kClThreads;
+        if (i < end) {
+            float4 o;
+            o.x = (v[u].x - mean) / denom; o.y = (v[u].y - mean) / denom; o.z = (v[u].z - mean) / denom; o.w = (v[u].w - mean) / denom;
+            ys[i] = o;
+        }
+    }
+    cluster.sync();   // no CTA may exit while a peer can still read its shared memory
+}
+
+template <int CL>
+__global__ void __launch_bounds__(kClThreads, 2) group_norm_bwd_cluster(const float* __restrict__ dy, float* __restrict__ dx,
+                                                                        const float* __restrict__ x, const float* __restrict__ means,
+                                                                        const float* __restrict__ stdevs, GnParams p) {
+    constexpr int F4 = 4;
+    __shared__ float red[kClThreads / 32];
+    __shared__ float slots[2];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int g = blockIdx.x / CL, img = blockIdx.y;
+    const int c0 = g * p.group_size;
+    const int nc = min(p.group_size, p.C - c0);
+    const int n4 = (nc * p.HW) >> 2;
+    const int per = (n4 + CL - 1) / CL;
+    const int beg = rank * per, end = min(n4, beg + per);
+    const size_t off = ((size_t)img * p.C + c0) * p.HW;
+    const float4* xs = reinterpret_cast<const float4*>(x + off);
+    const float4* gs4 = reinterpret_cast<const float4*>(dy + off);
+    float4* ds = reinterpret_cast<float4*>(dx + off);
+    const float mu = means[(size_t)img * p.G + g], sd = stdevs[(size_t)img * p.G + g];
+    float4 w[F4], d[F4];
+    float gs = 0.f, gw = 0.f;
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = beg + threadIdx.x + u * kClThreads;
+        w[u] = i < end ? xs[i] : make_float4(mu, mu, mu, mu);
+        d[u] = i < end ? gs4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        w[u].x = (w[u].x - mu) / sd; w[u].y = (w[u].y - mu) / sd; w[u].z = (w[u].z - mu) / sd; w[u].w = (w[u].w - mu) / sd;
+        gs += (d[u].x + d[u].y) + (d[u].z + d[u].w);
+        gw += (w[u].x * d[u].x + w[u].y * d[u].y) + (w[u].z * d[u].z + w[u].w * d[u].w);
+    }
+    const float inv_n = 1.f / (float)(4 * n4);
+    const float mean_g = cluster_total<CL>(gs, &slots[0], red) * inv_n;
+    const float mean_gw = cluster_total<CL>(gw, &slots[1], red) * inv_n;
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = beg + threadIdx.x + u * kClThreads;
+        if (i < end) {
+            float4 o;
+            o.x = (d[u].x - mean_g - w[u].x * mean_gw) / sd; o.y = (d[u].y - mean_g - w[u].y * mean_gw) / sd;
+            o.z = (d[u].z - mean_g - w[u].z * mean_gw) / sd; o.w = (d[u].w - mean_g - w[u].w * mean_gw) / sd;
+            ds[i] = o;
+        }
+    }
+    cluster.sync();
+}
+
+// ---- persistent forward with a TMA bulk-copy prefetch ring ------------------------------------------------
+// One CTA per SM walks over (image, group) slabs.  Slab i+1 is fetched into shared memory by ONE
+// cp.async.bulk (mbarrier complete_tx) while slab i -- already moved from shared memory into registers -- is
+// reduced, normalised and written out, so HBM never waits for the two block reductions.
+__device__ __forceinline__ uint32_t gn_smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+
+__global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_tma(const float* __restrict__ x, float* __restrict__ y, float* vars,
+                                                                      float* means, GnParams p, int images) {
+    extern __shared__ __align__(128) float slab[];     // up to 32768 floats
+    __shared__ float red[32];
+    __shared__ __align__(8) unsigned long long bar;
+    const int slabs = p.G * images;
+    const uint32_t bar_a = gn_smem_u32(&bar), slab_a = gn_smem_u32(slab);
+    auto slab_info = [&](int sidx, size_t& off, int& n4) {
+        const int g = sidx % p.G, img = sidx / p.G;
+        const int c0 = g * p.group_size;
+        const int nc = min(p.group_size, p.C - c0);
+        n4 = (nc * p.HW) >> 2;
+        off = ((size_t)img * p.C + c0) * p.HW;
+    };
+    auto issue = [&](int sidx) {       // thread 0 only
+        size_t off; int n4;
+        slab_info(sidx, off, n4);
+        const uint32_t bytes = (uint32_t)n4 * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        // chunks of <= 32 KB
+        for (uint32_t done = 0; done < bytes; done += 32768u) {
+            const uint32_t sz = min(32768u, bytes - done);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(slab_a + done), "l"(reinterpret_cast<const char*>(x + off) + done), "r"(sz), "r"(bar_a) : "memory");
+        }
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int sidx = blockIdx.x;
+    if (threadIdx.x == 0 && sidx < slabs) issue(sidx);
+    uint32_t phase = 0;
+    for (; sidx < slabs; sidx += gridDim.x) {
+        size_t off; int n4;
+        slab_info(sidx, off, n4);
+        // wait for this slab's bytes
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tGN_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra GN_DONE;\n\tbra GN_WAIT;\n\tGN_DONE:\n\t}"
+            ::"r"(bar_a), "r"(phase) : "memory");
+        phase ^= 1;
+        float4 v[kFastF4];
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < kFastF4; ++u) {
+            const int i = threadIdx.x + u * kFastThreads;
+            v[u] = i < n4 ? reinterpret_cast<const float4*>(slab)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+        }
+        __syncthreads();                                   // everyone has left shared memory: refill it
+        const int next = sidx + gridDim.x;
+        if (threadIdx.x == 0 && next < slabs) issue(next);
+        const float inv_n = 1.f / (float)(4 * n4);
+        const float mean = block_total_1024(s, red) * inv_n;
+        float q = 0.f;
+#pragma unroll
+        for (int u = 0; u < kFastF4; ++u) {
+            const int i = threadIdx.x + u * kFastThreads;
+            if (i < n4) {
+                const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+        const float var = block_total_1024(q, red) * inv_n;
+        const float denom = p.quirk ? var : sqrtf(var + 1e-8f);
+        if (threadIdx.x == 0) {
+            means[sidx] = mean;                            // [img][g] == sidx
+            vars[sidx] = p.quirk ? var : denom;
+        }
+        float4* ys = reinterpret_cast<float4*>(y + off);
+#pragma unroll
+        for (int u = 0; u < kFastF4; ++u) {
+            const int i = threadIdx.x + u * kFastThreads;
+            if (i < n4) {
+                float4 o;
+                o.x = (v[u].x - mean) / denom; o.y = (v[u].y - mean) / denom; o.z = (v[u].z - mean) / denom; o.w = (v[u].w - mean) / denom;
+                ys[i] = o;
+            }
+        }
+    }
+}
+
+template <int CL, class Kernel, class... Args>
+void launch_cluster(Kernel kernel, dim3 grid, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kClThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BLA_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+
+
 }  // namespace
 
 void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int images, int C, int HW, int group_size, int quirk,
@@ -245,7 +487,18 @@ void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int i
     dim3 grid(p.G, images);
     // every group slab starts 16-byte aligned and has a multiple of 4 elements?
     const bool vec_ok = al16(x) && al16(y) && (HW % 4 == 0) && (C % group_size == 0 || ((size_t)(C % group_size) * HW) % 4 == 0);
-    if (vec_ok && slab <= (size_t)kFastThreads * kFastF4 * 4) {
+    if (vec_ok && slab <= (size_t)kFastThreads * kFastF4 * 4 && (long long)p.G * images >= 2LL * rt().num_sms) {
+        // many slabs: persistent CTAs with a TMA prefetch of the next slab
+        static bool attr = false;
+        if (!attr) {
+            BLA_CUDA(cudaFuncSetAttribute(group_norm_fwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastThreads * kFastF4 * 16));
+            attr = true;
+        }
+        group_norm_fwd_tma<<<rt().num_sms, kFastThreads, slab * sizeof(float), s>>>(x, y, vars, means, p, images);
+    } else if (vec_ok && slab <= (size_t)2 * kClThreads * 8 * 4) {
+        // cluster of 2 CTAs x 512 threads x 8 float4 covers 32768 elements (32 channels x 32 x 32)
+        launch_cluster<2>(group_norm_fwd_cluster<2>, dim3(2 * p.G, images), s, x, y, vars, means, p);
+    } else if (vec_ok && slab <= (size_t)kFastThreads * kFastF4 * 4) {
         group_norm_fwd_regs<<<grid, kFastThreads, 0, s>>>(x, y, vars, means, p);
     } else if (slab <= kSmemSlabFloats) {
         static bool attr = false;
@@ -268,7 +521,11 @@ void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* m
     const size_t slab = (size_t)min(group_size, C) * HW;
     dim3 grid(p.G, images);
     const bool vec_ok = al16(dy) && al16(dx) && al16(x) && (HW % 4 == 0);
-    if (vec_ok) {
+    const bool tail_ok = (C % group_size == 0) || (((size_t)(C % group_size) * HW) % 4 == 0);
+    if (vec_ok && tail_ok && slab <= (size_t)4 * kClThreads * 4 * 4) {
+        // cluster of 4 CTAs x 512 threads x (4 + 4) float4: x and dy are read from HBM exactly once
+        launch_cluster<4>(group_norm_bwd_cluster<4>, dim3(4 * p.G, images), s, dy, dx, x, means, stdevs, p);
+    } else if (vec_ok) {
         group_norm_bwd_vec<<<grid, kFastThreads, 0, s>>>(dy, dx, x, means, stdevs, p);
     } else if (2 * slab <= kSmemSlabFloats) {
         static bool attr = false;

@@ -188,9 +188,30 @@ __global__ void __launch_bounds__(kThreads) col_sum_stage1(const float* __restri
     int j1 = j0 + chunk;
     if (j1 > cols) j1 = cols;
     float acc = 0.f;
-    for (int j = j0 + threadIdx.x; j < j1; j += kThreads) {
-        size_t at = base + j;
-        if (at < total) acc += m[at];
+    // clip the window at the end of the buffer once, then stream it with 128-bit loads when it is aligned
+    size_t lo = base + j0, hi = base + j1;
+    if (hi > total) hi = total;
+    if (lo < hi) {
+        const float* ptr = m + lo;
+        const size_t n = hi - lo;
+        if ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
+            const size_t n4 = n >> 2;
+            float a0 = 0.f, a1 = 0.f;
+            size_t i = threadIdx.x;
+            for (; i + kThreads < n4; i += 2 * kThreads) {
+                const float4 u = reinterpret_cast<const float4*>(ptr)[i], w = reinterpret_cast<const float4*>(ptr)[i + kThreads];
+                a0 += (u.x + u.y) + (u.z + u.w);
+                a1 += (w.x + w.y) + (w.z + w.w);
+            }
+            for (; i < n4; i += kThreads) {
+                const float4 u = reinterpret_cast<const float4*>(ptr)[i];
+                a0 += (u.x + u.y) + (u.z + u.w);
+            }
+            acc = a0 + a1;
+            if (threadIdx.x < (n & 3)) acc += ptr[(n4 << 2) + threadIdx.x];
+        } else {
+            for (size_t i = threadIdx.x; i < n; i += kThreads) acc += ptr[i];
+        }
     }
     acc = block_sum<float>(acc);
     if (threadIdx.x == 0) partial[(size_t)row * nchunks + ch] = acc;

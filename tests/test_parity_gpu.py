@@ -588,11 +588,12 @@ def test_implicit_conv_batched_vs_oracle(bla, imgs, Cin, H, W, F, k, s):
         b.bla_free(d)
 
 
-def test_group_norm_batched_device_vs_oracle(bla):
+@pytest.mark.parametrize("imgs,Cn,HW,gs", [(5, 128, 256, 32), (80, 128, 64, 32), (100, 96, 36, 32), (3, 64, 1024, 32)])
+def test_group_norm_batched_device_vs_oracle(bla, imgs, Cn, HW, gs):
+    """cluster/DSMEM path (few slabs), persistent TMA-prefetch path (>= 2 slabs per SM), ragged slab sizes"""
     b = bla
     o = load_oracle(np.float64)
-    rng = np.random.default_rng(8)
-    imgs, Cn, HW, gs = 5, 128, 256, 32
+    rng = np.random.default_rng(8 + imgs)
     G = Cn // gs
     x = rng.normal(0.2, 1.3, (imgs, Cn, HW)); dy = rng.normal(size=x.shape)
     y = np.empty_like(x); var = np.empty((imgs, G)); mu = np.empty((imgs, G)); dx = np.empty_like(x)
