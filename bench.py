@@ -180,17 +180,21 @@ def run_reference_arm(args, rank, world):
     warmup = min(args.warmup, 1)
     r = time_cpu_reference(steps, warmup, budget_s=90.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, args.scaling),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(world):
-    return {"workload": "model/mnist_nn.c train step: MLP 784-256-128-10, global batch 60000 columns sharded over the GPUs",
-            "global_batch": GLOBAL_BATCH, "per_gpu_batch": GLOBAL_BATCH // world, "parallelism": f"dp{world}",
+def workload_config(world, scaling="weak"):
+    gb = GLOBAL_BATCH * world if scaling == "weak" else GLOBAL_BATCH
+    return {"workload": "model/mnist_nn.c train step: MLP 784-256-128-10, one 60000-column batch per GPU "
+                        "(data-parallel column shards, one NCCL all-reduce of the flat gradient per step)"
+                        if scaling == "weak" else
+                        "model/mnist_nn.c train step: MLP 784-256-128-10, global batch 60000 columns split over the GPUs",
+            "global_batch": gb, "per_gpu_batch": gb // world, "parallelism": f"dp{world}",
             "flop_per_sample": FLOP_PER_SAMPLE, "lr": LR}
 
 
@@ -245,6 +249,9 @@ def main():
     ap.add_argument("--path", default=os.environ.get("BLA_BENCH_PATH", "auto"), choices=["auto", "fp32", "3xtf32"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every GPU takes a 60,000-column shard (global batch 60,000 x N); "
+                         "strong: the 60,000 columns are split over the GPUs")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
 
@@ -282,7 +289,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    Bg = GLOBAL_BATCH
+    Bg = GLOBAL_BATCH * world if args.scaling == "weak" else GLOBAL_BATCH
     c0, Bl = dp.shard_columns(Bg, world, rank)
     dims = (C.c_int * 4)(*DIMS)
     net = b.bla_mlp_create(dims, Bl)
@@ -359,6 +366,16 @@ def main():
     e2e_ms = e2e["ms"] / e2e_steps
     e2e_value = Bg / (e2e_ms * 1e-3)
 
+    # the same end-to-end step from BYTE pixels (MNIST's native storage; additive entry point): 4x less PCIe traffic
+    hx8 = b.bla_malloc_pinned(DIMS[0] * Bl)
+    np.ctypeslib.as_array(C.cast(hx8, C.POINTER(C.c_ubyte)), shape=(DIMS[0] * Bl,))[:] = rng.integers(0, 256, DIMS[0] * Bl, dtype=np.uint8)
+
+    def step_e2e_u8(i):
+        b.bla_mlp_train_step_u8(net, hx8, hy, Bl, Bg, c0, LR, e2e_stats.ctypes.data_as(C.c_void_p))
+
+    e2e8 = timed(step_e2e_u8, e2e_steps, 3)
+    e2e8_ms = e2e8["ms"] / e2e_steps
+
     # ---- roofline of the dominant kernel: layer-1 forward GEMM (256 x 784 x Bl), alone ----
     pk = peaks()
     a1 = b.bla_malloc_device(DIMS[1] * Bl * 4)
@@ -398,15 +415,18 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": dict(workload_config(world), gemm_path=args.path,
+                "config": dict(workload_config(world, args.scaling), gemm_path=args.path,
                                l2=f"inputs rotate over {nbuf} resident batches ({nbuf * x_bytes >> 20} MiB > 126 MB L2)"),
                 "tflops": value * FLOP_PER_SAMPLE / 1e12,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"] // e2e_steps,
                         "d2h_bytes_per_step": e2e["d2h"] // e2e_steps, "ms_per_step": e2e_ms,
                         "api": "bla_mlp_train_step(host float32 X[784xB], Y[10xB], &stats)"},
+                "e2e_u8": {"value": Bg / (e2e8_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e8["h2d"] // e2e_steps,
+                           "d2h_bytes_per_step": e2e8["d2h"] // e2e_steps, "ms_per_step": e2e8_ms,
+                           "api": "bla_mlp_train_step_u8(host uint8 X[784xB], Y[10xB], &stats)"},
                 "gpu_launches": int(res["launches"]), "clocks": clk,
                 "loss_per_sample_last": float(stats[0] / max(1, Bg * args.steps)) if world == 1 else None,
                 "extras": extras}

@@ -61,6 +61,18 @@ void ok(ncclResult_t r, const char* what) {
 
 namespace bla {
 bool comm_active() { return g.comm != nullptr && g.world > 1; }
+// A second stream for collectives that overlap with compute on the library stream (ordering by events).
+cudaStream_t comm_stream() {
+    static cudaStream_t s = nullptr;
+    if (!s) BLA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    return s;
+}
+void comm_allreduce_f32_on(float* buf, size_t n, cudaStream_t s) {
+    if (comm_active() && n) ok(g.AllReduce(buf, buf, n, ncclFloat32, ncclSum, g.comm, s), "ncclAllReduce");
+}
+void comm_allreduce_f64_on(double* buf, size_t n, cudaStream_t s) {
+    if (comm_active() && n) ok(g.AllReduce(buf, buf, n, ncclFloat64, ncclSum, g.comm, s), "ncclAllReduce");
+}
 void comm_group_start() { ok(g.GroupStart(), "ncclGroupStart"); }
 void comm_group_end() { ok(g.GroupEnd(), "ncclGroupEnd"); }
 }  // namespace bla

@@ -22,6 +22,9 @@ namespace bla {
 bool comm_active();
 void comm_group_start();
 void comm_group_end();
+cudaStream_t comm_stream();
+void comm_allreduce_f32_on(float* buf, size_t n, cudaStream_t s);
+void comm_allreduce_f64_on(double* buf, size_t n, cudaStream_t s);
 }  // namespace bla
 
 using namespace bla;
@@ -38,6 +41,7 @@ struct bla_mlp {
     double* stats;                        // {loss_sum, num_correct} on the device
     float* head_partial;                  // [ctas][n3][n2] partial dW3 of the skinny output layer
     int head_ctas;
+    cudaEvent_t ev_l1, ev_rest, ev_comm;   // ordering between the compute stream and the collective stream
 };
 
 namespace {
@@ -367,7 +371,10 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
         g.epi.gate = gate;   // A > 0  <=>  Z > 0
         gemm(g, s);
     };
-    if (skinny) {
+    // Backward order: the dZ chain first, then the layer-1 gradients (86 % of the bytes to exchange) so that
+    // their all-reduce runs on the collective stream while the two small layers' gradients are still being
+    // computed; the reference's order (:266-293) is dW3, dA2, dW2, dA1, dW1 -- same values, no dependence.
+    auto head_wgrad = [&]() {
         const int n2 = m->n[2], n3 = m->n[3];
         int ctas = m->head_ctas;
         int cols = (ceil_div(B, ctas) + 31) / 32 * 32;
@@ -378,26 +385,42 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
         BLA_LAUNCH_CHECK();
         bias_grad_kernel<<<n3, kBiasThreads, 0, s>>>(dz3, n3, B, Bg, c0, quirk, dB(m, 2));                               // :271
         BLA_LAUNCH_CHECK();
+        count_launch(3);
+    };
+    if (skinny) {
+        const int n2 = m->n[2], n3 = m->n[3];
         int blocks = ceil_div(B / 4, 256);
         const int cap = rt().num_sms * 4;
         if (blocks > cap) blocks = cap;
         const size_t smem = (size_t)n2 * n3 * sizeof(float);
         BLA_DISPATCH_NC(n3, head_dgrad_kernel<NC><<<blocks, 256, smem, s>>>(W(m, 2), dz3, m->a2, n2, B, m->dz2));        // :273-278
         BLA_LAUNCH_CHECK();
-        count_launch(4);
+        count_launch();
     } else {
-        wgrad(2, dz3, m->a2, 0.f);            // :266-271
         dgrad(2, dz3, m->a2, m->dz2);         // :273-278
     }
-    wgrad(1, m->dz2, m->a1, 0.f);         // :279-282
     dgrad(1, m->dz2, m->a1, m->dz1);      // :284-289
     wgrad(0, m->dz1, x, x_scale);         // :290-293 (X/255 again folded into alpha)
-
-    if (comm_active()) {                  // sum over the data-parallel shards: ONE flat buffer
+    const bool dp = comm_active();
+    cudaStream_t cs = dp ? comm_stream() : nullptr;
+    const size_t seg1 = m->off_w[1];      // [W1 | b1] occupy the first seg1 floats of the flat gradient buffer
+    if (dp) {
+        BLA_CUDA(cudaEventRecord(m->ev_l1, s));
+        BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_l1, 0));
+        comm_allreduce_f32_on(m->grads, seg1, cs);
+    }
+    wgrad(1, m->dz2, m->a1, 0.f);         // :279-282
+    if (skinny) head_wgrad();
+    else wgrad(2, dz3, m->a2, 0.f);       // :266-271
+    if (dp) {                             // the rest of the flat buffer + {loss, correct}
+        BLA_CUDA(cudaEventRecord(m->ev_rest, s));
+        BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
         comm_group_start();
-        bla_allreduce_sum_f32(m->grads, m->nparams);
-        bla_allreduce_sum_f64(m->stats, 2);
+        comm_allreduce_f32_on(m->grads + seg1, m->nparams - seg1, cs);
+        comm_allreduce_f64_on(m->stats, 2, cs);
         comm_group_end();
+        BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
+        BLA_CUDA(cudaStreamWaitEvent(s, m->ev_comm, 0));
     }
     // clip_gradient is a no-op (threshold INFINITY, :13,:296-301); scale by -lr and add  :303-315
     k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, s);
@@ -436,6 +459,9 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     m->dz1 = (float*)pool_alloc(kDevice, dims[1] * B * sizeof(float));
     m->stats = (double*)pool_alloc(kDevice, 2 * sizeof(double));
     BLA_CUDA(cudaMemsetAsync(m->stats, 0, 2 * sizeof(double), rt().stream));
+    BLA_CUDA(cudaEventCreateWithFlags(&m->ev_l1, cudaEventDisableTiming));
+    BLA_CUDA(cudaEventCreateWithFlags(&m->ev_rest, cudaEventDisableTiming));
+    BLA_CUDA(cudaEventCreateWithFlags(&m->ev_comm, cudaEventDisableTiming));
     m->head_ctas = rt().num_sms * 2;
     m->head_partial = (float*)pool_alloc(kDevice, (size_t)(m->head_ctas + 1) * kMaxClasses * 256 * sizeof(float));
     return m;
@@ -446,6 +472,7 @@ void bla_mlp_destroy(bla_mlp* m) {
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
     void* bufs[] = {m->params, m->grads, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
     for (void* b : bufs) pool_free(b);
+    cudaEventDestroy(m->ev_l1); cudaEventDestroy(m->ev_rest); cudaEventDestroy(m->ev_comm);
     free(m);
 }
 
