@@ -25,6 +25,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -35,16 +36,23 @@ namespace bla {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 16;   // BN = widest tile (TMEM stage); the tile width actually used is p.bn
-constexpr int kStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kSplitWarps = 8;   // 4 warps needed ~700 cycles per 24 KB stage, as long as its MMAs: the split was co-critical
 constexpr int kThreads = 32 * (6 + kSplitWarps);   // TMA, MMA, 4 epilogue, kSplitWarps splitters
 constexpr uint32_t kABytes = BM * BK * 4;               // 8 KB
-constexpr uint32_t kBBytes = BN * BK * 4;               // 16 KB
-constexpr uint32_t kRawBytes = kABytes + kBBytes;       // 24 KB  (lo tiles mirror it at +kRawBytes)
-constexpr uint32_t kStageBytes = 2 * kRawBytes;         // 48 KB
+// Per-CTA stage geometry.  One CTA per tile: raw A 8 KB + raw B 16 KB, mirrored by the lo tiles = 48 KB, 4 stages.
+// CTA pair: every CTA stages only half of B: 2 x (8 + 8) KB = 32 KB, 6 stages (the pair's barrier round trips cross
+// the cluster, so the ring is deeper).
+template <int CL> struct Geo {
+    static constexpr uint32_t kBBytes = (BN / CL) * BK * 4;
+    static constexpr uint32_t kRawBytes = kABytes + kBBytes;
+    static constexpr uint32_t kStageBytes = 2 * kRawBytes;
+    static constexpr int kStages = CL == 2 ? 6 : 4;
+};
 constexpr uint32_t kStagingBytes = 4 * 2 * 32 * 32 * 4; // 32 KB: two 32x32 fp32 tiles per epilogue warp
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 512 + 1024;   // + barriers + alignment slack
+constexpr uint32_t kSmemBytes = 4 * Geo<1>::kStageBytes + kStagingBytes + 1024 + 1024;   // + barriers/flags + alignment slack
+static_assert(6 * Geo<2>::kStageBytes == 4 * Geo<1>::kStageBytes, "both geometries fill the same 192 KB");
 
 struct TcParams {
     int m, n, k;
@@ -57,6 +65,8 @@ struct TcParams {
     bla_epilogue epi;
     bool c_vec;              // 16-byte aligned rows
     bool tma_store;          // epilogue writes C (or the split-K partials) with cp.async.bulk.tensor stores
+    int cluster;             // 1, or 2: CTA PAIRS (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages only HALF of B
+    int debug;               // BLA_TC_DEBUG: 1 = no split (1xTF32: hi.hi only), for bottleneck experiments
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -98,6 +108,60 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int 
 }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+// Arrive on a barrier of the leader CTA.  Default (CTA-scope release) semantics on purpose: what the leader's MMA
+// lane consumes is shared memory that each SM's own threads wrote and fenced to the async proxy; a cluster-scope
+// release/acquire pair compiles to MEMBAR.GPU + CCTL.IVALL per k-block and halved the kernel's speed.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAITC_DONE;\n\t"
+        "bra WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)0x3) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -142,14 +206,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, FP32 accumulate.
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_major, int bn) {
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_major, int bn, int m = BM) {
     return (1u << 4)                       // c_format  = F32
            | (2u << 7)                     // a_format  = TF32
            | (2u << 10)                    // b_format  = TF32
            | ((a_mn_major ? 1u : 0u) << 15)
            | ((b_mn_major ? 1u : 0u) << 16)
            | ((uint32_t)(bn >> 3) << 17)   // n_dim
-           | ((uint32_t)(BM >> 4) << 24);  // m_dim
+           | ((uint32_t)(m >> 4) << 24);   // m_dim (256 for a CTA pair)
 }
 
 __device__ __forceinline__ float epilogue_value(float acc, int i, int j, const TcParams& p) {
@@ -163,9 +227,13 @@ __device__ __forceinline__ float epilogue_value(float acc, int i, int j, const T
     return v;
 }
 
+template <int CL>   // 1: one CTA per tile (cta_group::1); 2: CTA pairs (cta_group::2) -- separate kernels so that the
+                    // single-CTA kernel carries no cluster-scoped instruction and can be launched without a cluster
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_c, const TcParams p) {
+    constexpr int kStages = Geo<CL>::kStages;
+    constexpr uint32_t kRawBytes = Geo<CL>::kRawBytes, kStageBytes = Geo<CL>::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -180,7 +248,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     auto bar_acc_empty = [&](int a) { return bar_base + 8u * (3 * kStages + kAccStages + a); };
     const uint32_t tmem_slot = bar_base + 8u * (3 * kStages + 2 * kAccStages);
     // per stage, per splitter warp: does the lo tile of A / of B contain any non-zero?  (uint32 [kStages][4][2])
-    volatile uint32_t* lo_flags = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base + 192u - smem_base));
+    const uint32_t lo_flags_u32 = bar_base + 256u;   // [kStages][2 * kSplitWarps] uint32: bit 0 = A lo tile non-zero, bit 1 = B
+    volatile uint32_t* lo_flags = reinterpret_cast<volatile uint32_t*>(smem_gen + (lo_flags_u32 - smem_base));
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,25 +260,46 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_split(s), kSplitWarps);   // one arrival per splitter warp
-            mbar_init(bar_empty(s), 1);      // tcgen05.commit
+            mbar_init(bar_split(s), kSplitWarps * CL);   // one arrival per splitter warp (of both CTAs of a pair)
+            mbar_init(bar_empty(s), 1);      // tcgen05.commit (multicast to both CTAs of a pair)
         }
         for (int a = 0; a < kAccStages; ++a) {
             mbar_init(bar_acc_full(a), 1);   // tcgen05.commit
-            mbar_init(bar_acc_empty(a), 4);  // one arrival per epilogue warp
+            mbar_init(bar_acc_empty(a), 4 * CL);  // one arrival per epilogue warp (of both CTAs of a pair)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // whole warp: allocate all 512 TMEM columns (2 accumulator stages x 256)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CL == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {   // same warp id, same slot address in both CTAs of the pair
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+    // Work units.  cluster == 1: a unit is one 128 x bn tile.  cluster == 2: a unit is a 256 x bn tile computed by a CTA
+    // PAIR with tcgen05.mma.cta_group::2: CTA r owns rows 128r.. (its own A tile and TMEM accumulator) and stages only
+    // columns [r*bn/2, (r+1)*bn/2) of B; the tensor cores of both SMs read both halves.  What bounds the one-CTA kernel
+    // is the rate at which TMA can fill one SM's shared memory with fp32 operands (measured ~24 B/clk/SM: a 1xTF32
+    // run with a third of the MMAs was barely faster); the pair stages 16 KB instead of 24 KB per k-block and SM.
+    constexpr int cl = CL;
+    const uint32_t rank = cl == 2 ? cluster_ctarank() : 0u;
+    if (cl == 2) cluster_sync_all();   // the peer's mbarriers are initialised before anything can signal them
+    const int m_units = p.m_tiles / cl;
+    const int total_tiles = m_units * p.n_tiles * p.splits;          // units
+    const int unit0 = (int)blockIdx.x / cl, unit_stride = (int)gridDim.x / cl;
+    auto decode = [&](int unit, int& split, int& m0, int& n0) {
+        split = unit / (m_units * p.n_tiles);
+        const int mn = unit % (m_units * p.n_tiles);
+        m0 = ((mn % m_units) * cl + (int)rank) * BM;
+        n0 = (mn / m_units) * p.bn;
+    };
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -220,15 +310,13 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             auto open_tile = [&](Cursor& c) {
                 c.valid = c.tile < total_tiles;
                 if (!c.valid) return;
-                const int split = c.tile / (p.m_tiles * p.n_tiles);
-                const int mn = c.tile % (p.m_tiles * p.n_tiles);
-                c.m0 = (mn % p.m_tiles) * BM;
-                c.n0 = (mn / p.m_tiles) * p.bn;
+                int split;
+                decode(c.tile, split, c.m0, c.n0);
                 c.kb = split * p.kblocks_per_split;
                 c.kb1 = min(p.kblocks, c.kb + p.kblocks_per_split);
             };
             auto advance = [&](Cursor& c) {
-                if (++c.kb >= c.kb1) { c.tile += gridDim.x; open_tile(c); }
+                if (++c.kb >= c.kb1) { c.tile += unit_stride; open_tile(c); }
             };
             auto prefetch = [&](const Cursor& c) {
                 const int k0 = c.kb * BK;
@@ -242,7 +330,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             // Measured on B200: lookahead prefetch LOSES 8-20 % (extra TMA traffic competes with the loads, L2-resident
             // operands gain nothing) -- kept as a switch, disabled.
             constexpr int kPrefetchDistance = 0;
-            Cursor cur{(int)blockIdx.x, 0, 0, 0, 0, false}, ahead{(int)blockIdx.x, 0, 0, 0, 0, false};
+            Cursor cur{unit0, 0, 0, 0, 0, false}, ahead{unit0, 0, 0, 0, 0, false};
             open_tile(cur);
             open_tile(ahead);
             for (int i = 0; i < kPrefetchDistance && ahead.valid; ++i) { prefetch(ahead); advance(ahead); }
@@ -259,11 +347,22 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     for (int at = 0; at < BM / 32; ++at)                                            // box {32 m, 16 k} per atom
                         tma_load_2d(sa + at * (BK * 128), &tma_a, m0 + 32 * at, k0, bar_full(stage));
                 }
-                if (p.b_kmajor) {
-                    tma_load_2d(sb, &tma_b, k0, n0, bar_full(stage));                              // box {16 k, bn n}
+                if (cl == 1) {
+                    if (p.b_kmajor) {
+                        tma_load_2d(sb, &tma_b, k0, n0, bar_full(stage));                          // box {16 k, bn n}
+                    } else {
+                        for (int at = 0; at < p.bn / 32; ++at)
+                            tma_load_2d(sb + at * (BK * 128), &tma_b, n0 + 32 * at, k0, bar_full(stage));
+                    }
                 } else {
-                    for (int at = 0; at < p.bn / 32; ++at)
-                        tma_load_2d(sb + at * (BK * 128), &tma_b, n0 + 32 * at, k0, bar_full(stage));
+                    // this CTA stages only ITS half of the B columns (at the start of its B region)
+                    const int half = p.bn / 2, nh = n0 + (int)rank * half;
+                    if (p.b_kmajor) {                                                              // box {16 k, bn/2 n}
+                        tma_load_2d(sb, &tma_b, k0, nh, bar_full(stage));
+                    } else {
+                        for (int at = 0; at < half / 32; ++at)
+                            tma_load_2d(sb + at * (BK * 128), &tma_b, nh + 32 * at, k0, bar_full(stage));
+                    }
                 }
                 if (kPrefetchDistance > 0 && ahead.valid) { prefetch(ahead); advance(ahead); }
                 advance(cur);
@@ -272,8 +371,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(!p.a_kmajor, !p.b_kmajor, p.bn);
+        if (lane == 0 && rank == 0) {   // in a pair only the leader CTA issues (for both SMs)
+            const uint32_t idesc = make_idesc(!p.a_kmajor, !p.b_kmajor, p.bn, cl == 2 ? 2 * BM : BM);
             // K-major (rows of BK floats = 64 B, SWIZZLE_64B): 8-row groups 512 B apart (SBO), k-step = 32 B
             // inside the swizzle row.
             // MN-major (SWIZZLE_128B_BASE32B): 32-wide atoms BK*128 B apart (LBO), 4-k groups 512 B apart
@@ -284,36 +383,56 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             const uint32_t a_kstep = p.a_kmajor ? 32u : 1024u, b_kstep = p.b_kmajor ? 32u : 1024u;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int split = tile / (p.m_tiles * p.n_tiles);
+            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+                int split, m0_, n0_;
+                decode(tile, split, m0_, n0_);
                 const int kb0 = split * p.kblocks_per_split;
                 const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
-                mbar_wait(bar_acc_empty(acc), acc_phase ^ 1);      // epilogue has drained this accumulator
+                if (cl == 1) mbar_wait(bar_acc_empty(acc), acc_phase ^ 1);      // epilogue has drained this accumulator
+                else mbar_wait_cluster(bar_acc_empty(acc), acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                 uint32_t accumulate = 0;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(bar_split(stage), phase);            // raw tile landed AND lo tile written
+                    if (cl == 1) mbar_wait(bar_split(stage), phase);            // raw tile landed AND lo tile written
+                    else mbar_wait_cluster(bar_split(stage), phase);            // ... in both CTAs of the pair
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
                     uint32_t a_lo_nz = 0, b_lo_nz = 0;
 #pragma unroll
-                    for (int w = 0; w < kSplitWarps; ++w) { a_lo_nz |= lo_flags[(stage * kSplitWarps + w) * 2]; b_lo_nz |= lo_flags[(stage * kSplitWarps + w) * 2 + 1]; }
+                    if (cl == 1) {   // lo-tile-is-zero shortcut (single-CTA kernel only: the flags are CTA-local)
+                        uint32_t f = 0;
+#pragma unroll
+                        for (int w = 0; w < kSplitWarps; ++w) f |= lo_flags[stage * 2 * kSplitWarps + w];
+                        a_lo_nz = f & 1u; b_lo_nz = f & 2u;
+                    } else {
+                        a_lo_nz = b_lo_nz = 1u;
+                    }
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
                         const uint64_t a_hi = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lt);
                         const uint64_t b_hi = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lt);
                         const uint64_t a_lo = make_desc(sa + kRawBytes + ks * a_kstep, a_lbo, a_sbo, a_lt);
                         const uint64_t b_lo = make_desc(sb + kRawBytes + ks * b_kstep, b_lbo, b_sbo, b_lt);
-                        if (a_lo_nz) { umma_tf32(tmem_d, a_lo, b_hi, idesc, accumulate); accumulate = 1u; }
-                        if (b_lo_nz) { umma_tf32(tmem_d, a_hi, b_lo, idesc, accumulate); accumulate = 1u; }
-                        umma_tf32(tmem_d, a_hi, b_hi, idesc, accumulate);
+                        if (cl == 1) {
+                            if (a_lo_nz) { umma_tf32(tmem_d, a_lo, b_hi, idesc, accumulate); accumulate = 1u; }
+                            if (b_lo_nz) { umma_tf32(tmem_d, a_hi, b_lo, idesc, accumulate); accumulate = 1u; }
+                            umma_tf32(tmem_d, a_hi, b_hi, idesc, accumulate);
+                        } else {
+                            if (a_lo_nz) { umma_tf32_pair(tmem_d, a_lo, b_hi, idesc, accumulate); accumulate = 1u; }
+                            if (b_lo_nz) { umma_tf32_pair(tmem_d, a_hi, b_lo, idesc, accumulate); accumulate = 1u; }
+                            umma_tf32_pair(tmem_d, a_hi, b_hi, idesc, accumulate);
+                        }
                         accumulate = 1u;
                     }
-                    tcgen05_commit(bar_empty(stage));              // stage reusable once these MMAs retire
+                    // stage reusable once these MMAs retire; with a cluster the peer fills half of this stage and this CTA
+                    // fills half of the peer's, so both CTAs' empty barriers hear from both MMA issuers
+                    if (cl == 1) tcgen05_commit(bar_empty(stage));
+                    else tcgen05_commit_pair(bar_empty(stage));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(bar_acc_full(acc));                 // accumulator complete -> epilogue
+                if (cl == 1) tcgen05_commit(bar_acc_full(acc));    // accumulator complete -> epilogue (of both CTAs)
+                else tcgen05_commit_pair(bar_acc_full(acc));
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -321,17 +440,20 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         // ===================================== splitters ========================================
         const int t = threadIdx.x - 6 * 32;   // 0 .. 32*kSplitWarps-1
         int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int split = tile / (p.m_tiles * p.n_tiles);
+        for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+            int split, m0_, n0_;
+            decode(tile, split, m0_, n0_);
             const int kb0 = split * p.kblocks_per_split;
             const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(bar_full(stage), phase);
                 float4* raw = reinterpret_cast<float4*>(smem_gen + stage * kStageBytes);
                 float4* lo = reinterpret_cast<float4*>(smem_gen + stage * kStageBytes + kRawBytes);
+                const int n_f4 = (int)(kABytes / 16) + (p.bn / cl) * (BK * 4 / 16);   // A tile + the staged part of the B tile
                 uint32_t nz_a = 0, nz_b = 0;
+                if (p.debug != 1)
 #pragma unroll 4
-                for (int i = t; i < (int)(kRawBytes / 16); i += 32 * kSplitWarps) {
+                for (int i = t; i < n_f4; i += 32 * kSplitWarps) {
                     const float4 v = raw[i];
                     float4 r;
                     uint32_t u, any;
@@ -347,13 +469,18 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 // Operands that are exactly representable in TF32 (pixel values, one-hot labels, small integers) have an
                 // all-zero lo tile: the MMA issuer skips the product with it -- bit-identical result, a third less work.
                 const bool wa = __any_sync(0xffffffffu, nz_a != 0), wb = __any_sync(0xffffffffu, nz_b != 0);
-                if (lane == 0) {
-                    lo_flags[(stage * kSplitWarps + (warp - 6)) * 2 + 0] = wa;
-                    lo_flags[(stage * kSplitWarps + (warp - 6)) * 2 + 1] = wb;
-                }
+                const int slot = stage * 2 * kSplitWarps + (int)rank * kSplitWarps + (warp - 6);
+                const uint32_t fl = (wa ? 1u : 0u) | (wb ? 2u : 0u);
                 fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_split(stage));
+                if (lane == 0) {
+                    if (cl == 1) {
+                        lo_flags[slot] = fl;
+                        mbar_arrive(bar_split(stage));
+                    } else {   // the arrival goes to the leader CTA, whose MMA lane issues for the pair
+                        mbar_arrive_cluster(mapa_shared(bar_split(stage), 0));
+                    }
+                }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -364,10 +491,9 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         const uint32_t stg_u32 = staging_base + (warp - 2) * 8192;
         int sbuf = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int split = tile / (p.m_tiles * p.n_tiles);
-            const int mn = tile % (p.m_tiles * p.n_tiles);
-            const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * p.bn;
+        for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+            int split, m0, n0;
+            decode(tile, split, m0, n0);
             const int n_end = min(p.n, n0 + p.bn);
             mbar_wait(bar_acc_full(acc), acc_phase);
             tcgen05_fence_after();
@@ -512,7 +638,10 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+            if (lane == 0) {
+                if (cl == 1) mbar_arrive(bar_acc_empty(acc));
+                else mbar_arrive_cluster(mapa_shared(bar_acc_empty(acc), 0));   // the leader's MMA lane waits on it
+            }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
         if (p.tma_store && lane == 0) tma_store_wait_all();
@@ -520,9 +649,11 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 
     tcgen05_fence_before();
     __syncthreads();
+    if (cl == 2) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or signal its barriers
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (cl == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -598,6 +729,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     p.a_kmajor = !g.ta;           // A row-major [m][k]  -> K-major;  stored [k][m] -> MN-major
     p.b_kmajor = g.tb;            // B stored [n][k]     -> K-major;  row-major [k][n] -> MN-major
     p.c = g.c; p.ldc = g.ldc; p.epi = g.epi;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("BLA_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     p.c_vec = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 4 == 0);
     p.m_tiles = ceil_div(g.m, BM);
     p.n_tiles = ceil_div(g.n, BN);
@@ -606,14 +738,19 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     // last wave of the persistent grid is not mostly idle (470 tiles on 148 SMs = 4 waves at width 256,
     // but also 4 waves at width 224), then shrink it to the narrowest width with the same tile count
     // (784 columns -> 4 x 208 instead of 4 x 256).
-    const int gran = 32;   // whole 32-column epilogue chunks (and whole MN-major atoms)
+    // Clusters of 2 (TMA multicast of the B tile) need an even number of m tiles; each CTA then fetches half of
+    // the B tile, so the width must split into two whole 32-column atoms.
+    { static int en = -1; if (en < 0) { const char* e = getenv("BLA_TC_CLUSTER"); en = e ? atoi(e) : 1; }
+      p.cluster = (en && p.m_tiles >= 2 && p.m_tiles % 2 == 0) ? 2 : 1; }
+    const int gran = p.cluster == 2 ? 64 : 32;   // whole 32-column epilogue chunks / MN-major atoms (per CTA half)
     {
-        const int sms_ = rt().num_sms;
+        const int slots = rt().num_sms / p.cluster;
+        const int m_units = p.m_tiles / p.cluster;
         double best_cost = -1.0;
         int best_bn = BN;
         for (int bn = BN; bn >= 192; bn -= gran) {
-            const long long tiles_ = (long long)p.m_tiles * ceil_div(g.n, bn);
-            const long long waves = (tiles_ + sms_ - 1) / sms_;
+            const long long units_ = (long long)m_units * ceil_div(g.n, bn);
+            const long long waves = (units_ + slots - 1) / slots;
             // measured on B200 (square 4096): a 192-wide tile costs 1.33x more per column than a 256-wide one
             // (the A tile and its split are amortised over fewer columns)
             const double cost = (double)waves * bn * (1.0 + 0.33 * (BN - bn) / 64.0);
@@ -623,18 +760,18 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         p.bn = (ceil_div(g.n, p.n_tiles) + gran - 1) / gran * gran;
         if (p.bn > BN) p.bn = BN;
     }
-    p.stage_tx_bytes = kABytes + (uint32_t)p.bn * BK * 4;
+    p.stage_tx_bytes = kABytes + (uint32_t)(p.bn / p.cluster) * BK * 4;   // per CTA: its A tile + its share of the B tile
 
     CUtensorMap ma, mb;
     bool ok = p.a_kmajor ? make_map(&ma, g.a, g.m, g.k, g.lda, BM, false) : make_map(&ma, g.a, g.k, g.m, g.lda, BK, true);
-    ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, p.bn, false) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
+    ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, p.bn / p.cluster, false) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
     if (!ok) return false;
 
     const int sms = rt().num_sms;
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     int splits = 1;
     if (tiles * 2 <= sms && p.kblocks >= 32) {
-        long long want = sms / tiles;          // one wave: tiles * splits <= SMs
+        long long want = (sms / p.cluster) / (tiles / p.cluster);          // one wave: units * splits <= cluster slots
         long long maxs = p.kblocks / 16;
         splits = (int)(want < maxs ? want : maxs);
         if (splits < 1) splits = 1;
@@ -659,7 +796,8 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_3xtf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) {
             cudaGetLastError();
             g_tc_broken = true;
@@ -668,10 +806,27 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         }
         attr_set = true;
     }
-    const long long total = tiles * splits;
-    const int grid = (int)(total < sms ? total : sms);
-    gemm_3xtf32_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, mc, p);
-    BLA_LAUNCH_CHECK();
+    const long long units = tiles / p.cluster * splits;
+    const int slots = sms / p.cluster;
+    const int grid = (int)(units < slots ? units : slots) * p.cluster;
+    if (p.cluster == 1) {
+        gemm_3xtf32_kernel<1><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, mc, p);
+        BLA_LAUNCH_CHECK();
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSmemBytes;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        BLA_CUDA(cudaLaunchKernelEx(&cfg, gemm_3xtf32_kernel<2>, ma, mb, mc, p));
+    }
     count_launch();
     ++g_tc_launches;
     if (ws) {
