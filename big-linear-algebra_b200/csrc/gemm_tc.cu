@@ -657,9 +657,42 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     }
 }
 
-// sums split-K partials in a fixed order and applies the epilogue
+// sums split-K partials in a fixed order and applies the epilogue.  Block = 64 float4 columns x 4 split groups:
+// every thread keeps 8 independent 128-bit loads in flight, the four group sums are combined through shared memory.
 __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p) {
     const size_t total = (size_t)p.m * p.n;
+    if ((total & 3) == 0 && (p.n & 3) == 0 && p.c_vec) {
+        __shared__ float4 part[4][64];
+        const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+        const size_t total4 = total >> 2;
+        for (size_t base = (size_t)blockIdx.x * 64; base < total4; base += (size_t)gridDim.x * 64) {
+            const size_t e4 = base + col;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e4 < total4) {
+                const float4* src = reinterpret_cast<const float4*>(p.partial) + e4;
+#pragma unroll 8
+                for (int z = grp; z < p.splits; z += 4) {
+                    const float4 v = src[(size_t)z * total4];
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            }
+            part[grp][col] = acc;
+            __syncthreads();
+            if (grp == 0 && e4 < total4) {
+                float4 t = part[0][col];
+#pragma unroll
+                for (int g2 = 1; g2 < 4; ++g2) { t.x += part[g2][col].x; t.y += part[g2][col].y; t.z += part[g2][col].z; t.w += part[g2][col].w; }
+                const size_t e = e4 << 2;
+                const int i = (int)(e / p.n), j = (int)(e % p.n);
+                float4 o;
+                o.x = epilogue_value(t.x, i, j, p); o.y = epilogue_value(t.y, i, j + 1, p);
+                o.z = epilogue_value(t.z, i, j + 2, p); o.w = epilogue_value(t.w, i, j + 3, p);
+                *reinterpret_cast<float4*>(p.c + (size_t)i * p.ldc + j) = o;
+            }
+            __syncthreads();
+        }
+        return;
+    }
     for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
         float s = 0.f;
         for (int z = 0; z < p.splits; ++z) s += p.partial[(size_t)z * total + e];
@@ -741,7 +774,9 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     // Clusters of 2 (TMA multicast of the B tile) need an even number of m tiles; each CTA then fetches half of
     // the B tile, so the width must split into two whole 32-column atoms.
     { static int en = -1; if (en < 0) { const char* e = getenv("BLA_TC_CLUSTER"); en = e ? atoi(e) : 1; }
-      p.cluster = (en && p.m_tiles >= 2 && p.m_tiles % 2 == 0) ? 2 : 1; }
+      // short contractions stay on the single-CTA kernel: the pair's cluster start-up and cross-SM barrier hops cost
+      // more than the halved staging saves (K = 128: 62 us as a pair, 33 us alone)
+      p.cluster = (en && p.m_tiles >= 2 && p.m_tiles % 2 == 0 && g.k >= 512) ? 2 : 1; }
     const int gran = p.cluster == 2 ? 64 : 32;   // whole 32-column epilogue chunks / MN-major atoms (per CTA half)
     {
         const int slots = rt().num_sms / p.cluster;
@@ -831,7 +866,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     ++g_tc_launches;
     if (ws) {
         size_t totalc = (size_t)g.m * g.n;
-        size_t blocks = (totalc + 255) / 256;
+        size_t blocks = (totalc / 4 + 63) / 64;   // 64 float4 columns per block on the vector path
         size_t cap = (size_t)sms * 8;
         if (blocks > cap) blocks = cap;
         tc_splitk_reduce_kernel<<<(int)blocks, 256, 0, s>>>(p);

@@ -113,55 +113,73 @@ template <int NC>
 __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restrict__ W3, const float* __restrict__ b3,
                                                            const float* __restrict__ A2, const float* __restrict__ Y, int hidden, int B,
                                                            float* dz, float* probs, float scale, double* stats) {
+    // block = 64 sample columns x 4 groups of hidden units: four times the loads in flight of a thread-per-column
+    // layout (the kernel only streams A2: 4 B/elem), partial logits combined through shared memory
     extern __shared__ float w_s[];   // [hidden][NC]  (transposed so one k gives NC consecutive floats)
+    __shared__ float part[3][64][NC + 1];
     for (int e = threadIdx.x; e < hidden * NC; e += 256) {
         const int k = e / NC, r = e % NC;
         w_s[e] = W3[(size_t)r * hidden + k];
     }
     __syncthreads();
+    const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int kper = (hidden + 3) / 4, kbeg = grp * kper, kend = min(hidden, kbeg + kper);
     double loss = 0.0;
     int correct = 0;
-    for (int c = blockIdx.x * 256 + threadIdx.x; c < B; c += gridDim.x * 256) {
+    for (int c0 = blockIdx.x * 64; c0 < B; c0 += gridDim.x * 64) {
+        const int c = c0 + col;
         float acc[NC];
 #pragma unroll
         for (int r = 0; r < NC; ++r) acc[r] = 0.f;
-        int k = 0;
-        for (; k + 8 <= hidden; k += 8) {
-            float a[8];
+        if (c < B) {
+            int k = kbeg;
+            for (; k + 8 <= kend; k += 8) {
+                float a[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = A2[(size_t)(k + u) * B + c];     // 8 coalesced rows in flight
+                for (int u = 0; u < 8; ++u) a[u] = A2[(size_t)(k + u) * B + c];     // 8 coalesced rows in flight
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+                for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int r = 0; r < NC; ++r) acc[r] = fmaf(w_s[(k + u) * NC + r], a[u], acc[r]);
-        }
-        for (; k < hidden; ++k) {
-            const float a = A2[(size_t)k * B + c];
+                    for (int r = 0; r < NC; ++r) acc[r] = fmaf(w_s[(k + u) * NC + r], a[u], acc[r]);
+            }
+            for (; k < kend; ++k) {
+                const float a = A2[(size_t)k * B + c];
 #pragma unroll
-            for (int r = 0; r < NC; ++r) acc[r] = fmaf(w_s[k * NC + r], a, acc[r]);
-        }
-        float mx = -INFINITY;
-#pragma unroll
-        for (int r = 0; r < NC; ++r) { acc[r] += b3[r]; mx = fmaxf(mx, acc[r]); }
-        float tot = 0.f;
-#pragma unroll
-        for (int r = 0; r < NC; ++r) { acc[r] = expf(acc[r] - mx); tot += acc[r]; }
-        int pred = 0;
-        float best = 0.f, l = 0.f;
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-            const size_t at = (size_t)r * B + c;
-            const float pr = acc[r] / tot;
-            if (probs) probs[at] = pr;
-            if (Y) {
-                const float y = Y[at];
-                if (pr > best) { best = pr; pred = r; }
-                l += -1.f * (y * logf(pr + 1e-15f));
-                dz[at] = (pr + (-1.0f) * y) * scale;
+                for (int r = 0; r < NC; ++r) acc[r] = fmaf(w_s[k * NC + r], a, acc[r]);
             }
         }
-        if (Y && Y[(size_t)pred * B + c] == 1.f) ++correct;
-        loss += (double)l;
+        if (grp > 0) {
+#pragma unroll
+            for (int r = 0; r < NC; ++r) part[grp - 1][col][r] = acc[r];
+        }
+        __syncthreads();
+        if (grp == 0 && c < B) {
+#pragma unroll
+            for (int r = 0; r < NC; ++r) acc[r] = ((acc[r] + part[0][col][r]) + part[1][col][r]) + part[2][col][r];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < NC; ++r) { acc[r] += b3[r]; mx = fmaxf(mx, acc[r]); }
+            float tot = 0.f;
+#pragma unroll
+            for (int r = 0; r < NC; ++r) { acc[r] = expf(acc[r] - mx); tot += acc[r]; }
+            int pred = 0;
+            float best = 0.f, l = 0.f;
+#pragma unroll
+            for (int r = 0; r < NC; ++r) {
+                const size_t at = (size_t)r * B + c;
+                const float pr = acc[r] / tot;
+                if (probs) probs[at] = pr;
+                if (Y) {
+                    const float y = Y[at];
+                    if (pr > best) { best = pr; pred = r; }
+                    l += -1.f * (y * logf(pr + 1e-15f));
+                    dz[at] = (pr + (-1.0f) * y) * scale;
+                }
+            }
+            if (Y && Y[(size_t)pred * B + c] == 1.f) ++correct;
+            loss += (double)l;
+        }
+        __syncthreads();
     }
     // block reduction of the two statistics
     __shared__ double red[2][8];
@@ -183,49 +201,64 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
 template <int NC>
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ A2, int hidden, int B,
                                                          int cols_per_cta, float* partial) {
-    __shared__ float a_s[256][33];          // [hidden unit][column in step]
-    __shared__ __align__(16) float d_s[32][NC];   // [column in step][class]
-    const int k = threadIdx.x;
+    constexpr int STEP = 64;
+    __shared__ float a_s[128][STEP + 1];          // [hidden unit (128 per pass)][column in step]
+    __shared__ __align__(16) float d_s[STEP][NC];  // [column in step][class]
     const int cbeg = blockIdx.x * cols_per_cta;
     const int cend = min(B, cbeg + cols_per_cta);
-    float acc[NC];
-#pragma unroll
-    for (int r = 0; r < NC; ++r) acc[r] = 0.f;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        // rows of A2 (hidden units) are read 32 columns = 128 bytes at a time by one warp each
-        for (int row = wrp; row < hidden; row += 8) {
-            const int c = c0 + lane;
-            a_s[row][lane] = c < cend ? A2[(size_t)row * B + c] : 0.f;
-        }
-        for (int e = threadIdx.x; e < 32 * NC; e += 256) {
-            const int cc = e % 32, r = e / 32;
-            const int c = c0 + cc;
-            d_s[cc][r] = c < cend ? dz[(size_t)r * B + c] : 0.f;
-        }
-        __syncthreads();
-        if (k < hidden) {
+    for (int h0 = 0; h0 < hidden; h0 += 128) {     // hidden <= 256: at most two passes
+        const int k = h0 + (threadIdx.x & 127), half = threadIdx.x >> 7;   // thread = (hidden unit, half of the classes' columns)
+        float acc[NC];
+#pragma unroll
+        for (int r = 0; r < NC; ++r) acc[r] = 0.f;
+        for (int c0 = cbeg; c0 < cend; c0 += STEP) {
+            // rows of A2 (hidden units) are read 64 columns = 256 bytes at a time by one warp each
+            for (int row = wrp; row < 128; row += 8) {
+#pragma unroll
+                for (int u = 0; u < STEP / 32; ++u) {
+                    const int c = c0 + lane + 32 * u;
+                    a_s[row][lane + 32 * u] = (h0 + row < hidden && c < cend) ? A2[(size_t)(h0 + row) * B + c] : 0.f;
+                }
+            }
+            for (int e = threadIdx.x; e < STEP * NC; e += 256) {
+                const int cc = e % STEP, r = e / STEP;
+                const int c = c0 + cc;
+                d_s[cc][r] = c < cend ? dz[(size_t)r * B + c] : 0.f;
+            }
+            __syncthreads();
+            // the two halves of the block split the 64 columns of the step
 #pragma unroll 8
-            for (int cc = 0; cc < 32; ++cc) {
-                const float a = a_s[k][cc];
+            for (int cc = half * (STEP / 2); cc < (half + 1) * (STEP / 2); ++cc) {
+                const float a = a_s[threadIdx.x & 127][cc];
 #pragma unroll
                 for (int r = 0; r < NC; ++r) acc[r] = fmaf(d_s[cc][r], a, acc[r]);
             }
+            __syncthreads();
+        }
+        // combine the two halves through shared memory (reuse a_s), then one partial per CTA
+        float* comb = &a_s[0][0];
+        if (half == 1) {
+#pragma unroll
+            for (int r = 0; r < NC; ++r) comb[(threadIdx.x & 127) * NC + r] = acc[r];
+        }
+        __syncthreads();
+        if (half == 0 && k < hidden) {
+#pragma unroll
+            for (int r = 0; r < NC; ++r) partial[((size_t)blockIdx.x * NC + r) * hidden + k] = acc[r] + comb[(threadIdx.x & 127) * NC + r];
         }
         __syncthreads();
     }
-    if (k < hidden) {
-#pragma unroll
-        for (int r = 0; r < NC; ++r) partial[((size_t)blockIdx.x * NC + r) * hidden + k] = acc[r];
-    }
 }
 
-__global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int count, float* out) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// out[e] = sum_p partial[p][e]: one warp per output, lanes stride over the partials, shuffle tree
+__global__ void __launch_bounds__(256) head_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int count, float* out) {
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (e >= count) return;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * count + e];
-    out[e] = s;
+    for (int p = lane; p < nparts; p += 32) s += partial[(size_t)p * count + e];
+    s = warp_sum(s);
+    if (lane == 0) out[e] = s;
 }
 
 // dZ2 = (A2 > 0) (.) (W3^T . dZ3)  (model/mnist_nn.c:273-278): a thread owns 4 sample columns (float4) and
@@ -240,11 +273,13 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict
     }
     __syncthreads();
     const int B4 = B >> 2;
+    const int hper = ((hidden + gridDim.y - 1) / gridDim.y + 3) / 4 * 4;   // hidden units of this blockIdx.y, a multiple of 4
+    const int hbeg = blockIdx.y * hper, hend = min(hidden, hbeg + hper);
     for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < B4; c4 += gridDim.x * 256) {
         float4 d[NC];
 #pragma unroll
         for (int r = 0; r < NC; ++r) d[r] = *reinterpret_cast<const float4*>(dz + (size_t)r * B + 4 * c4);
-        for (int k0 = 0; k0 < hidden; k0 += 4) {
+        for (int k0 = hbeg; k0 < hend; k0 += 4) {
             float4 g[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) g[u] = *reinterpret_cast<const float4*>(A2 + (size_t)(k0 + u) * B + 4 * c4);   // hidden % 4 == 0
@@ -308,8 +343,8 @@ bool skinny_head(const bla_mlp* m, int B) {
 
 // output layer + softmax (+ loss / accuracy / dZ3 when y is given), one kernel
 void head_forward(bla_mlp* m, const float* y, int B, float* dz, float* probs, cudaStream_t s) {
-    int blocks = ceil_div(B, 256);
-    const int cap = rt().num_sms * 4;
+    int blocks = ceil_div(B, 64);
+    const int cap = rt().num_sms * 8;
     if (blocks > cap) blocks = cap;
     const size_t smem = (size_t)m->n[2] * m->n[3] * sizeof(float);
     BLA_DISPATCH_NC(m->n[3], head_forward_kernel<NC><<<blocks, 256, smem, s>>>(m->params + m->off_w[2], m->params + m->off_b[2], m->a2, y,
@@ -377,11 +412,11 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
     auto head_wgrad = [&]() {
         const int n2 = m->n[2], n3 = m->n[3];
         int ctas = m->head_ctas;
-        int cols = (ceil_div(B, ctas) + 31) / 32 * 32;
+        int cols = (ceil_div(B, ctas) + 63) / 64 * 64;
         ctas = ceil_div(B, cols);
         BLA_DISPATCH_NC(n3, head_wgrad_kernel<NC><<<ctas, 256, 0, s>>>(dz3, m->a2, n2, B, cols, m->head_partial));       // :266-270
         BLA_LAUNCH_CHECK();
-        head_wgrad_reduce_kernel<<<ceil_div(n3 * n2, 256), 256, 0, s>>>(m->head_partial, ctas, n3 * n2, dW(m, 2));
+        head_wgrad_reduce_kernel<<<ceil_div(n3 * n2, 8), 256, 0, s>>>(m->head_partial, ctas, n3 * n2, dW(m, 2));
         BLA_LAUNCH_CHECK();
         bias_grad_kernel<<<n3, kBiasThreads, 0, s>>>(dz3, n3, B, Bg, c0, quirk, dB(m, 2));                               // :271
         BLA_LAUNCH_CHECK();
@@ -393,7 +428,7 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
         const int cap = rt().num_sms * 4;
         if (blocks > cap) blocks = cap;
         const size_t smem = (size_t)n2 * n3 * sizeof(float);
-        BLA_DISPATCH_NC(n3, head_dgrad_kernel<NC><<<blocks, 256, smem, s>>>(W(m, 2), dz3, m->a2, n2, B, m->dz2));        // :273-278
+        BLA_DISPATCH_NC(n3, head_dgrad_kernel<NC><<<dim3(blocks, 4), 256, smem, s>>>(W(m, 2), dz3, m->a2, n2, B, m->dz2));   // :273-278
         BLA_LAUNCH_CHECK();
         count_launch();
     } else {
@@ -462,7 +497,7 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_l1, cudaEventDisableTiming));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_rest, cudaEventDisableTiming));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_comm, cudaEventDisableTiming));
-    m->head_ctas = rt().num_sms * 2;
+    m->head_ctas = rt().num_sms * 4;
     m->head_partial = (float*)pool_alloc(kDevice, (size_t)(m->head_ctas + 1) * kMaxClasses * 256 * sizeof(float));
     return m;
 }
