@@ -38,10 +38,13 @@ struct bla_mlp {
     float *x, *y;                         // staging for host-side batches  [n0 x B], [n3 x B]
     unsigned char* x_u8;
     float *a1, *a2, *z3, *dz2, *dz1;      // [n1 x B] [n2 x B] [n3 x B] [n2 x B] [n1 x B]
-    double* stats;                        // {loss_sum, num_correct} on the device
+    double* stats;                        // kStatSlots x {loss_sum, num_correct} on the device (striped: ~1000 CTAs
+                                          // adding into ONE pair of doubles serialise in the L2 atomic unit)
     float* head_partial;                  // [ctas][n3][n2] partial dW3 of the skinny output layer
     int head_ctas;
     cudaEvent_t ev_l1, ev_rest, ev_comm;   // ordering between the compute stream and the collective stream
+    cudaStream_t side;                     // bias-gradient window sums run here, next to the wgrad GEMMs
+    cudaEvent_t ev_fork, ev_join;
 };
 
 namespace {
@@ -58,9 +61,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // [rows x Bg] matrix of which this process holds columns [c0, c0 + Bl).
 //   quirk: out[i] = sum of the Bg flat elements starting at i*rows  (two row segments)
 //   else : out[i] = sum of row i
-// One 1024-thread CTA per output element, 4 independent loads in flight per thread; elements of
-// other shards contribute through the all-reduce.
-constexpr int kBiasThreads = 1024;
+// One 256-thread CTA per output element, 4 independent loads in flight per thread; elements of other shards
+// contribute through the all-reduce.  Small on purpose (256 threads, <= 32 registers): the kernel runs on a side
+// stream and must fit on an SM next to the 448-thread, 57K-register GEMM CTA it overlaps with.
+constexpr int kBiasThreads = 256;
 
 __device__ __forceinline__ float segment_sum(const float* __restrict__ p, long long n) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(kBiasThreads) bias_grad_kernel(const float* __
 // All three stream the [hidden x B] activation matrix once with coalesced rows; the tiny weight
 // matrix lives in shared memory and is read as broadcasts.
 constexpr int kMaxClasses = 16;
+constexpr int kStatSlots = 32;
 
 // logits = W3 . A2 + b3 (model/mnist_nn.c:231-232), then per column softmax, argmax hit, the reference's
 // flat-slice cross-entropy and dZ3 = (p - y) * scale (:234-268) -- one thread per sample column.
@@ -191,8 +196,8 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
     if (threadIdx.x == 0 && stats) {
         double tl = 0.0, tc = 0.0;
         for (int w = 0; w < 8; ++w) { tl += red[0][w]; tc += red[1][w]; }
-        atomicAdd(&stats[0], tl);
-        atomicAdd(&stats[1], tc);
+        atomicAdd(&stats[2 * (blockIdx.x % kStatSlots) + 0], tl);
+        atomicAdd(&stats[2 * (blockIdx.x % kStatSlots) + 1], tc);
     }
 }
 
@@ -387,16 +392,26 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
     else k_softmax_xent(m->z3, y, m->n[3], B, nullptr, m->z3, (float)(1.0 / (double)m->n[0]), m->stats, s);
     const float* dz3 = m->z3;
 
+    // dz is complete on `s` when this is called: fork, so the window sums overlap the GEMM issued right after
+    auto bias_on_side = [&](const float* dz, int rows, float* out) {
+        BLA_CUDA(cudaEventRecord(m->ev_fork, s));
+        BLA_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+        bias_grad_kernel<<<rows, kBiasThreads, 0, m->side>>>(dz, rows, B, Bg, c0, quirk, out);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+    };
+    auto join_side = [&]() {
+        BLA_CUDA(cudaEventRecord(m->ev_join, m->side));
+        BLA_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
+    };
     auto wgrad = [&](int l, const float* dz, const float* act_prev, float alpha) {   // dW_l = dZ_l . A_{l-1}^T
         GemmArgs g{};
         g.m = m->n[l + 1]; g.n = m->n[l]; g.k = B;
         g.a = dz; g.lda = B; g.b = act_prev; g.ldb = B; g.tb = true;
         g.c = dW(m, l); g.ldc = m->n[l];
         g.epi.alpha = alpha;
+        bias_on_side(dz, m->n[l + 1], dB(m, l));                                                          // :271,:282,:293
         gemm(g, s);
-        bias_grad_kernel<<<m->n[l + 1], kBiasThreads, 0, s>>>(dz, m->n[l + 1], B, Bg, c0, quirk, dB(m, l));   // :271,:282,:293
-        BLA_LAUNCH_CHECK();
-        count_launch();
     };
     auto dgrad = [&](int l, const float* dz, const float* gate, float* out) {         // dZ_{l-1} = relu'(Z) (.) (W_l^T . dZ_l)
         GemmArgs g{};
@@ -414,13 +429,12 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
         int ctas = m->head_ctas;
         int cols = (ceil_div(B, ctas) + 63) / 64 * 64;
         ctas = ceil_div(B, cols);
+        bias_on_side(dz3, n3, dB(m, 2));                                                                                 // :271
         BLA_DISPATCH_NC(n3, head_wgrad_kernel<NC><<<ctas, 256, 0, s>>>(dz3, m->a2, n2, B, cols, m->head_partial));       // :266-270
         BLA_LAUNCH_CHECK();
         head_wgrad_reduce_kernel<<<ceil_div(n3 * n2, 8), 256, 0, s>>>(m->head_partial, ctas, n3 * n2, dW(m, 2));
         BLA_LAUNCH_CHECK();
-        bias_grad_kernel<<<n3, kBiasThreads, 0, s>>>(dz3, n3, B, Bg, c0, quirk, dB(m, 2));                               // :271
-        BLA_LAUNCH_CHECK();
-        count_launch(3);
+        count_launch(2);
     };
     if (skinny) {
         const int n2 = m->n[2], n3 = m->n[3];
@@ -436,6 +450,7 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
     }
     dgrad(1, m->dz2, m->a1, m->dz1);      // :284-289
     wgrad(0, m->dz1, x, x_scale);         // :290-293 (X/255 again folded into alpha)
+    join_side();                          // db1 is part of the first segment
     const bool dp = comm_active();
     cudaStream_t cs = dp ? comm_stream() : nullptr;
     const size_t seg1 = m->off_w[1];      // [W1 | b1] occupy the first seg1 floats of the flat gradient buffer
@@ -447,12 +462,13 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
     wgrad(1, m->dz2, m->a1, 0.f);         // :279-282
     if (skinny) head_wgrad();
     else wgrad(2, dz3, m->a2, 0.f);       // :266-271
+    join_side();
     if (dp) {                             // the rest of the flat buffer + {loss, correct}
         BLA_CUDA(cudaEventRecord(m->ev_rest, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
         comm_group_start();
         comm_allreduce_f32_on(m->grads + seg1, m->nparams - seg1, cs);
-        comm_allreduce_f64_on(m->stats, 2, cs);
+        comm_allreduce_f64_on(m->stats, 2 * kStatSlots, cs);
         comm_group_end();
         BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
         BLA_CUDA(cudaStreamWaitEvent(s, m->ev_comm, 0));
@@ -492,8 +508,11 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     m->z3 = (float*)pool_alloc(kDevice, dims[3] * B * sizeof(float));
     m->dz2 = (float*)pool_alloc(kDevice, dims[2] * B * sizeof(float));
     m->dz1 = (float*)pool_alloc(kDevice, dims[1] * B * sizeof(float));
-    m->stats = (double*)pool_alloc(kDevice, 2 * sizeof(double));
-    BLA_CUDA(cudaMemsetAsync(m->stats, 0, 2 * sizeof(double), rt().stream));
+    m->stats = (double*)pool_alloc(kDevice, 2 * kStatSlots * sizeof(double));
+    BLA_CUDA(cudaMemsetAsync(m->stats, 0, 2 * kStatSlots * sizeof(double), rt().stream));
+    BLA_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+    BLA_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    BLA_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_l1, cudaEventDisableTiming));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_rest, cudaEventDisableTiming));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_comm, cudaEventDisableTiming));
@@ -507,6 +526,7 @@ void bla_mlp_destroy(bla_mlp* m) {
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
     void* bufs[] = {m->params, m->grads, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
     for (void* b : bufs) pool_free(b);
+    cudaStreamDestroy(m->side); cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join);
     cudaEventDestroy(m->ev_l1); cudaEventDestroy(m->ev_rest); cudaEventDestroy(m->ev_comm);
     free(m);
 }
@@ -543,10 +563,16 @@ void bla_mlp_init_params(bla_mlp* m, unsigned long long seed) {
 }
 
 void bla_mlp_read_stats(bla_mlp* m, double* stats_host) {
-    BLA_CUDA(cudaMemcpyAsync(stats_host, m->stats, 2 * sizeof(double), cudaMemcpyDeviceToHost, rt().stream));
-    rt().d2h_bytes += 2 * sizeof(double);
-    BLA_CUDA(cudaMemsetAsync(m->stats, 0, 2 * sizeof(double), rt().stream));
+    double slots[2 * kStatSlots];
+    BLA_CUDA(cudaMemcpyAsync(slots, m->stats, sizeof(slots), cudaMemcpyDeviceToHost, rt().stream));
+    rt().d2h_bytes += sizeof(slots);
+    BLA_CUDA(cudaMemsetAsync(m->stats, 0, sizeof(slots), rt().stream));
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
+    stats_host[0] = stats_host[1] = 0.0;
+    for (int i = 0; i < kStatSlots; ++i) {
+        stats_host[0] += slots[2 * i];
+        stats_host[1] += slots[2 * i + 1];
+    }
 }
 
 void bla_mlp_train_step(bla_mlp* m, const float* x, const float* y, int batch, int global_batch, int col_offset, float lr_mult,
