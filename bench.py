@@ -404,6 +404,10 @@ def main():
     extras = None
     if not args.no_extras and rank == 0 and world == 1:
         extras = run_extras(b, torch, stream, pk)
+    if not args.no_extras and world > 1:
+        sharded = run_sharded_gemm(b, torch, dist, stream, rank, world, barrier)
+        if rank == 0:
+            extras = {"gemm_sweep_row_sharded": sharded}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -438,6 +442,45 @@ def main():
 
 def tc_available(b):
     return bool(getattr(b, "bla_tc_available", lambda: 0)())
+
+
+def run_sharded_gemm(b, torch, dist, stream, rank, world, barrier):
+    """BASELINE.json configs[3] on N GPUs: C[r] = A[r] . B with A and C row-sharded and B broadcast from rank 0 over
+    NVLink (bla_broadcast_f32) -- no reduction.  Aggregate TFLOP/s, with and without the broadcast in the timed region."""
+    out = []
+    for n in (4096, 8192, 16384):
+        rows = n // world
+        A = b.bla_malloc_device(rows * n * 4); B = b.bla_malloc_device(n * n * 4); Cm = b.bla_malloc_device(rows * n * 4)
+        b.bla_fill_uniform(A, rows * n, 100 + rank, -0.5, 0.5)
+        if rank == 0:
+            b.bla_fill_uniform(B, n * n, 2, -0.5, 0.5)
+        row = {"n": n, "rows_per_gpu": rows}
+        for name, path in (("3xtf32", b.GEMM_3XTF32), ("fp32", b.GEMM_FP32)):
+            b.bla_set_gemm_path(path)
+            for with_bcast in (False, True):
+                def once():
+                    if with_bcast:
+                        b.bla_broadcast_f32(B, n * n, 0)
+                    b.bla_gemm(0, 0, rows, n, n, A, n, B, n, Cm, n)
+                b.bla_broadcast_f32(B, n * n, 0)
+                for _ in range(2):
+                    once()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                iters = 5 if n <= 8192 else 2
+                e0.record(stream)
+                for _ in range(iters):
+                    once()
+                e1.record(stream)
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                row[name + ("_with_broadcast" if with_bcast else "") + "_tflops"] = 2.0 * n ** 3 / (float(t.item()) * 1e-3) / 1e12
+        out.append(row)
+        for p_ in (A, B, Cm):
+            b.bla_free(p_)
+    b.bla_set_gemm_path(b.GEMM_AUTO)
+    return out
 
 
 def run_extras(b, torch, stream, pk):

@@ -59,6 +59,25 @@ def main():
         errs = [rel_err(g, w) for g, w in zip(got, p64)]
         ok &= all(e <= tol * steps for e in errs) and all(t.item() == 1.0 for t in gathered)
         print("DP_CHECK_OK" if ok else "DP_CHECK_FAIL", "world", world, "errs", ["%.2e" % e for e in errs], flush=True)
+    # row-sharded GEMM (BASELINE.json configs[3]): every rank multiplies its row block by the broadcast B
+    n = 512
+    rowsn = n // world
+    Ah = np.ascontiguousarray(np.random.default_rng(100 + rank).uniform(-0.5, 0.5, (rowsn, n)), np.float32)
+    Bh = np.ascontiguousarray(np.random.default_rng(7).uniform(-0.5, 0.5, (n, n)), np.float32)      # only rank 0's copy is used
+    Ad = b.bla_malloc_device(Ah.nbytes); Bd = b.bla_malloc_device(Bh.nbytes); Cd = b.bla_malloc_device(Ah.nbytes)
+    b.bla_copy_h2d(Ad, ptr(Ah), Ah.nbytes)
+    if rank == 0:
+        b.bla_copy_h2d(Bd, ptr(Bh), Bh.nbytes)
+    else:
+        b.bla_memset_zero(Bd, Bh.nbytes)
+    b.bla_broadcast_f32(Bd, n * n, 0)
+    b.bla_gemm(0, 0, rowsn, n, n, Ad, n, Bd, n, Cd, n)
+    Ch = np.empty_like(Ah); b.bla_copy_d2h(ptr(Ch), Cd, Ch.nbytes); b.bla_sync()
+    gemm_ok = rel_err(Ch, Ah.astype(np.float64) @ Bh.astype(np.float64)) <= (1e-5 if path == b.GEMM_FP32 else 1e-4)
+    flags = [torch.zeros(1, device="cuda") for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([1.0 if gemm_ok else 0.0], device="cuda"))
+    if rank == 0:
+        print("SHARDED_GEMM_OK" if all(f.item() == 1.0 for f in flags) else "SHARDED_GEMM_FAIL", flush=True)
     b.bla_mlp_destroy(net)
     b.bla_comm_destroy()
     dist.destroy_process_group()
