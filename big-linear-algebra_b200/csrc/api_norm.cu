@@ -459,6 +459,114 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_tma(const floa
     }
 }
 
+// ---- persistent backward: 2-CTA clusters + TMA bulk prefetch + DSMEM sums ---------------------------------------
+// A cluster owns one (image, group) slab at a time; each CTA handles half of it.  The NEXT slab's halves of x and dy
+// are fetched into shared memory by cp.async.bulk while the current ones -- already in registers -- are reduced
+// (two sums, exchanged between the CTAs through distributed shared memory) and dx is written: x and dy are read from
+// HBM exactly once (12 B/elem) and the reductions never leave HBM idle.
+__global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const float* __restrict__ dy, float* __restrict__ dx,
+                                                                      const float* __restrict__ x, const float* __restrict__ means,
+                                                                      const float* __restrict__ stdevs, GnParams p, int images) {
+    constexpr int F4 = 4;                                  // float4 per thread per tensor: 2 CTAs x 1024 x 4 x 4 = 32768 elements
+    extern __shared__ __align__(128) float stage[];        // [x half | dy half], each up to 16384 floats
+    __shared__ float red[32];
+    __shared__ float slots[2];
+    __shared__ __align__(8) unsigned long long bar;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int slabs = p.G * images;
+    const uint32_t bar_a = gn_smem_u32(&bar), st_a = gn_smem_u32(stage);
+    constexpr int kHalfFloats = kFastThreads * F4 * 4;     // 16384
+    auto slab_info = [&](int sidx, size_t& off, int& beg, int& end) {
+        const int g = sidx % p.G, img = sidx / p.G;
+        const int c0 = g * p.group_size;
+        const int nc = min(p.group_size, p.C - c0);
+        const int n4 = (nc * p.HW) >> 2;
+        const int per = (n4 + 1) / 2;
+        beg = rank * per;
+        end = min(n4, beg + per);
+        off = ((size_t)img * p.C + c0) * p.HW;
+    };
+    auto issue = [&](int sidx) {       // thread 0 only
+        size_t off; int beg, end;
+        slab_info(sidx, off, beg, end);
+        const uint32_t bytes = (uint32_t)max(0, end - beg) * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * bytes) : "memory");
+        for (uint32_t done = 0; done < bytes; done += 32768u) {
+            const uint32_t sz = min(32768u, bytes - done);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(st_a + done), "l"(reinterpret_cast<const char*>(x + off) + (size_t)beg * 16 + done), "r"(sz), "r"(bar_a) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(st_a + (uint32_t)kHalfFloats * 4u + done), "l"(reinterpret_cast<const char*>(dy + off) + (size_t)beg * 16 + done),
+                           "r"(sz), "r"(bar_a) : "memory");
+        }
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
+    int sidx = cid;
+    if (threadIdx.x == 0 && sidx < slabs) issue(sidx);
+    uint32_t phase = 0;
+    for (; sidx < slabs; sidx += ncl) {
+        size_t off; int beg, end;
+        slab_info(sidx, off, beg, end);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tGNB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra GNB_DONE;\n\tbra GNB_WAIT;\n\tGNB_DONE:\n\t}"
+            ::"r"(bar_a), "r"(phase) : "memory");
+        phase ^= 1;
+        const float mu = means[sidx], sd = stdevs[sidx];
+        float4 w[F4], d[F4];
+#pragma unroll
+        for (int u = 0; u < F4; ++u) {
+            const int i = threadIdx.x + u * kFastThreads;
+            const bool ok = beg + i < end;
+            w[u] = ok ? reinterpret_cast<const float4*>(stage)[i] : make_float4(mu, mu, mu, mu);
+            d[u] = ok ? reinterpret_cast<const float4*>(stage + kHalfFloats)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();                                   // shared memory is free again: prefetch the next slab
+        const int next = sidx + ncl;
+        if (threadIdx.x == 0 && next < slabs) issue(next);
+        float gs = 0.f, gw = 0.f;
+#pragma unroll
+        for (int u = 0; u < F4; ++u) {
+            w[u].x = (w[u].x - mu) / sd; w[u].y = (w[u].y - mu) / sd; w[u].z = (w[u].z - mu) / sd; w[u].w = (w[u].w - mu) / sd;
+            gs += (d[u].x + d[u].y) + (d[u].z + d[u].w);
+            gw += (w[u].x * d[u].x + w[u].y * d[u].y) + (w[u].z * d[u].z + w[u].w * d[u].w);
+        }
+        // CTA totals -> slots, exchanged through DSMEM (same summation order in both CTAs)
+        float tot[2];
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            float v = which == 0 ? gs : gw;
+            v = block_total_1024(v, red);
+            if (threadIdx.x == 0) slots[which] = v;
+        }
+        cluster.sync();
+        tot[0] = *cluster.map_shared_rank(&slots[0], 0) + *cluster.map_shared_rank(&slots[0], 1);
+        tot[1] = *cluster.map_shared_rank(&slots[1], 0) + *cluster.map_shared_rank(&slots[1], 1);
+        cluster.sync();                                    // both CTAs have read before anyone overwrites the slots
+        const int g = sidx % p.G;
+        const int nc = min(p.group_size, p.C - g * p.group_size);
+        const float inv_n = 1.f / (float)(nc * p.HW);
+        const float mean_g = tot[0] * inv_n, mean_gw = tot[1] * inv_n;
+        float4* ds = reinterpret_cast<float4*>(dx + off) + beg;
+#pragma unroll
+        for (int u = 0; u < F4; ++u) {
+            const int i = threadIdx.x + u * kFastThreads;
+            if (beg + i < end) {
+                float4 o;
+                o.x = (d[u].x - mean_g - w[u].x * mean_gw) / sd; o.y = (d[u].y - mean_g - w[u].y * mean_gw) / sd;
+                o.z = (d[u].z - mean_g - w[u].z * mean_gw) / sd; o.w = (d[u].w - mean_g - w[u].w * mean_gw) / sd;
+                ds[i] = o;
+            }
+        }
+    }
+    cluster.sync();
+}
+
 template <int CL, class Kernel, class... Args>
 void launch_cluster(Kernel kernel, dim3 grid, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg{};
@@ -522,7 +630,26 @@ void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* m
     dim3 grid(p.G, images);
     const bool vec_ok = al16(dy) && al16(dx) && al16(x) && (HW % 4 == 0);
     const bool tail_ok = (C % group_size == 0) || (((size_t)(C % group_size) * HW) % 4 == 0);
-    if (vec_ok && tail_ok && slab <= (size_t)4 * kClThreads * 4 * 4) {
+    if (vec_ok && tail_ok && slab <= (size_t)2 * kFastThreads * 4 * 4 && slab % 8 == 0 && (long long)p.G * images >= (long long)rt().num_sms) {
+        // many slabs: persistent 2-CTA clusters with TMA prefetch (each CTA's half slab must be a whole number of float4)
+        static bool attr = false;
+        const int smem = 2 * kFastThreads * 4 * 16;   // 128 KB
+        if (!attr) {
+            BLA_CUDA(cudaFuncSetAttribute(group_norm_bwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr = true;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((rt().num_sms / 2) * 2);
+        cfg.blockDim = dim3(kFastThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr1[1];
+        attr1[0].id = cudaLaunchAttributeClusterDimension;
+        attr1[0].val.clusterDim.x = 2; attr1[0].val.clusterDim.y = 1; attr1[0].val.clusterDim.z = 1;
+        cfg.attrs = attr1;
+        cfg.numAttrs = 1;
+        BLA_CUDA(cudaLaunchKernelEx(&cfg, group_norm_bwd_tma, dy, dx, x, means, stdevs, p, images));
+    } else if (vec_ok && tail_ok && slab <= (size_t)4 * kClThreads * 4 * 4) {
         // cluster of 4 CTAs x 512 threads x (4 + 4) float4: x and dy are read from HBM exactly once
         launch_cluster<4>(group_norm_bwd_cluster<4>, dim3(4 * p.G, images), s, dy, dx, x, means, stdevs, p);
     } else if (vec_ok) {
