@@ -609,3 +609,95 @@ def test_group_norm_batched_device_vs_oracle(bla, imgs, Cn, HW, gs):
     assert rel_err(_host(b, dxd, x.shape), dx) <= 5 * FP32_TOL
     for d in (xd, dyd, yd, dxd, vd, md):
         b.bla_free(d)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-block parity: the U-Net's ResNet block (model/cifar_unet.c:1044-1072, dropout disabled) driven
+# through the reference API on both sides -- the compiled reference (double, D3-fixed conv) and libbla
+# ------------------------------------------------------------------------------------------------
+class _Backend:
+    def __init__(self, kind):
+        import helpers as H
+        self.kind = kind
+        if kind == "ref":
+            self.lib = H.load_ref("f64_convfix")
+            self.dt = np.float64
+            self.M = self.lib.MatrixT
+            self.CD = self.lib.ConvDataT
+            self.planes = lambda a: H.planes(self.lib, a)
+            self.ktable = lambda a: H.kernel_table(self.lib, a)
+            self.mat = lambda a: H.as_matrix(self.lib, a)
+        else:
+            import bla_b200 as b
+            self.lib = b.lib
+            self.dt = np.float32
+            self.M = b.Matrix
+            self.CD = b.ConvData
+            self.planes = b.planes
+            self.ktable = b.kernel_table
+            self.mat = b.host_matrix
+        self.P = C.POINTER(self.M)
+
+    def conv_data(self, Cin, H, W, F, k, s):
+        Ho, Wo = -(-H // s), -(-W // s)
+        bufs = dict(im2col=np.zeros((Ho * Wo, k * k * Cin), self.dt), kernel_matrix=np.zeros((k * k * Cin, F), self.dt),
+                    product=np.zeros((Ho * Wo, F), self.dt), output=np.zeros((F, Ho, Wo), self.dt))
+        mats = {n: self.mat(v) for n, v in bufs.items() if n != "output"}
+        outp = self.planes(bufs["output"])
+        cd = self.CD(C.pointer(mats["im2col"]), C.pointer(mats["kernel_matrix"]), C.pointer(mats["product"]), C.cast(outp, self.P))
+        cd._keep = (bufs, mats, outp)
+        return cd, bufs
+
+    def resnet_block(self, x, temb, prm, gs):
+        """model/cifar_unet.c:1044-1072 with _dropout replaced by a copy"""
+        L = self.lib
+        dt = self.dt
+        Cin, H, W = x.shape
+        F = prm["k1"].shape[0]
+        x = np.ascontiguousarray(x, dt)
+        G1, G2 = -(-Cin // gs), -(-F // gs)
+        relu1 = np.zeros_like(x); sd1 = np.zeros(G1, dt); mu1 = np.zeros(G1, dt)
+        L.group_norm(C.cast(self.planes(x), self.P), C.cast(self.planes(relu1), self.P), ptr(sd1), ptr(mu1), Cin, gs)
+        L.relu(ptr(relu1), C.c_int(relu1.size))                                                    # multi_channel_relu
+        k1 = np.ascontiguousarray(prm["k1"], dt); k2 = np.ascontiguousarray(prm["k2"], dt)
+        cd1, b1 = self.conv_data(Cin, H, W, F, 3, 1)
+        L.conv(C.cast(self.planes(relu1), self.P), self.ktable(k1), C.byref(cd1), Cin, F, 1)
+        te = np.ascontiguousarray(temb, dt).reshape(1, -1)
+        tw = np.ascontiguousarray(prm["tw"], dt); tb = np.ascontiguousarray(prm["tb"], dt).reshape(1, -1)
+        td = np.zeros((1, F), dt)
+        tem, twm, tdm, tbm = self.mat(te), self.mat(tw), self.mat(td), self.mat(tb)
+        L.matrix_multiply_inplace(C.byref(tem), C.byref(twm), C.byref(tdm))
+        L.matrix_add(C.byref(tdm), C.byref(tbm))
+        h = b1["output"] + td.reshape(F, 1, 1)                                                    # _add_time_embedding (model-local loop)
+        h = np.ascontiguousarray(h, dt)
+        relu2 = np.zeros_like(h); sd2 = np.zeros(G2, dt); mu2 = np.zeros(G2, dt)
+        L.group_norm(C.cast(self.planes(h), self.P), C.cast(self.planes(relu2), self.P), ptr(sd2), ptr(mu2), F, gs)
+        L.relu(ptr(relu2), C.c_int(relu2.size))
+        cd2, b2 = self.conv_data(F, H, W, F, 3, 1)
+        L.conv(C.cast(self.planes(relu2), self.P), self.ktable(k2), C.byref(cd2), F, F, 1)
+        res = x
+        if Cin != F:
+            kr = np.ascontiguousarray(prm["kr"], dt)
+            cdr, br = self.conv_data(Cin, H, W, F, 1, 1)
+            L.conv(C.cast(self.planes(x), self.P), self.ktable(kr), C.byref(cdr), Cin, F, 1)
+            res = br["output"]
+        return b2["output"] + res, dict(gn1=relu1, conv1=b1["output"].copy(), time=td.copy(), gn2=relu2)
+
+
+@pytest.mark.parametrize("Cin,F,HW", [(32, 64, 16), (64, 64, 8)])
+def test_unet_resnet_block_vs_reference(bla, Cin, F, HW):
+    import helpers as H
+    if not H.ref_available("f64_convfix"):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(Cin + F + HW)
+    x = rng.normal(0, 1, (Cin, HW, HW)); temb = rng.normal(0, 1, 512)
+    # group norm divides by the variance (D5): keep the activations O(1) with small weights
+    prm = dict(k1=rng.normal(0, 0.02, (F, Cin, 3, 3)), k2=rng.normal(0, 0.02, (F, F, 3, 3)), kr=rng.normal(0, 0.1, (F, Cin, 1, 1)),
+               tw=rng.normal(0, 0.02, (512, F)), tb=rng.normal(0, 0.1, F))
+    x32, t32 = f32(x), f32(temb)
+    prm32 = {k: f32(v) for k, v in prm.items()}
+    want, wi = _Backend("ref").resnet_block(x32.astype(np.float64), t32.astype(np.float64), {k: v.astype(np.float64) for k, v in prm32.items()}, 32)
+    got, gi = _Backend("bla").resnet_block(x32, t32, prm32, 32)
+    for name in ("gn1", "conv1", "time", "gn2"):
+        assert rel_err(gi[name], wi[name]) <= 2e-5, (name, rel_err(gi[name], wi[name]))
+    assert rel_err(got, want) <= 5e-5, rel_err(got, want)
