@@ -554,7 +554,7 @@ def run_extras(b, torch, stream, pk):
         b.bla_free(p_)
     for m_ in (X, Y, bias):
         b.free_matrix(m_)
-    # implicit-GEMM conv2d at the U-Net's shapes, batch of 64 images, FP32 path: 2*M*N*K flop
+    # implicit-GEMM conv2d at the U-Net's shapes, batch of 64 images, both GEMM paths: 2*M*N*K flop
     out["conv"] = []
     imgs = 64
     for (Cn, H, F, k, st) in ((128, 32, 128, 3, 1), (128, 32, 256, 3, 2), (256, 16, 256, 3, 1), (256, 8, 256, 3, 1), (256, 16, 256, 1, 1)):
@@ -565,12 +565,21 @@ def run_extras(b, torch, stream, pk):
         b.bla_fill_uniform(dxp, nx, 8, -1, 1); b.bla_fill_uniform(dwp, nw, 9, -0.05, 0.05); b.bla_fill_uniform(dyp, ny, 10, -1, 1)
         flop = 2.0 * F * (imgs * Ho * Ho) * (Cn * k * k)
         row = {"shape": f"{imgs}x{Cn}x{H}x{H} -> {F}, k{k} s{st}", "gflop": flop / 1e9}
-        for name, fn in (("fprop", lambda: b.bla_conv2d_forward(dxp, dwp, dyp, imgs, Cn, H, H, F, k, st)),
-                         ("wgrad", lambda: b.bla_conv2d_wgrad(dxp, dyp, gwp, imgs, Cn, H, H, F, k, st)),
-                         ("dgrad", lambda: b.bla_conv2d_dgrad(dyp, dwp, gxp, imgs, Cn, H, H, F, k, st))):
-            ms = t(fn, 5)
-            row[name + "_tflops"] = flop / (ms * 1e-3) / 1e12
-            row[name + "_frac_fp32"] = row[name + "_tflops"] / fp32_peak
+        ops = (("fprop", lambda: b.bla_conv2d_forward(dxp, dwp, dyp, imgs, Cn, H, H, F, k, st)),
+               ("wgrad", lambda: b.bla_conv2d_wgrad(dxp, dyp, gwp, imgs, Cn, H, H, F, k, st)),
+               ("dgrad", lambda: b.bla_conv2d_dgrad(dyp, dwp, gxp, imgs, Cn, H, H, F, k, st)))
+        for pname, path, peak in (("fp32", b.GEMM_FP32, fp32_peak), ("3xtf32", b.GEMM_3XTF32, pk["bf16"] / 6.0)):
+            if path == b.GEMM_3XTF32 and not tc_available(b):
+                continue
+            b.bla_set_gemm_path(path)
+            for name, fn in ops:
+                tc0 = b.bla_tc_launch_count()
+                ms = t(fn, 5)
+                if path == b.GEMM_3XTF32 and b.bla_tc_launch_count() == tc0:
+                    continue                      # this op/shape has no tensor path yet: the fp32 figure stands
+                row[f"{name}_{pname}_tflops"] = flop / (ms * 1e-3) / 1e12
+                row[f"{name}_{pname}_frac"] = row[f"{name}_{pname}_tflops"] / peak
+        b.bla_set_gemm_path(saved)
         out["conv"].append(row)
         for p_ in (dxp, dwp, dyp, gxp, gwp):
             b.bla_free(p_)

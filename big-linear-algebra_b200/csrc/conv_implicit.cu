@@ -14,6 +14,8 @@
 
 #include "../../include/bla.h"
 #include "kernels.h"
+
+extern "C" int bla_tc_available(void);
 #include "runtime.h"
 
 namespace bla {
@@ -212,6 +214,34 @@ __global__ void __launch_bounds__(256) permute_weights_dgrad(const float* __rest
     }
 }
 
+// tensor-path weight layouts: taps[f][(ki*k + kj)*C + c] = W[f][c][ki][kj]        (fprop: 16 consecutive k' = 16 channels of one tap)
+//                             flip [c][(ki*k + kj)*F + f] = W[f][c][k-1-ki][k-1-kj]   (stride-1 dgrad as a forward conv of dy)
+__global__ void __launch_bounds__(256) permute_weights_taps(const float* __restrict__ w, float* out, int F, int C, int k2, int flip) {
+    const size_t total = (size_t)F * C * k2;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        if (!flip) {
+            const int c = (int)(e % C), tap = (int)((e / C) % k2), f = (int)(e / ((size_t)C * k2));
+            out[e] = w[((size_t)f * C + c) * k2 + tap];
+        } else {
+            const int f = (int)(e % F), tap = (int)((e / F) % k2), c = (int)(e / ((size_t)F * k2));
+            out[e] = w[((size_t)f * C + c) * k2 + (k2 - 1 - tap)];
+        }
+    }
+}
+
+bool tensor_path_wanted() { return rt().gemm_path != BLA_GEMM_FP32 && bla_tc_available(); }
+
+float* permuted_weights(const float* w, int F, int C, int k, int flip, cudaStream_t s) {
+    const size_t total = (size_t)F * C * k * k;
+    float* out = (float*)pool_alloc(kDevice, total * sizeof(float));
+    size_t blocks = (total + 255) / 256, cap = (size_t)rt().num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    permute_weights_taps<<<(int)blocks, 256, 0, s>>>(w, out, F, C, k * k, flip);
+    BLA_LAUNCH_CHECK();
+    count_launch();
+    return out;
+}
+
 ConvP base_params(int imgs, int C, int H, int W, int F, int k, int stride) {
     ConvP p{};
     p.imgs = imgs; p.C = C; p.H = H; p.W = W; p.F = F; p.k = k; p.stride = stride;
@@ -247,6 +277,13 @@ void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, i
     p.M = F; p.N = imgs * p.Ho * p.Wo; p.K = C * k * k;
     p.a = w; p.src = x; p.out = y; p.k_chunk = p.K;
     if (p.M <= 0 || p.N <= 0) return;
+    if (tensor_path_wanted() && F >= 64 && p.N >= 256 && C % 16 == 0) {
+        // tcgen05 implicit GEMM: the im2col tile is gathered by 4-D TMA boxes (gemm_tc.cu, conv mode)
+        float* wt = permuted_weights(w, F, C, k, 0, s);
+        const bool done = conv2d_tc(x, wt, y, imgs, C, H, W, F, k, stride, p.pad_top, p.pad_left, s);
+        pool_free(wt);
+        if (done) return;
+    }
     launch<kFprop>(p, 1, s);
 }
 
@@ -288,6 +325,13 @@ void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, i
     ConvP p = base_params(imgs, C, H, W, F, k, stride);
     p.M = C; p.N = imgs * H * W; p.K = F * k * k;
     if (p.M <= 0 || p.N <= 0) return;
+    if (stride == 1 && (k & 1) && tensor_path_wanted() && C >= 64 && p.N >= 256 && F % 16 == 0) {
+        // stride 1, odd kernel: dgrad is the SAME-padded forward convolution of dy with the flipped, transposed filters
+        float* wf = permuted_weights(w, F, C, k, 1, s);
+        const bool done = conv2d_tc(dy, wf, dx, imgs, F, H, W, C, k, 1, (k - 1) / 2, (k - 1) / 2, s);
+        pool_free(wf);
+        if (done) return;
+    }
     float* wt = (float*)pool_alloc(kDevice, (size_t)F * C * k * k * sizeof(float));
     const size_t total = (size_t)F * C * k * k;
     size_t blocks = (total + 255) / 256, cap = (size_t)rt().num_sms * 8;

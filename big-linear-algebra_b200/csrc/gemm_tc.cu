@@ -66,6 +66,9 @@ struct TcParams {
     bool c_vec;              // 16-byte aligned rows
     bool tma_store;          // epilogue writes C (or the split-K partials) with cp.async.bulk.tensor stores
     int cluster;             // 1, or 2: CTA PAIRS (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages only HALF of B
+    // implicit-GEMM convolution (conv != 0): B[k'][n] is gathered from x [img][C][H][W] by 4-D TMA boxes, k' = (ki, kj, c)
+    // and n = (img, oi, oj); C is y [img][F][P] written by 3-D TMA boxes.  See conv2d_forward_tc().
+    int conv, cv_P, cv_Wo, cv_stride, cv_pad_top, cv_pad_left, cv_k, cv_cblocks, cv_bw, cv_bh;
     int debug;               // BLA_TC_DEBUG: 1 = no split (1xTF32: hi.hi only), for bottleneck experiments
 };
 
@@ -104,6 +107,15 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, i
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y), "r"(src)
                  : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(src) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -303,7 +315,39 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
+        if (p.conv) {
+            // Implicit im2col, whole warp: lane `at` owns the at-th 32-pixel atom of the tile's B columns.  Its pixel
+            // coordinates are decoded ONCE per tile (three integer divisions); per k-block = 16 channels of one filter tap
+            // (ki, kj) every lane only adds the tap to its box origin and issues ONE 4-D box {16 c, bw, bh, images} of the
+            // padded NHWC input = 32 K-major rows of 64 bytes.  (A single issuing lane doing the divisions per atom and
+            // k-block was the bottleneck of the first version: 62 TFLOP/s.)
+            const int ncols = p.bn / cl, natoms = ncols / 32;
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+                int split, m0, n0;
+                decode(tile, split, m0, n0);
+                const int kb0 = split * p.kblocks_per_split, kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
+                const int n = n0 + (int)rank * ncols * (cl - 1) + 32 * lane;
+                const int img = n / p.cv_P, pix = n - img * p.cv_P;
+                const int oi = pix / p.cv_Wo, oj = pix - oi * p.cv_Wo;
+                const int x0 = oj * p.cv_stride - p.cv_pad_left, y0 = oi * p.cv_stride - p.cv_pad_top;
+                int tap = kb0 / p.cv_cblocks, cb = kb0 - tap * p.cv_cblocks;
+                int ki = tap / p.cv_k, kj = tap - ki * p.cv_k;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                    if (lane == 0) {
+                        mbar_wait(bar_empty(stage), phase ^ 1);
+                        mbar_arrive_expect_tx(bar_full(stage), p.stage_tx_bytes);
+                        tma_load_2d(sa, &tma_a, kb * BK, m0, bar_full(stage));                     // weights [F][(ki, kj, c)]: K-major
+                    }
+                    __syncwarp();
+                    if (lane < natoms && p.debug != 2)   // debug 2: no gather (the host drops the B bytes from the expected count)
+                        tma_load_4d(sb + lane * (BK * 128), &tma_b, cb * BK, x0 + kj, y0 + ki, img, bar_full(stage));
+                    if (++cb == p.cv_cblocks) { cb = 0; if (++kj == p.cv_k) { kj = 0; ++ki; } }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (lane == 0) {
             // two cursors over this CTA's (tile, k-block) sequence: `cur` feeds shared memory, `ahead`
             // runs kPrefetchDistance k-blocks in front of it and only warms L2
             struct Cursor { int tile, kb, kb1, m0, n0; bool valid; };
@@ -555,7 +599,16 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                             make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) tma_store_2d(&tma_c, col0, (p.partial ? split * p.m : 0) + row_base, stg_u32 + sbuf * 4096);
+                    if (lane == 0) {
+                        if (!p.conv) {
+                            tma_store_2d(&tma_c, col0, (p.partial ? split * p.m : 0) + row_base, stg_u32 + sbuf * 4096);
+                        } else {
+                            const int img = col0 / p.cv_P, pix = col0 - img * p.cv_P;
+                            if (p.debug == 3) { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }   // experiment: no store
+                            else if (p.cv_P >= 32) tma_store_3d(&tma_c, pix, row_base, img, stg_u32 + sbuf * 4096);   // y as {P, F, img}
+                            else tma_store_3d(&tma_c, 0, img, row_base, stg_u32 + sbuf * 4096);                  // y as {P, img, F}
+                        }
+                    }
                     sbuf ^= 1;
                     continue;
                 }
@@ -746,6 +799,41 @@ bool make_map_c(CUtensorMap* map, float* base, long long rows, int cols, int ld)
     return r == CUDA_SUCCESS;
 }
 
+// 4-D map over the conv input in padded NHWC form xp [img][Hp][Wp][C]: a box {16 c, bw*s, bh*s, 32/(bw*bh)} with traversal
+// strides {1, s, s, 1} lands in shared memory as 32 (output pixels) rows of 16 channels = 64 bytes: 32 rows of a K-major
+// B tile of the implicit im2col matrix.  (Channels must be innermost: a TMA box has to start on a 16-byte boundary of the
+// innermost dimension, so a one-pixel filter-tap shift is impossible with W innermost -- profiles/probes/tma4d_probe.cu.)
+bool make_map_conv_in(CUtensorMap* map, const ConvTc& cv, int bw, int bh) {
+    const int nimg = 32 / (bw * bh);
+    cuuint64_t dims[4] = {(cuuint64_t)cv.C, (cuuint64_t)cv.W, (cuuint64_t)cv.H, (cuuint64_t)cv.imgs};
+    cuuint64_t strides[3] = {(cuuint64_t)cv.C * 4, (cuuint64_t)cv.W * cv.C * 4, (cuuint64_t)cv.H * cv.W * cv.C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * cv.stride), (cuuint32_t)(bh * cv.stride), (cuuint32_t)nimg};
+    cuuint32_t elem[4] = {1u, (cuuint32_t)cv.stride, (cuuint32_t)cv.stride, 1u};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)cv.in, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// 3-D map over the conv output y [img][F][P] for the epilogue's 32 (filters) x 32 (pixels) tiles: {P, F, img} when an
+// image has at least 32 pixels, {P, img, F} when a tile spans several small images.
+bool make_map_conv_out(CUtensorMap* map, const ConvTc& cv) {
+    const int P = cv.Ho * cv.Wo;
+    cuuint64_t dims[3], strides[2];
+    cuuint32_t box[3], elem[3] = {1u, 1u, 1u};
+    if (P >= 32) {
+        dims[0] = P; dims[1] = cv.F; dims[2] = cv.imgs;
+        strides[0] = (cuuint64_t)P * 4; strides[1] = (cuuint64_t)cv.F * P * 4;
+        box[0] = 32; box[1] = 32; box[2] = 1;
+    } else {
+        dims[0] = P; dims[1] = cv.imgs; dims[2] = cv.F;
+        strides[0] = (cuuint64_t)cv.F * P * 4; strides[1] = (cuuint64_t)P * 4;
+        box[0] = P; box[1] = 32 / P; box[2] = 32;
+    }
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)cv.out, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 bool g_tc_broken = false;
 unsigned long long g_tc_launches = 0;
 
@@ -755,12 +843,13 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     if (g_tc_broken || !encode_fn()) return false;
     if (g.m <= 0 || g.n <= 0 || g.k <= 0) return false;
     // TMA needs 16-byte aligned bases and row pitches
-    if (((uintptr_t)g.a & 15) || ((uintptr_t)g.b & 15) || (g.lda & 3) || (g.ldb & 3)) return false;
+    if (((uintptr_t)g.a & 15) || (g.lda & 3)) return false;
+    if (!g.conv && (((uintptr_t)g.b & 15) || (g.ldb & 3))) return false;
 
     TcParams p{};
     p.m = g.m; p.n = g.n; p.k = g.k;
     p.a_kmajor = !g.ta;           // A row-major [m][k]  -> K-major;  stored [k][m] -> MN-major
-    p.b_kmajor = g.tb;            // B stored [n][k]     -> K-major;  row-major [k][n] -> MN-major
+    p.b_kmajor = g.conv ? true : g.tb;    // B stored [n][k] (and the NHWC conv gather) -> K-major;  row-major [k][n] -> MN-major
     p.c = g.c; p.ldc = g.ldc; p.epi = g.epi;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("BLA_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     p.c_vec = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 4 == 0);
@@ -777,13 +866,21 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
       // short contractions stay on the single-CTA kernel: the pair's cluster start-up and cross-SM barrier hops cost
       // more than the halved staging saves (K = 128: 62 us as a pair, 33 us alone)
       p.cluster = (en && p.m_tiles >= 2 && p.m_tiles % 2 == 0 && g.k >= 512) ? 2 : 1; }
+    if (g.conv) {
+        const ConvTc& cv = *g.conv;
+        p.conv = 1; p.cv_P = cv.Ho * cv.Wo; p.cv_Wo = cv.Wo; p.cv_stride = cv.stride; p.cv_pad_top = cv.pad_top; p.cv_pad_left = cv.pad_left;
+        p.cv_k = cv.k; p.cv_cblocks = cv.C / BK;
+        p.cv_bw = cv.Wo < 32 ? cv.Wo : 32;
+        p.cv_bh = 32 / p.cv_bw < cv.Ho ? 32 / p.cv_bw : cv.Ho;
+    }
     const int gran = p.cluster == 2 ? 64 : 32;   // whole 32-column epilogue chunks / MN-major atoms (per CTA half)
     {
         const int slots = rt().num_sms / p.cluster;
         const int m_units = p.m_tiles / p.cluster;
         double best_cost = -1.0;
         int best_bn = BN;
-        for (int bn = BN; bn >= 192; bn -= gran) {
+        // conv has no split-K: a small batch of small images is spread over the SMs by narrower tiles instead
+        for (int bn = BN; bn >= (g.conv ? gran : 192); bn -= gran) {
             const long long units_ = (long long)m_units * ceil_div(g.n, bn);
             const long long waves = (units_ + slots - 1) / slots;
             // measured on B200 (square 4096): a 192-wide tile costs 1.33x more per column than a 256-wide one
@@ -796,16 +893,18 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         if (p.bn > BN) p.bn = BN;
     }
     p.stage_tx_bytes = kABytes + (uint32_t)(p.bn / p.cluster) * BK * 4;   // per CTA: its A tile + its share of the B tile
+    if (p.conv && p.debug == 2) p.stage_tx_bytes = kABytes;
 
     CUtensorMap ma, mb;
     bool ok = p.a_kmajor ? make_map(&ma, g.a, g.m, g.k, g.lda, BM, false) : make_map(&ma, g.a, g.k, g.m, g.lda, BK, true);
-    ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, p.bn / p.cluster, false) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
+    if (g.conv) ok = ok && make_map_conv_in(&mb, *g.conv, p.cv_bw, p.cv_bh);
+    else ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, p.bn / p.cluster, false) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
     if (!ok) return false;
 
     const int sms = rt().num_sms;
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     int splits = 1;
-    if (tiles * 2 <= sms && p.kblocks >= 32) {
+    if (!g.conv && tiles * 2 <= sms && p.kblocks >= 32) {
         long long want = (sms / p.cluster) / (tiles / p.cluster);          // one wave: units * splits <= cluster slots
         long long maxs = p.kblocks / 16;
         splits = (int)(want < maxs ? want : maxs);
@@ -825,7 +924,10 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     memset(&mc, 0, sizeof(mc));
     p.tma_store = p.c_vec && !g.epi.pre_activation && !g.epi.bias_cols &&
                   (splits == 1 || (g.m % BM == 0 && g.n % 4 == 0));
-    if (p.tma_store) {
+    if (g.conv) {
+        p.tma_store = make_map_conv_out(&mc, *g.conv);
+        if (!p.tma_store) { if (ws) pool_free(ws); return false; }
+    } else if (p.tma_store) {
         p.tma_store = splits == 1 ? make_map_c(&mc, g.c, g.m, g.n, g.ldc) : make_map_c(&mc, ws, (long long)splits * g.m, g.n, g.n);
     }
 
@@ -875,6 +977,63 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         pool_free(ws);
     }
     return true;
+}
+
+// NCHW -> zero-padded NHWC: xp[img][pt + i][pl + j][c] = x[img][c][i][j].  32 x 32 (channel x column) tiles through shared
+// memory so that both the reads (along j) and the writes (along c) are coalesced; the border was zeroed by a memset.
+__global__ void __launch_bounds__(256) nchw_to_padded_nhwc_kernel(const float* __restrict__ x, float* __restrict__ xp, int C, int H, int W,
+                                                                  int Hp, int Wp, int pt, int pl) {
+    __shared__ float tile[32][33];
+    const int img = blockIdx.z, i = blockIdx.y;
+    const int tiles_c = C / 32 + (C % 32 != 0), tiles_w = (W + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int t = blockIdx.x; t < tiles_c * tiles_w; t += gridDim.x) {
+        const int c0 = (t / tiles_w) * 32, j0 = (t % tiles_w) * 32;
+        for (int cc = ty; cc < 32; cc += 8) {
+            const int c = c0 + cc, j = j0 + tx;
+            tile[cc][tx] = (c < C && j < W) ? x[(((size_t)img * C + c) * H + i) * W + j] : 0.f;
+        }
+        __syncthreads();
+        for (int jj = ty; jj < 32; jj += 8) {
+            const int c = c0 + tx, j = j0 + jj;
+            if (c < C && j < W) xp[(((size_t)img * Hp + pt + i) * Wp + pl + j) * C + c] = tile[tx][jj];
+        }
+        __syncthreads();
+    }
+}
+
+bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int H, int W, int F, int k, int stride, int pad_top,
+               int pad_left, cudaStream_t s) {
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const int P = Ho * Wo;
+    // eligibility: whole 16-channel k-blocks, 16-byte aligned rows, and 32-pixel atoms that tile the output exactly
+    if (C % BK || ((uintptr_t)in & 15) || ((uintptr_t)out & 15) || (P % 4)) return false;
+    const bool big = P >= 32 && P % 32 == 0 && Wo <= 32 && 32 % Wo == 0;
+    const bool small = P < 32 && 32 % P == 0;
+    if (!big && !small) return false;
+    // The SAME padding is materialised once in a zero-padded NHWC copy of the input (8 B/elem, against k*k*F uses of every
+    // element): every TMA box then starts inside the tensor, on a 16-channel (64-byte) boundary.
+    const int Hp = (Ho - 1) * stride + k > H + pad_top ? (Ho - 1) * stride + k : H + pad_top;
+    const int Wp = (Wo - 1) * stride + k > W + pad_left ? (Wo - 1) * stride + k : W + pad_left;
+    const size_t xp_elems = (size_t)imgs * Hp * Wp * C;
+    float* xp = (float*)pool_alloc(kDevice, xp_elems * sizeof(float));
+    BLA_CUDA(cudaMemsetAsync(xp, 0, xp_elems * sizeof(float), s));
+    {
+        int gx = (C + 31) / 32 * ((W + 31) / 32);
+        if (gx > 64) gx = 64;
+        nchw_to_padded_nhwc_kernel<<<dim3(gx, H, imgs), 256, 0, s>>>(in, xp, C, H, W, Hp, Wp, pad_top, pad_left);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+    }
+    ConvTc cv{xp, out, imgs, C, Hp, Wp, F, k, stride, Ho, Wo, 0, 0};
+    GemmArgs g{};
+    g.m = F; g.n = imgs * P; g.k = k * k * C;
+    g.a = w_taps; g.lda = g.k;
+    g.c = out; g.ldc = P;
+    g.conv = &cv;
+    const bool done = gemm_3xtf32(g, s);
+    pool_free(xp);   // stream-ordered reuse
+    return done;
 }
 
 }  // namespace bla

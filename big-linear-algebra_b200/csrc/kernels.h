@@ -38,6 +38,13 @@ void k_softmax_xent(const float* logits, const float* expected, int classes, int
                     float grad_scale, double* stats, cudaStream_t s);                                    // mnist_nn.c:234-268
 
 // ---- GEMM (gemm_simt.cu / gemm_tc.cu) ---------------------------------------------------------
+// Implicit-GEMM convolution on the tensor path: B is not a matrix but the NCHW input, gathered by TMA.
+struct ConvTc {
+    const float* in;      // [imgs][C][H][W]
+    float* out;           // [imgs][F][Ho][Wo]
+    int imgs, C, H, W, F, k, stride, Ho, Wo, pad_top, pad_left;
+};
+
 struct GemmArgs {
     bool ta, tb;          // A stored [k x m] / B stored [n x k]
     int m, n, k;
@@ -45,11 +52,15 @@ struct GemmArgs {
     const float* b; int ldb;
     float* c; int ldc;
     bla_epilogue epi;     // zero-initialised = plain store
+    const ConvTc* conv;   // nullptr for a plain GEMM; else m = F, n = imgs*Ho*Wo, k = k*k*C, a = weights [F][(ki,kj,c)]
 };
 // Dispatch on rt().gemm_path and the shape.
 void gemm(const GemmArgs& g, cudaStream_t s);
 void gemm_simt(const GemmArgs& g, cudaStream_t s);
 // returns false when the shape/alignment is not eligible for the tensor path
 bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s);
+// conv2d forward on the tensor path: out = conv(in, w) with w already arranged as [F][(ki, kj, c)]; false if ineligible
+bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int H, int W, int F, int k, int stride, int pad_top,
+               int pad_left, cudaStream_t s);
 
 }  // namespace bla

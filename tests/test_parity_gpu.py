@@ -561,9 +561,18 @@ def _host(b, d, shape):
 
 @pytest.mark.parametrize("imgs,Cin,H,W,F,k,s", [(3, 128, 32, 32, 128, 3, 1), (2, 128, 32, 32, 256, 3, 2), (4, 3, 32, 32, 128, 3, 1),
                                                 (5, 256, 8, 8, 256, 1, 1), (7, 256, 4, 4, 256, 3, 1), (2, 5, 9, 7, 6, 3, 2),
-                                                (1, 128, 32, 32, 3, 3, 1)])
-def test_implicit_conv_batched_vs_oracle(bla, imgs, Cin, H, W, F, k, s):
+                                                (1, 128, 32, 32, 3, 3, 1), (4, 256, 16, 16, 256, 3, 1), (9, 128, 16, 16, 128, 3, 2)])
+@pytest.mark.parametrize("path", ["fp32", "3xtf32"])
+def test_implicit_conv_batched_vs_oracle(bla, imgs, Cin, H, W, F, k, s, path):
     b = bla
+    b.bla_set_gemm_path(b.GEMM_FP32 if path == "fp32" else b.GEMM_3XTF32)
+    try:
+        _implicit_conv_check(b, imgs, Cin, H, W, F, k, s, FP32_TOL if path == "fp32" else 2e-5)
+    finally:
+        b.bla_set_gemm_path(b.GEMM_FP32)
+
+
+def _implicit_conv_check(b, imgs, Cin, H, W, F, k, s, tol):
     o = load_oracle(np.float64)
     rng = np.random.default_rng(imgs + Cin + H + F + k + s)
     Ho, Wo = -(-H // s), -(-W // s)
@@ -581,9 +590,9 @@ def test_implicit_conv_batched_vs_oracle(bla, imgs, Cin, H, W, F, k, s):
     b.bla_conv2d_wgrad(dxd, dyd, dkd, imgs, Cin, H, W, F, k, s)
     b.bla_conv2d_dgrad(dyd, dwd, dxo, imgs, Cin, H, W, F, k, s)
     assert b.bla_h2d_bytes() == h2d0                       # device-resident: nothing staged
-    assert rel_err(_host(b, yd, y.shape), y) <= FP32_TOL
-    assert rel_err(_host(b, dkd, kr.shape), dk) <= FP32_TOL
-    assert rel_err(_host(b, dxo, x.shape), dx) <= FP32_TOL
+    assert rel_err(_host(b, yd, y.shape), y) <= tol, rel_err(_host(b, yd, y.shape), y)
+    assert rel_err(_host(b, dkd, kr.shape), dk) <= tol
+    assert rel_err(_host(b, dxo, x.shape), dx) <= tol, rel_err(_host(b, dxo, x.shape), dx)
     for d in (dxd, dwd, dyd, yd, dkd, dxo):
         b.bla_free(d)
 
