@@ -219,7 +219,10 @@ __global__ void __launch_bounds__(256) permute_weights_dgrad(const float* __rest
 __global__ void __launch_bounds__(256) permute_weights_taps(const float* __restrict__ w, float* out, int F, int C, int k2, int flip) {
     const size_t total = (size_t)F * C * k2;
     for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-        if (!flip) {
+        if (flip == 2) {      // inverse of the taps layout: out [F][C][k2] <- w [F][(tap, c)]
+            const int tap = (int)(e % k2), c = (int)((e / k2) % C), f = (int)(e / ((size_t)C * k2));
+            out[e] = w[((size_t)f * k2 + tap) * C + c];
+        } else if (!flip) {
             const int c = (int)(e % C), tap = (int)((e / C) % k2), f = (int)(e / ((size_t)C * k2));
             out[e] = w[((size_t)f * C + c) * k2 + tap];
         } else {
@@ -280,7 +283,7 @@ void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, i
     if (tensor_path_wanted() && F >= 64 && p.N >= 256 && C % 16 == 0) {
         // tcgen05 implicit GEMM: the im2col tile is gathered by 4-D TMA boxes (gemm_tc.cu, conv mode)
         float* wt = permuted_weights(w, F, C, k, 0, s);
-        const bool done = conv2d_tc(x, wt, y, imgs, C, H, W, F, k, stride, p.pad_top, p.pad_left, s);
+        const bool done = conv2d_tc(x, wt, y, imgs, C, H, W, 1, H, W, F, k, stride, p.pad_top, p.pad_left, s);
         pool_free(wt);
         if (done) return;
     }
@@ -292,6 +295,21 @@ void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, i
     p.M = F; p.N = C * k * k; p.K = imgs * p.Ho * p.Wo;
     p.a = dy; p.src = x; p.out = dw;
     if (p.M <= 0 || p.N <= 0) return;
+    if (tensor_path_wanted() && F >= 64 && p.K >= 1024) {
+        // tcgen05 implicit GEMM over the output pixels into the tap-major layout, then back to [F][C][k][k]
+        const size_t total = (size_t)F * C * k * k;
+        float* taps = (float*)pool_alloc(kDevice, total * sizeof(float));
+        const bool done = conv2d_wgrad_tc(x, dy, taps, imgs, C, H, W, F, k, stride, p.pad_top, p.pad_left, s);
+        if (done) {
+            size_t blocks = (total + 255) / 256, cap = (size_t)rt().num_sms * 8;
+            if (blocks > cap) blocks = cap;
+            permute_weights_taps<<<(int)blocks, 256, 0, s>>>(taps, dw, F, C, k * k, 2);
+            BLA_LAUNCH_CHECK();
+            count_launch();
+        }
+        pool_free(taps);
+        if (done) return;
+    }
     const int sms = rt().num_sms;
     const long long tiles = (long long)ceil_div(p.M, 64) * ceil_div(p.N, 64);
     int splits = 1;
@@ -325,10 +343,12 @@ void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, i
     ConvP p = base_params(imgs, C, H, W, F, k, stride);
     p.M = C; p.N = imgs * H * W; p.K = F * k * k;
     if (p.M <= 0 || p.N <= 0) return;
-    if (stride == 1 && (k & 1) && tensor_path_wanted() && C >= 64 && p.N >= 256 && F % 16 == 0) {
-        // stride 1, odd kernel: dgrad is the SAME-padded forward convolution of dy with the flipped, transposed filters
+    if (tensor_path_wanted() && C >= 64 && p.N >= 256 && F % 16 == 0) {
+        // dgrad is a stride-1 convolution of dy -- spread out with stride-1 zeros between its pixels when the forward conv was
+        // strided -- with the flipped, transposed filters: dx[i] = sum_ki' dyu[i - (k-1-pad) + ki'] . w[k-1-ki'].  (For stride 2
+        // three quarters of the gathered values are zeros; still several times faster than the FP32 FMA kernel.)
         float* wf = permuted_weights(w, F, C, k, 1, s);
-        const bool done = conv2d_tc(dy, wf, dx, imgs, F, H, W, C, k, 1, (k - 1) / 2, (k - 1) / 2, s);
+        const bool done = conv2d_tc(dy, wf, dx, imgs, F, p.Ho, p.Wo, stride, H, W, C, k, 1, k - 1 - p.pad_top, k - 1 - p.pad_left, s);
         pool_free(wf);
         if (done) return;
     }

@@ -68,7 +68,9 @@ struct TcParams {
     int cluster;             // 1, or 2: CTA PAIRS (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages only HALF of B
     // implicit-GEMM convolution (conv != 0): B[k'][n] is gathered from x [img][C][H][W] by 4-D TMA boxes, k' = (ki, kj, c)
     // and n = (img, oi, oj); C is y [img][F][P] written by 3-D TMA boxes.  See conv2d_forward_tc().
-    int conv, cv_P, cv_Wo, cv_stride, cv_pad_top, cv_pad_left, cv_k, cv_cblocks, cv_bw, cv_bh;
+    // conv == 2 is the weight gradient: A = dy [img][F][P] (3-D boxes, K-major, k = pixel), B[k = pixel][n = (ki, kj, c)] gathered from
+    // the same padded NHWC input as MN-major atoms of 32 channels x 16 pixels; C = dW [F][(ki, kj, c)] through the plain GEMM epilogue.
+    int conv, cv_P, cv_Wo, cv_stride, cv_pad_top, cv_pad_left, cv_k, cv_cblocks, cv_bw, cv_bh, cv_C;
     int debug;               // BLA_TC_DEBUG: 1 = no split (1xTF32: hi.hi only), for bottleneck experiments
 };
 
@@ -112,6 +114,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
@@ -315,7 +321,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (p.conv) {
+        if (p.conv == 1) {
             // Implicit im2col, whole warp: lane `at` owns the at-th 32-pixel atom of the tile's B columns.  Its pixel
             // coordinates are decoded ONCE per tile (three integer divisions); per k-block = 16 channels of one filter tap
             // (ki, kj) every lane only adds the tap to its box origin and issues ONE 4-D box {16 c, bw, bh, images} of the
@@ -344,6 +350,40 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     if (lane < natoms && p.debug != 2)   // debug 2: no gather (the host drops the B bytes from the expected count)
                         tma_load_4d(sb + lane * (BK * 128), &tma_b, cb * BK, x0 + kj, y0 + ki, img, bar_full(stage));
                     if (++cb == p.cv_cblocks) { cb = 0; if (++kj == p.cv_k) { kj = 0; ++ki; } }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (p.conv == 2) {
+            // Weight gradient, whole warp: the contraction runs over the output pixels.  k-block = 16 consecutive pixels of
+            // one image; lane `at` owns the at-th 32-column atom of the tile = 32 channels of one filter tap (decoded once per
+            // tile) and issues ONE box {32 c, bw, bh, 1} of the padded NHWC input shifted by its tap = 16 MN-major rows of
+            // 128 bytes; lane 0 also loads the 128 x 16 tile of dy (3-D box {16 pixels, 128 filters, 1 image}).
+            const int ncols = p.bn / cl, natoms = ncols / 32;
+            const int blocks_per_img = p.cv_P / BK;
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+                int split, m0, n0;
+                decode(tile, split, m0, n0);
+                const int kb0 = split * p.kblocks_per_split, kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
+                const int nn = n0 + (int)rank * ncols * (cl - 1) + 32 * lane;
+                const int tap = nn / p.cv_C, c0 = nn - tap * p.cv_C;
+                const int ki = tap / p.cv_k, kj = tap - ki * p.cv_k;
+                const int dx = kj - p.cv_pad_left, dy = ki - p.cv_pad_top;
+                int img = kb0 / blocks_per_img, pix0 = (kb0 - img * blocks_per_img) * BK;
+                int oi0 = pix0 / p.cv_Wo, oj0 = pix0 - oi0 * p.cv_Wo;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                    if (lane == 0) {
+                        mbar_wait(bar_empty(stage), phase ^ 1);
+                        mbar_arrive_expect_tx(bar_full(stage), p.stage_tx_bytes);
+                        tma_load_3d(sa, &tma_a, pix0, m0, img, bar_full(stage));
+                    }
+                    __syncwarp();
+                    if (lane < natoms)
+                        tma_load_4d(sb + lane * (BK * 128), &tma_b, c0, oj0 * p.cv_stride + dx, oi0 * p.cv_stride + dy, img, bar_full(stage));
+                    pix0 += BK; oj0 += BK;
+                    while (oj0 >= p.cv_Wo) { oj0 -= p.cv_Wo; ++oi0; }
+                    if (pix0 == p.cv_P) { pix0 = 0; oi0 = 0; oj0 = 0; ++img; }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -600,7 +640,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        if (!p.conv) {
+                        if (p.conv != 1) {
                             tma_store_2d(&tma_c, col0, (p.partial ? split * p.m : 0) + row_base, stg_u32 + sbuf * 4096);
                         } else {
                             const int img = col0 / p.cv_P, pix = col0 - img * p.cv_P;
@@ -814,6 +854,32 @@ bool make_map_conv_in(CUtensorMap* map, const ConvTc& cv, int bw, int bh) {
     return r == CUDA_SUCCESS;
 }
 
+// Weight gradient, B operand: the same padded NHWC input as MN-major atoms -- a box {32 c, bw*s, bh*s, 1} with traversal strides
+// {1, s, s, 1} lands as 16 (output pixels = k) rows of 32 channels = 128 bytes, 32-byte swizzle atoms (the layout the tensor core
+// wants for MN-major 32-bit operands).
+bool make_map_conv_in_mn(CUtensorMap* map, const ConvTc& cv) {
+    const int bw = cv.Wo < BK ? cv.Wo : BK, bh = BK / bw;
+    cuuint64_t dims[4] = {(cuuint64_t)cv.C, (cuuint64_t)cv.W, (cuuint64_t)cv.H, (cuuint64_t)cv.imgs};
+    cuuint64_t strides[3] = {(cuuint64_t)cv.C * 4, (cuuint64_t)cv.W * cv.C * 4, (cuuint64_t)cv.H * cv.W * cv.C * 4};
+    cuuint32_t box[4] = {32u, (cuuint32_t)(bw * cv.stride), (cuuint32_t)(bh * cv.stride), 1u};
+    cuuint32_t elem[4] = {1u, (cuuint32_t)cv.stride, (cuuint32_t)cv.stride, 1u};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)cv.in, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// Weight gradient, A operand: dy [img][F][P] as {P, F, img}; a box {16 pixels, 128 filters, 1} is a K-major 128 x 16 tile.
+bool make_map_conv_dy(CUtensorMap* map, const float* dy, const ConvTc& cv) {
+    const int P = cv.Ho * cv.Wo;
+    cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)cv.F, (cuuint64_t)cv.imgs};
+    cuuint64_t strides[2] = {(cuuint64_t)P * 4, (cuuint64_t)cv.F * P * 4};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1u};
+    cuuint32_t elem[3] = {1u, 1u, 1u};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)dy, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // 3-D map over the conv output y [img][F][P] for the epilogue's 32 (filters) x 32 (pixels) tiles: {P, F, img} when an
 // image has at least 32 pixels, {P, img, F} when a tile spans several small images.
 bool make_map_conv_out(CUtensorMap* map, const ConvTc& cv) {
@@ -843,13 +909,14 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     if (g_tc_broken || !encode_fn()) return false;
     if (g.m <= 0 || g.n <= 0 || g.k <= 0) return false;
     // TMA needs 16-byte aligned bases and row pitches
-    if (((uintptr_t)g.a & 15) || (g.lda & 3)) return false;
+    const int cmode = g.conv ? g.conv->mode : 0;   // 0 plain GEMM, 1 conv forward, 2 conv weight gradient
+    if (((uintptr_t)g.a & 15) || (cmode != 2 && (g.lda & 3))) return false;
     if (!g.conv && (((uintptr_t)g.b & 15) || (g.ldb & 3))) return false;
 
     TcParams p{};
     p.m = g.m; p.n = g.n; p.k = g.k;
     p.a_kmajor = !g.ta;           // A row-major [m][k]  -> K-major;  stored [k][m] -> MN-major
-    p.b_kmajor = g.conv ? true : g.tb;    // B stored [n][k] (and the NHWC conv gather) -> K-major;  row-major [k][n] -> MN-major
+    p.b_kmajor = g.conv ? cmode == 1 : g.tb;   // B stored [n][k] (and the forward conv's NHWC gather) -> K-major;  row-major [k][n] -> MN-major
     p.c = g.c; p.ldc = g.ldc; p.epi = g.epi;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("BLA_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     p.c_vec = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 4 == 0);
@@ -868,7 +935,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
       p.cluster = (en && p.m_tiles >= 2 && p.m_tiles % 2 == 0 && g.k >= 512) ? 2 : 1; }
     if (g.conv) {
         const ConvTc& cv = *g.conv;
-        p.conv = 1; p.cv_P = cv.Ho * cv.Wo; p.cv_Wo = cv.Wo; p.cv_stride = cv.stride; p.cv_pad_top = cv.pad_top; p.cv_pad_left = cv.pad_left;
+        p.conv = cmode; p.cv_C = cv.C; p.cv_P = cv.Ho * cv.Wo; p.cv_Wo = cv.Wo; p.cv_stride = cv.stride; p.cv_pad_top = cv.pad_top; p.cv_pad_left = cv.pad_left;
         p.cv_k = cv.k; p.cv_cblocks = cv.C / BK;
         p.cv_bw = cv.Wo < 32 ? cv.Wo : 32;
         p.cv_bh = 32 / p.cv_bw < cv.Ho ? 32 / p.cv_bw : cv.Ho;
@@ -880,7 +947,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         double best_cost = -1.0;
         int best_bn = BN;
         // conv has no split-K: a small batch of small images is spread over the SMs by narrower tiles instead
-        for (int bn = BN; bn >= (g.conv ? gran : 192); bn -= gran) {
+        for (int bn = BN; bn >= (cmode == 1 ? gran : 192); bn -= gran) {
             const long long units_ = (long long)m_units * ceil_div(g.n, bn);
             const long long waves = (units_ + slots - 1) / slots;
             // measured on B200 (square 4096): a 192-wide tile costs 1.33x more per column than a 256-wide one
@@ -896,15 +963,18 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     if (p.conv && p.debug == 2) p.stage_tx_bytes = kABytes;
 
     CUtensorMap ma, mb;
-    bool ok = p.a_kmajor ? make_map(&ma, g.a, g.m, g.k, g.lda, BM, false) : make_map(&ma, g.a, g.k, g.m, g.lda, BK, true);
-    if (g.conv) ok = ok && make_map_conv_in(&mb, *g.conv, p.cv_bw, p.cv_bh);
+    bool ok;
+    if (cmode == 2) ok = make_map_conv_dy(&ma, g.a, *g.conv);
+    else ok = p.a_kmajor ? make_map(&ma, g.a, g.m, g.k, g.lda, BM, false) : make_map(&ma, g.a, g.k, g.m, g.lda, BK, true);
+    if (cmode == 1) ok = ok && make_map_conv_in(&mb, *g.conv, p.cv_bw, p.cv_bh);
+    else if (cmode == 2) ok = ok && make_map_conv_in_mn(&mb, *g.conv);
     else ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, p.bn / p.cluster, false) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
     if (!ok) return false;
 
     const int sms = rt().num_sms;
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     int splits = 1;
-    if (!g.conv && tiles * 2 <= sms && p.kblocks >= 32) {
+    if (cmode != 1 && tiles * 2 <= sms && p.kblocks >= 32) {
         long long want = (sms / p.cluster) / (tiles / p.cluster);          // one wave: units * splits <= cluster slots
         long long maxs = p.kblocks / 16;
         splits = (int)(want < maxs ? want : maxs);
@@ -924,7 +994,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     memset(&mc, 0, sizeof(mc));
     p.tma_store = p.c_vec && !g.epi.pre_activation && !g.epi.bias_cols &&
                   (splits == 1 || (g.m % BM == 0 && g.n % 4 == 0));
-    if (g.conv) {
+    if (cmode == 1) {
         p.tma_store = make_map_conv_out(&mc, *g.conv);
         if (!p.tma_store) { if (ws) pool_free(ws); return false; }
     } else if (p.tma_store) {
@@ -979,31 +1049,51 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     return true;
 }
 
-// NCHW -> zero-padded NHWC: xp[img][pt + i][pl + j][c] = x[img][c][i][j].  32 x 32 (channel x column) tiles through shared
-// memory so that both the reads (along j) and the writes (along c) are coalesced; the border was zeroed by a memset.
+// NCHW -> zero-padded (and optionally zero-dilated) NHWC: xp[img][pt + i*dil][pl + j*dil][c] = x[img][c][i][j], every other
+// element of xp = 0.  One block row per padded image row; 32 x 32 (channel x padded column) tiles through shared memory so
+// that both the reads (along j) and the writes (along c) are coalesced.  The kernel writes the zeros itself (no memset pass).
 __global__ void __launch_bounds__(256) nchw_to_padded_nhwc_kernel(const float* __restrict__ x, float* __restrict__ xp, int C, int H, int W,
-                                                                  int Hp, int Wp, int pt, int pl) {
+                                                                  int Hp, int Wp, int pt, int pl, int dil) {
     __shared__ float tile[32][33];
-    const int img = blockIdx.z, i = blockIdx.y;
-    const int tiles_c = C / 32 + (C % 32 != 0), tiles_w = (W + 31) / 32;
+    const int img = blockIdx.z, ip = blockIdx.y;
+    const int tiles_c = (C + 31) / 32, tiles_w = (Wp + 31) / 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int di = ip - pt;
+    const int i = di / dil;
+    const bool row_ok = di >= 0 && di - i * dil == 0 && i < H;
     for (int t = blockIdx.x; t < tiles_c * tiles_w; t += gridDim.x) {
         const int c0 = (t / tiles_w) * 32, j0 = (t % tiles_w) * 32;
+        const int dj = j0 + tx - pl;
+        const int j = dj / dil;
+        const bool col_ok = row_ok && dj >= 0 && dj - j * dil == 0 && j < W;
         for (int cc = ty; cc < 32; cc += 8) {
-            const int c = c0 + cc, j = j0 + tx;
-            tile[cc][tx] = (c < C && j < W) ? x[(((size_t)img * C + c) * H + i) * W + j] : 0.f;
+            const int c = c0 + cc;
+            tile[cc][tx] = (col_ok && c < C) ? x[(((size_t)img * C + c) * H + i) * W + j] : 0.f;
         }
         __syncthreads();
         for (int jj = ty; jj < 32; jj += 8) {
-            const int c = c0 + tx, j = j0 + jj;
-            if (c < C && j < W) xp[(((size_t)img * Hp + pt + i) * Wp + pl + j) * C + c] = tile[tx][jj];
+            const int c = c0 + tx, jp = j0 + jj;
+            if (c < C && jp < Wp) xp[(((size_t)img * Hp + ip) * Wp + jp) * C + c] = tile[tx][jj];
         }
         __syncthreads();
     }
 }
 
-bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int H, int W, int F, int k, int stride, int pad_top,
-               int pad_left, cudaStream_t s) {
+// the padded NHWC copy every tensor-path conv gathers from (pool block; free with pool_free, stream-ordered)
+float* padded_nhwc(const float* in, int imgs, int C, int H, int W, int Hp, int Wp, int pad_top, int pad_left, int dil, cudaStream_t s) {
+    float* xp = (float*)pool_alloc(kDevice, (size_t)imgs * Hp * Wp * C * sizeof(float));
+    int gx = (C + 31) / 32 * ((Wp + 31) / 32);
+    if (gx > 64) gx = 64;
+    nchw_to_padded_nhwc_kernel<<<dim3(gx, Hp, imgs), 256, 0, s>>>(in, xp, C, H, W, Hp, Wp, pad_top, pad_left, dil);
+    BLA_LAUNCH_CHECK();
+    count_launch();
+    return xp;
+}
+
+// out [imgs][F][Ho][Wo] = conv(in, w): `in` is [imgs][C][Hin][Win], placed at spacing `dil` (zeros between: the transposed conv of a
+// strided dgrad) and offset (pad_top, pad_left) inside a logical image of H x W, then convolved with stride `stride`.
+bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int Hin, int Win, int dil, int H, int W, int F, int k,
+               int stride, int pad_top, int pad_left, cudaStream_t s) {
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const int P = Ho * Wo;
     // eligibility: whole 16-channel k-blocks, 16-byte aligned rows, and 32-pixel atoms that tile the output exactly
@@ -1015,17 +1105,9 @@ bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C
     // element): every TMA box then starts inside the tensor, on a 16-channel (64-byte) boundary.
     const int Hp = (Ho - 1) * stride + k > H + pad_top ? (Ho - 1) * stride + k : H + pad_top;
     const int Wp = (Wo - 1) * stride + k > W + pad_left ? (Wo - 1) * stride + k : W + pad_left;
-    const size_t xp_elems = (size_t)imgs * Hp * Wp * C;
-    float* xp = (float*)pool_alloc(kDevice, xp_elems * sizeof(float));
-    BLA_CUDA(cudaMemsetAsync(xp, 0, xp_elems * sizeof(float), s));
-    {
-        int gx = (C + 31) / 32 * ((W + 31) / 32);
-        if (gx > 64) gx = 64;
-        nchw_to_padded_nhwc_kernel<<<dim3(gx, H, imgs), 256, 0, s>>>(in, xp, C, H, W, Hp, Wp, pad_top, pad_left);
-        BLA_LAUNCH_CHECK();
-        count_launch();
-    }
-    ConvTc cv{xp, out, imgs, C, Hp, Wp, F, k, stride, Ho, Wo, 0, 0};
+    if (pad_top + (Hin - 1) * dil + 1 > Hp || pad_left + (Win - 1) * dil + 1 > Wp) return false;
+    float* xp = padded_nhwc(in, imgs, C, Hin, Win, Hp, Wp, pad_top, pad_left, dil, s);
+    ConvTc cv{1, xp, out, imgs, C, Hp, Wp, F, k, stride, Ho, Wo, 0, 0};
     GemmArgs g{};
     g.m = F; g.n = imgs * P; g.k = k * k * C;
     g.a = w_taps; g.lda = g.k;
@@ -1033,6 +1115,29 @@ bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C
     g.conv = &cv;
     const bool done = gemm_3xtf32(g, s);
     pool_free(xp);   // stream-ordered reuse
+    return done;
+}
+
+// dw_taps [F][(ki, kj, c)] = sum over images and output pixels of dy[img][f][pixel] * x[img][c][pixel*stride + tap - pad]
+bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, int C, int H, int W, int F, int k, int stride, int pad_top,
+                     int pad_left, cudaStream_t s) {
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const int P = Ho * Wo;
+    // eligibility: 32-channel atoms, 16-pixel k-blocks inside one image that are whole box rows
+    if (C % 32 || P % BK || ((uintptr_t)x & 15) || ((uintptr_t)dy & 15) || ((uintptr_t)dw_taps & 15)) return false;
+    if (!(Wo % BK == 0 || (Wo < BK && BK % Wo == 0))) return false;
+    const int Hp = (Ho - 1) * stride + k > H + pad_top ? (Ho - 1) * stride + k : H + pad_top;
+    const int Wp = (Wo - 1) * stride + k > W + pad_left ? (Wo - 1) * stride + k : W + pad_left;
+    float* xp = padded_nhwc(x, imgs, C, H, W, Hp, Wp, pad_top, pad_left, 1, s);
+    ConvTc cv{2, xp, nullptr, imgs, C, Hp, Wp, F, k, stride, Ho, Wo, pad_top, pad_left};
+    cv.pad_top = 0; cv.pad_left = 0;     // the padding is inside xp
+    GemmArgs g{};
+    g.m = F; g.n = k * k * C; g.k = imgs * P;
+    g.a = dy; g.lda = P;
+    g.c = dw_taps; g.ldc = g.n;
+    g.conv = &cv;
+    const bool done = gemm_3xtf32(g, s);
+    pool_free(xp);
     return done;
 }
 

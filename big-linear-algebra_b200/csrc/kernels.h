@@ -40,7 +40,8 @@ void k_softmax_xent(const float* logits, const float* expected, int classes, int
 // ---- GEMM (gemm_simt.cu / gemm_tc.cu) ---------------------------------------------------------
 // Implicit-GEMM convolution on the tensor path: B is not a matrix but the NCHW input, gathered by TMA.
 struct ConvTc {
-    const float* in;      // [imgs][C][H][W]
+    int mode;             // 1 forward (B gathered K-major), 2 weight gradient (A = dy, B gathered MN-major)
+    const float* in;      // padded NHWC input [imgs][H][W][C]
     float* out;           // [imgs][F][Ho][Wo]
     int imgs, C, H, W, F, k, stride, Ho, Wo, pad_top, pad_left;
 };
@@ -59,8 +60,12 @@ void gemm(const GemmArgs& g, cudaStream_t s);
 void gemm_simt(const GemmArgs& g, cudaStream_t s);
 // returns false when the shape/alignment is not eligible for the tensor path
 bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s);
-// conv2d forward on the tensor path: out = conv(in, w) with w already arranged as [F][(ki, kj, c)]; false if ineligible
-bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int H, int W, int F, int k, int stride, int pad_top,
-               int pad_left, cudaStream_t s);
+// conv2d forward on the tensor path: out = conv(in, w) with w already arranged as [F][(ki, kj, c)]; false if ineligible.
+// `in` [imgs][C][Hin][Win] is placed at spacing `dil` inside a logical H x W image (dil = 1, Hin = H for an ordinary conv).
+bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int Hin, int Win, int dil, int H, int W, int F, int k,
+               int stride, int pad_top, int pad_left, cudaStream_t s);
+// weight gradient on the tensor path into dw_taps [F][(ki, kj, c)]; false if ineligible
+bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, int C, int H, int W, int F, int k, int stride, int pad_top,
+                     int pad_left, cudaStream_t s);
 
 }  // namespace bla
