@@ -400,6 +400,14 @@ def main():
         bound = "fp32-simt"
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "kernel": "layer-1 forward GEMM 256x784x%d (40%% of step flops)" % Bl, "ms_per_launch": gemm_ms, "peak_note": note}
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (taken at the N=1 shape, tensor path)
+    cap = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_dominant.json")
+    if used_tc and Bl == 60000 and os.path.isfile(cap):
+        with open(cap) as f:
+            cj = json.load(f)
+        roofline["traffic"] = cj["dram_bytes_read"] + cj["dram_bytes_write"]
+        roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum, %s; algorithmic minimum %.1f MB (X read once, "
+                                    "A1 written once, W1)" % (cj["source"], (DIMS[0] * Bl + DIMS[1] * Bl + DIMS[0] * DIMS[1]) * 4 / 1e6))
 
     extras = None
     if not args.no_extras and rank == 0 and world == 1:
