@@ -50,6 +50,13 @@ Layer._fields_ = [("num_nodes", C.c_int), ("nodes", MatrixP), ("raw_nodes", Matr
                   ("activation_ddx", ACT_FN), ("has_previous_layer", C.c_char), ("has_nodes", C.c_char)]
 
 
+class UnetConfig(C.Structure):
+    """include/bla.h bla_unet_config (model/cifar_unet.c:26-37)"""
+    _fields_ = [("image_side", C.c_int), ("dims", C.c_int * 4), ("time_dim", C.c_int), ("kernel_size", C.c_int),
+                ("group_size", C.c_int), ("key_dim", C.c_int), ("dropout", C.c_float), ("max_imgs", C.c_int),
+                ("seed", C.c_ulonglong)]
+
+
 class Epilogue(C.Structure):
     """bla_epilogue of include/bla.h."""
     _fields_ = [("bias_rows", C.c_void_p), ("bias_cols", C.c_void_p), ("pre_activation", C.c_void_p),
@@ -148,6 +155,23 @@ PROTOTYPES = {
     "bla_conv2d_dgrad": (None, [C.c_void_p] * 3 + [C.c_int] * 7),
     "bla_group_norm": (None, [C.c_void_p] * 4 + [C.c_int] * 4),
     "bla_group_norm_ddx": (None, [C.c_void_p] * 5 + [C.c_int] * 4),
+    # include/bla.h -- fused self attention
+    "bla_attention_forward": (None, [C.c_void_p] * 9 + [C.c_int] * 3),
+    "bla_attention_backward": (None, [C.c_void_p] * 11 + [C.c_int] * 3),
+    # include/bla.h -- CIFAR U-Net trainer
+    "bla_unet_create": (C.c_void_p, [C.POINTER(UnetConfig)]),
+    "bla_unet_destroy": (None, [C.c_void_p]),
+    "bla_unet_num_params": (C.c_size_t, [C.c_void_p]),
+    "bla_unet_num_tensors": (C.c_int, [C.c_void_p]),
+    "bla_unet_tensor_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "bla_unet_tensor_offset": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "bla_unet_tensor_size": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "bla_unet_init_params": (None, [C.c_void_p, C.c_ulonglong]),
+    "bla_unet_set_params": (None, [C.c_void_p, C.c_void_p]),
+    "bla_unet_get_params": (None, [C.c_void_p, C.c_void_p]),
+    "bla_unet_get_grads": (None, [C.c_void_p, C.c_void_p]),
+    "bla_unet_forward": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "bla_unet_train_step": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     # include/bla.h -- MNIST MLP trainer
     "bla_mlp_create": (C.c_void_p, [C.POINTER(C.c_int), C.c_int]),
     "bla_mlp_destroy": (None, [C.c_void_p]),

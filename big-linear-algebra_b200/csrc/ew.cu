@@ -252,14 +252,7 @@ void k_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t 
 // ---------------------------------------------------------------------------------------------
 // synthetic data: counter-based generator (splitmix64 of seed + index), identical on host/device
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline float uniform_at(unsigned long long seed, unsigned long long i, float lo, float hi) {
-    unsigned long long z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    float u = (float)(z >> 40) * (1.0f / 16777216.0f);  // 24 bits -> [0,1)
-    return fmaf(hi - lo, u, lo);  // explicit fma: same bits from nvcc and from the host compiler
-}
+// uniform_at() lives in kernels.h (shared with the U-Net's dropout mask)
 
 namespace {
 __global__ void __launch_bounds__(kThreads) fill_uniform_kernel(float* dst, size_t n, unsigned long long seed, float lo, float hi) {

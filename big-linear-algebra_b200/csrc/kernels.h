@@ -68,4 +68,23 @@ bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C
 bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, int C, int H, int W, int F, int k, int stride, int pad_top,
                      int pad_left, cudaStream_t s);
 
+// ---- batched device-resident conv2d / group norm (conv_implicit.cu, api_norm.cu) ----------------
+void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s);
+void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s);
+void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s);
+void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int images, int C, int HW, int group_size, int quirk,
+                      cudaStream_t s);
+void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* means, const float* stdevs, int images, int C, int HW,
+                      int group_size, cudaStream_t s);
+
+// counter-based generator (splitmix64 of seed + index), identical on host and device
+__host__ __device__ inline float uniform_at(unsigned long long seed, unsigned long long i, float lo, float hi) {
+    unsigned long long z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    float u = (float)(z >> 40) * (1.0f / 16777216.0f);  // 24 bits -> [0,1)
+    return fmaf(hi - lo, u, lo);  // explicit fma: same bits from nvcc and from the host compiler
+}
+
 }  // namespace bla

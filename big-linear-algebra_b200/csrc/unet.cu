@@ -1,0 +1,859 @@
+// unet.cu -- model/cifar_unet.c as a batched, device-resident training step (include/bla.h "CIFAR U-Net trainer",
+// SURVEY.md 8(f) N1 + N4).
+//
+// The reference runs ONE image at a time through ~46 conv() calls, 45 group norms, 5 attention blocks and a page of
+// model-local host loops (cifar_unet.c:999-1437), every channel plane its own malloc.  Here a whole batch lives in HBM
+// as NCHW tensors [images][C][H*W] and one step is a fixed sequence of launches on the library stream:
+//   conv / conv_ddx        -> conv2d_forward / wgrad / dgrad   (implicit GEMM, tcgen05 3xTF32 or FP32 FMA, conv_implicit.cu)
+//   group_norm(+_ddx)      -> k_group_norm_fwd / bwd           (api_norm.cu, batched over images)
+//   time dense             -> one GEMM with the bias in the epilogue + a per-plane broadcast add
+//   self attention         -> 1 batched transpose, 1 GEMM for Q|K|V, ONE fused scores/softmax/PV kernel per block,
+//                             1 GEMM (+bias) for the output projection; backward = 2 fused kernels + 4 GEMMs
+//   model-local loops      -> ReLU / ReLU' / dropout mask / nearest-neighbour up-sampling and its adjoint / concat and
+//                             split of skip connections / residual adds / MSE gradient, as device kernels
+// and parameters / gradients are two flat buffers (one SGD axpy, one NCCL all-reduce when data-parallel).
+//
+// The graph is the reference's forward() (cifar_unet.c:1099-1168) node for node; where the reference's WIP backward()
+// is wrong (gradients written over the weights, _softmax_ddx fed the pre-softmax scores, up_3 attention 2
+// running with attention 1's parameters, an uninitialised time embedding) the mathematically intended adjoint is
+// implemented instead and validated against float64 autograd (tests/test_unet_gpu.py).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "runtime.h"
+
+namespace bla {
+bool comm_active();
+void comm_allreduce_f32_on(float* buf, size_t n, cudaStream_t s);
+void comm_allreduce_f64_on(double* buf, size_t n, cudaStream_t s);
+void gemm(const GemmArgs& g, cudaStream_t s);
+}  // namespace bla
+
+using namespace bla;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(size_t items, int per_block) {
+    size_t blocks = (items + per_block - 1) / per_block, cap = (size_t)rt().num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    return blocks < 1 ? 1 : (int)blocks;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- model-local loops ---------------------------------------------------------------------------------------------
+
+// cifar_unet.c:1192-1197: time-bias gradient = per-plane total.  One warp per (image, channel) plane.
+__global__ void __launch_bounds__(kThreads) plane_sum_kernel(const float* __restrict__ t, int planes, int hw, float* __restrict__ out) {
+    const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * kThreads) >> 5;
+    for (int p = warp; p < planes; p += nwarps) {
+        const float* src = t + (size_t)p * hw;
+        float a = 0.f;
+        if ((hw & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            for (int i = lane; i < hw / 4; i += 32) { const float4 v = s4[i]; a += (v.x + v.y) + (v.z + v.w); }
+        } else {
+            for (int i = lane; i < hw; i += 32) a += src[i];
+        }
+        a = warp_sum(a);
+        if (lane == 0) out[p] = a;
+    }
+}
+
+// cifar_unet.c:1032-1042 (_dropout): y = u < rate ? 0 : x with u from the library's counter-based generator
+__global__ void __launch_bounds__(kThreads) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, unsigned long long seed,
+                                                           float rate) {
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
+        y[i] = uniform_at(seed, i, 0.f, 1.f) < rate ? 0.f : x[i];
+}
+
+// cifar_unet.c:1074-1086 (_nearest_neighbours, scale 2): out[p][i][j] = in[p][i/2][j/2]
+__global__ void __launch_bounds__(kThreads) upsample2_kernel(const float* __restrict__ in, float* __restrict__ out, size_t planes, int h, int w) {
+    const size_t total = planes * (size_t)h * w;   // one thread per INPUT element: writes a 2x2 block
+    for (size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (size_t)gridDim.x * kThreads) {
+        const int j = (int)(e % w), i = (int)((e / w) % h);
+        const size_t p = e / ((size_t)w * h);
+        const float v = in[e];
+        float* o = out + (p * 2 * h + 2 * i) * (size_t)(2 * w) + 2 * j;
+        *reinterpret_cast<float2*>(o) = make_float2(v, v);
+        *reinterpret_cast<float2*>(o + 2 * w) = make_float2(v, v);
+    }
+}
+// cifar_unet.c:1228-1243 (_nearest_neighbours_ddx): din[p][i][j] (+)= the 2x2 block of dout
+__global__ void __launch_bounds__(kThreads) upsample2_backward_kernel(const float* __restrict__ dout, float* __restrict__ din, size_t planes, int h,
+                                                                      int w, int accumulate) {
+    const size_t total = planes * (size_t)h * w;
+    for (size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (size_t)gridDim.x * kThreads) {
+        const int j = (int)(e % w), i = (int)((e / w) % h);
+        const size_t p = e / ((size_t)w * h);
+        const float* o = dout + (p * 2 * h + 2 * i) * (size_t)(2 * w) + 2 * j;
+        const float2 a = *reinterpret_cast<const float2*>(o), b = *reinterpret_cast<const float2*>(o + 2 * w);
+        const float v = (a.x + a.y) + (b.x + b.y);
+        din[e] = accumulate ? din[e] + v : v;
+    }
+}
+
+// cifar_unet.c:1088-1097 (_concat_skip) and :1337-1349 (_split_concat): `rows` slabs of `width` floats (multiple of 4) between
+// two pitched tensors, copy or accumulate
+__global__ void __launch_bounds__(kThreads) slab_kernel(float* __restrict__ dst, size_t dpitch, const float* __restrict__ src, size_t spitch,
+                                                        size_t width4, int rows, int accumulate) {
+    const size_t total = width4 * rows;
+    for (size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (size_t)gridDim.x * kThreads) {
+        const size_t r = e / width4, c = e - r * width4;
+        const float4 v = reinterpret_cast<const float4*>(src + r * spitch)[c];
+        float4* d = reinterpret_cast<float4*>(dst + r * dpitch) + c;
+        if (accumulate) { const float4 o = *d; *d = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w); }
+        else *d = v;
+    }
+}
+
+// reshape_channels_matrix / reshape_matrix_channels (lib/conv.c:174-203) for a batch: [b][r][c] -> [b][c][r]
+__global__ void __launch_bounds__(kThreads) transpose_batched_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* s = src + (size_t)b * rows * cols;
+    float* d = dst + (size_t)b * rows * cols;
+    for (int rr = ty; rr < 32; rr += 8)
+        if (r0 + rr < rows && c0 + tx < cols) tile[rr][tx] = s[(size_t)(r0 + rr) * cols + c0 + tx];
+    __syncthreads();
+    for (int cc = ty; cc < 32; cc += 8)
+        if (c0 + cc < cols && r0 + tx < rows) d[(size_t)(c0 + cc) * rows + r0 + tx] = tile[tx][cc];
+}
+
+// cifar_unet.c:1353-1365 + :1858-1872: dY = 2 (out - noise); loss_sum += sum over images of mean squared residual
+__global__ void __launch_bounds__(kThreads) mse_grad_kernel(const float* __restrict__ out, const float* __restrict__ noise, float* __restrict__ dy,
+                                                            size_t n, float inv_per_image, double* loss_sum) {
+    __shared__ float red[kThreads / 32];
+    float acc = 0.f;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const float r = out[i] - noise[i];
+        dy[i] = 2.f * r;
+        acc = fmaf(r, r, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) atomicAdd(loss_sum, (double)t * inv_per_image);
+    }
+}
+
+// ---- self attention (cifar_unet.c:999-1022, :1261-1335): S = H*W tokens, one head of width D = 16 ------------------
+constexpr int kD = 16;          // SELF_ATTENTION_KEY_DIM (cifar_unet.c:36)
+constexpr int kAttnRows = 32;   // query rows per CTA
+
+// qkv [imgs*S][3*kD] (Q | K | V), probs [imgs][S][S] (softmax output, kept for the backward pass), att [imgs*S][kD].
+// grid (S / kAttnRows, imgs), 256 threads: K and V of the image sit in shared memory (rows padded to 17 floats), one warp
+// per query row: lane j scores keys j, j+32, ..., warp-shuffle max / sum, then lane (half, d) sums P.V over half the keys.
+__global__ void __launch_bounds__(kThreads) attention_forward_kernel(const float* __restrict__ qkv, float* __restrict__ probs,
+                                                                     float* __restrict__ att, int S, float scale) {
+    extern __shared__ float sm[];
+    float* Ks = sm;                       // [S][17]
+    float* Vs = Ks + (size_t)S * 17;      // [S][17]
+    float* Ps = Vs + (size_t)S * 17;      // [8 warps][S]
+    const int img = blockIdx.y, r0 = blockIdx.x * kAttnRows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* base = qkv + (size_t)img * S * (3 * kD);
+    for (int e = threadIdx.x; e < S * kD; e += kThreads) {
+        const int j = e / kD, d = e - j * kD;
+        Ks[j * 17 + d] = base[(size_t)j * (3 * kD) + kD + d];
+        Vs[j * 17 + d] = base[(size_t)j * (3 * kD) + 2 * kD + d];
+    }
+    __syncthreads();
+    float* P = Ps + warp * S;
+    for (int r = r0 + warp; r < min(S, r0 + kAttnRows); r += kThreads / 32) {
+        float q[kD];
+#pragma unroll
+        for (int d = 0; d < kD; ++d) q[d] = base[(size_t)r * (3 * kD) + d];
+        float mx = -INFINITY;
+        for (int j = lane; j < S; j += 32) {
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < kD; ++d) s = fmaf(q[d], Ks[j * 17 + d], s);
+            s *= scale;
+            P[j] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < S; j += 32) { const float e = expf(P[j] - mx); P[j] = e; sum += e; }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        float* prow = probs + ((size_t)img * S + r) * S;
+        for (int j = lane; j < S; j += 32) { const float pv = P[j] * inv; P[j] = pv; prow[j] = pv; }
+        __syncwarp();
+        const int d = lane & 15, half = lane >> 4;
+        float o = 0.f;
+        for (int j = half; j < S; j += 2) o = fmaf(P[j], Vs[j * 17 + d], o);
+        o += __shfl_xor_sync(0xffffffffu, o, 16);
+        if (lane < kD) att[((size_t)img * S + r) * kD + d] = o;
+        __syncwarp();
+    }
+}
+
+// Row-wise half of the backward pass.  dA = gradient w.r.t. the attention output [imgs*S][kD].
+//   dS_ij = dA_i . V_j;  dI_ij = P_ij (dS_ij - sum_j P_ij dS_ij) * scale   (softmax Jacobian, then the 1/sqrt(d) scaling)
+//   dQ_i  = sum_j dI_ij K_j
+// dI overwrites a scratch [imgs][S][S]; dqkv [imgs*S][3*kD] receives dQ in its first kD columns.
+__global__ void __launch_bounds__(kThreads) attention_backward_rows_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
+                                                                           const float* __restrict__ dA, float* __restrict__ dI,
+                                                                           float* __restrict__ dqkv, int S, float scale) {
+    extern __shared__ float sm[];
+    float* Ks = sm;
+    float* Vs = Ks + (size_t)S * 17;
+    float* Ps = Vs + (size_t)S * 17;
+    const int img = blockIdx.y, r0 = blockIdx.x * kAttnRows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* base = qkv + (size_t)img * S * (3 * kD);
+    for (int e = threadIdx.x; e < S * kD; e += kThreads) {
+        const int j = e / kD, d = e - j * kD;
+        Ks[j * 17 + d] = base[(size_t)j * (3 * kD) + kD + d];
+        Vs[j * 17 + d] = base[(size_t)j * (3 * kD) + 2 * kD + d];
+    }
+    __syncthreads();
+    float* T = Ps + warp * S;
+    for (int r = r0 + warp; r < min(S, r0 + kAttnRows); r += kThreads / 32) {
+        float g[kD];
+#pragma unroll
+        for (int d = 0; d < kD; ++d) g[d] = dA[((size_t)img * S + r) * kD + d];
+        const float* prow = probs + ((size_t)img * S + r) * S;
+        float dot = 0.f;
+        for (int j = lane; j < S; j += 32) {
+            float ds = 0.f;
+#pragma unroll
+            for (int d = 0; d < kD; ++d) ds = fmaf(g[d], Vs[j * 17 + d], ds);
+            T[j] = ds;
+            dot = fmaf(prow[j], ds, dot);
+        }
+        dot = warp_sum(dot);
+        float* irow = dI + ((size_t)img * S + r) * S;
+        for (int j = lane; j < S; j += 32) { const float v = prow[j] * (T[j] - dot) * scale; T[j] = v; irow[j] = v; }
+        __syncwarp();
+        const int d = lane & 15, half = lane >> 4;
+        float o = 0.f;
+        for (int j = half; j < S; j += 2) o = fmaf(T[j], Ks[j * 17 + d], o);
+        o += __shfl_xor_sync(0xffffffffu, o, 16);
+        if (lane < kD) dqkv[((size_t)img * S + r) * (3 * kD) + d] = o;
+        __syncwarp();
+    }
+}
+
+// Column-wise half: dK_j = sum_i dI_ij Q_i,  dV_j = sum_i P_ij dA_i.  grid (S / 32, imgs): a CTA owns 32 key columns, walks the
+// query rows in tiles of 32 (tiles of dI and P transposed through shared memory), thread (j, d-group) keeps 4 + 4 sums.
+__global__ void __launch_bounds__(kThreads) attention_backward_cols_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
+                                                                           const float* __restrict__ dA, const float* __restrict__ dI,
+                                                                           float* __restrict__ dqkv, int S) {
+    __shared__ float It[32][33], Pt[32][33], Qs[32][kD + 1], As[32][kD + 1];
+    const int img = blockIdx.y, j0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty: 0..7
+    const int j = threadIdx.x >> 3, dg = (threadIdx.x & 7) * 2;   // thread -> (column j, two d's) for K and for V
+    float ak[2] = {0.f, 0.f}, av[2] = {0.f, 0.f};
+    for (int i0 = 0; i0 < S; i0 += 32) {
+        for (int rr = ty; rr < 32; rr += 8) {
+            const size_t row = ((size_t)img * S + i0 + rr) * S + j0 + tx;
+            const bool ok = i0 + rr < S && j0 + tx < S;
+            It[rr][tx] = ok ? dI[row] : 0.f;
+            Pt[rr][tx] = ok ? probs[row] : 0.f;
+        }
+        for (int e = threadIdx.x; e < 32 * kD; e += kThreads) {
+            const int rr = e / kD, d = e - rr * kD;
+            const bool ok = i0 + rr < S;
+            Qs[rr][d] = ok ? qkv[((size_t)img * S + i0 + rr) * (3 * kD) + d] : 0.f;
+            As[rr][d] = ok ? dA[((size_t)img * S + i0 + rr) * kD + d] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const float di = It[i][j], pi = Pt[i][j];
+            ak[0] = fmaf(di, Qs[i][dg], ak[0]); ak[1] = fmaf(di, Qs[i][dg + 1], ak[1]);
+            av[0] = fmaf(pi, As[i][dg], av[0]); av[1] = fmaf(pi, As[i][dg + 1], av[1]);
+        }
+        __syncthreads();
+    }
+    if (j0 + j < S) {
+        float* o = dqkv + ((size_t)img * S + j0 + j) * (3 * kD);
+        o[kD + dg] = ak[0]; o[kD + dg + 1] = ak[1];
+        o[2 * kD + dg] = av[0]; o[2 * kD + dg + 1] = av[1];
+    }
+}
+
+// ---- launch helpers ------------------------------------------------------------------------------------------------
+void slab(float* dst, size_t dpitch, const float* src, size_t spitch, size_t width, int rows, bool accumulate, cudaStream_t s) {
+    if (width % 4) die("bla: U-Net slabs must be multiples of 4 floats, exiting");
+    slab_kernel<<<grid_for(width / 4 * rows, kThreads), kThreads, 0, s>>>(dst, dpitch, src, spitch, width / 4, rows, accumulate ? 1 : 0);
+    BLA_LAUNCH_CHECK();
+    count_launch();
+}
+void transpose_batched(const float* src, float* dst, int batch, int rows, int cols, cudaStream_t s) {
+    transpose_batched_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32), batch), kThreads, 0, s>>>(src, dst, rows, cols);
+    BLA_LAUNCH_CHECK();
+    count_launch();
+}
+void gemm_plain(bool ta, bool tb, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c, int ldc,
+                const float* bias_cols, cudaStream_t s) {
+    GemmArgs g{};
+    g.ta = ta; g.tb = tb; g.m = m; g.n = n; g.k = k;
+    g.a = a; g.lda = lda; g.b = b; g.ldb = ldb; g.c = c; g.ldc = ldc;
+    g.epi.bias_cols = bias_cols;
+    gemm(g, s);
+}
+
+// _forward_attention (cifar_unet.c:999-1022) for a batch: x [imgs][C][S] -> out [imgs][C][S]; z, qkv, probs, att are kept for
+// the backward pass; `dense` is scratch [imgs*S][C]
+void attn_forward(const float* x, const float* wqkv, const float* wo, const float* bo, float* z, float* qkv, float* probs, float* att,
+                  float* dense, float* out, int imgs, int Cn, int S, cudaStream_t s) {
+    transpose_batched(x, z, imgs, Cn, S, s);                                                          // (C, H*W) -> (H*W, C)
+    gemm_plain(false, false, imgs * S, 3 * kD, Cn, z, Cn, wqkv, 3 * kD, qkv, 3 * kD, nullptr, s);
+    const size_t smem = ((size_t)2 * S * 17 + (kThreads / 32) * S) * sizeof(float);
+    attention_forward_kernel<<<dim3(ceil_div(S, kAttnRows), imgs), kThreads, smem, s>>>(qkv, probs, att, S, 1.f / sqrtf((float)kD));
+    BLA_LAUNCH_CHECK();
+    count_launch();
+    gemm_plain(false, false, imgs * S, Cn, kD, att, kD, wo, Cn, dense, Cn, bo, s);                     // dense + bias
+    transpose_batched(dense, out, imgs, S, Cn, s);
+}
+
+// _backward_attention (cifar_unet.c:1261-1335), with the softmax Jacobian taken at the softmax OUTPUT.  Scratch: dY [imgs*S][C],
+// dA [imgs*S][kD], dI [imgs][S][S], dqkv [imgs*S][3*kD].  dx may be NULL.
+void attn_backward(const float* dout, const float* wqkv, const float* wo, const float* z, const float* qkv, const float* probs,
+                   const float* att, float* dwqkv, float* dwo, float* dbo, float* dx, float* dY, float* dA, float* dI, float* dqkv,
+                   int imgs, int Cn, int S, cudaStream_t s) {
+    const int M = imgs * S;
+    transpose_batched(dout, dY, imgs, Cn, S, s);
+    gemm_plain(true, false, kD, Cn, M, att, kD, dY, Cn, dwo, Cn, nullptr, s);                          // dW = P^T . dY'
+    k_row_sum(dY, M, Cn, dbo, s);                                                                     // bias: column totals
+    gemm_plain(false, true, M, kD, Cn, dY, Cn, wo, Cn, dA, kD, nullptr, s);                            // dP = dY' . W^T
+    const size_t smem = ((size_t)2 * S * 17 + (kThreads / 32) * S) * sizeof(float);
+    attention_backward_rows_kernel<<<dim3(ceil_div(S, kAttnRows), imgs), kThreads, smem, s>>>(qkv, probs, dA, dI, dqkv, S,
+                                                                                              1.f / sqrtf((float)kD));
+    BLA_LAUNCH_CHECK();
+    attention_backward_cols_kernel<<<dim3(ceil_div(S, 32), imgs), kThreads, 0, s>>>(qkv, probs, dA, dI, dqkv, S);
+    BLA_LAUNCH_CHECK();
+    count_launch(2);
+    gemm_plain(true, false, Cn, 3 * kD, M, z, Cn, dqkv, 3 * kD, dwqkv, 3 * kD, nullptr, s);            // Z^T . [dQ | dK | dV]
+    if (!dx) return;
+    gemm_plain(false, true, M, Cn, 3 * kD, dqkv, 3 * kD, wqkv, 3 * kD, dY, Cn, nullptr, s);            // dZ
+    transpose_batched(dY, dx, imgs, S, Cn, s);
+}
+
+void attn_smem_opt_in(int S) {
+    const int smem = (int)(((size_t)2 * S * 17 + (kThreads / 32) * S) * sizeof(float));
+    if (smem > 227 * 1024) die("bla: attention over %d tokens does not fit shared memory, exiting", S);
+    static int granted = 0;
+    if (smem <= granted) return;
+    BLA_CUDA(cudaFuncSetAttribute(attention_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BLA_CUDA(cudaFuncSetAttribute(attention_backward_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    granted = smem;
+}
+
+enum Kind { kInput, kRes, kAttn, kConv, kUp, kCat, kGnRelu };
+
+struct Node {
+    Kind kind;
+    int in0 = -1, in1 = -1;   // producer nodes
+    int C = 0, side = 0;      // output channels / spatial side
+    int cin = 0, k = 0, stride = 1;
+    float* out = nullptr;     // [imgs][C][side*side]
+    float* gout = nullptr;    // gradient w.r.t. out
+    bool gout_set = false;    // within one backward pass: has a consumer written gout yet?
+    // parameters (offsets into the flat buffer; (size_t)-1 = absent)
+    size_t w1 = (size_t)-1, w2 = (size_t)-1, wt = (size_t)-1, bt = (size_t)-1, wr = (size_t)-1;   // res block / conv (w1)
+    size_t wqkv = (size_t)-1, wo = (size_t)-1, bo = (size_t)-1;                                   // attention
+    // saved activations
+    float *relu1 = nullptr, *conv1 = nullptr, *relu2 = nullptr, *drop = nullptr, *res = nullptr, *td = nullptr;
+    float *mu1 = nullptr, *var1 = nullptr, *mu2 = nullptr, *var2 = nullptr;
+    float *z = nullptr, *qkv = nullptr, *probs = nullptr, *att = nullptr;
+    int id = 0;
+};
+
+struct ParamT { std::string name; size_t off, n; int init; double fan_in, fan_out; };   // init: 0 zeros, 1 He, 2 Xavier
+
+}  // namespace
+
+struct bla_unet {
+    bla_unet_config cfg;
+    std::vector<Node> nodes;
+    std::vector<ParamT> tensors;
+    size_t nparams = 0;
+    float *params = nullptr, *grads = nullptr;
+    float *x = nullptr, *temb = nullptr, *noise = nullptr;   // staging for host-side batches
+    float *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;        // backward scratch, each max activation size
+    float *sq = nullptr, *sdi = nullptr, *sdz = nullptr;      // attention scratch: dqkv, dI, dZ / dense
+    float* sdt = nullptr;                                     // time-dense gradient [imgs][Cmax]
+    double* loss = nullptr;
+    unsigned long long step = 0;
+    int out_node = -1;
+};
+
+namespace {
+
+size_t add_tensor(bla_unet* n, const std::string& name, size_t count, int init, double fan_in, double fan_out = 0) {
+    const size_t off = n->nparams;
+    n->tensors.push_back({name, off, count, init, fan_in, fan_out});
+    n->nparams += (count + 3) / 4 * 4;   // keep every tensor 16-byte aligned (TMA operands)
+    return off;
+}
+
+float* dev_alloc(size_t floats) { return (float*)pool_alloc(kDevice, (floats ? floats : 1) * sizeof(float)); }
+
+int add_node(bla_unet* n, Node nd) {
+    nd.id = (int)n->nodes.size();
+    n->nodes.push_back(nd);
+    return nd.id;
+}
+
+// cifar_unet.c:255-440 (allocate_model_params / allocate_model_data) and :1439-1482 (fan-ins of init_parameters)
+int add_res(bla_unet* n, const std::string& name, int in, int cout) {
+    const bla_unet_config& c = n->cfg;
+    const Node& src = n->nodes[in];
+    Node nd; nd.kind = kRes; nd.in0 = in; nd.C = cout; nd.side = src.side; nd.cin = src.C; nd.k = c.kernel_size;
+    const double fan = (double)nd.side * nd.side;
+    const size_t k2 = (size_t)c.kernel_size * c.kernel_size;
+    nd.w1 = add_tensor(n, name + "/conv_1", (size_t)cout * src.C * k2, 1, fan);
+    nd.w2 = add_tensor(n, name + "/conv_2", (size_t)cout * cout * k2, 1, fan);
+    nd.wt = add_tensor(n, name + "/time_weight", (size_t)c.time_dim * cout, 1, c.time_dim);
+    nd.bt = add_tensor(n, name + "/time_bias", cout, 0, 0);
+    if (src.C != cout) nd.wr = add_tensor(n, name + "/residual_conv", (size_t)cout * src.C, 1, fan);
+    const size_t hw = (size_t)nd.side * nd.side, m = c.max_imgs;
+    const int g1 = ceil_div(src.C, c.group_size), g2 = ceil_div(cout, c.group_size);
+    nd.relu1 = dev_alloc(m * src.C * hw); nd.conv1 = dev_alloc(m * cout * hw); nd.relu2 = dev_alloc(m * cout * hw);
+    nd.drop = c.dropout > 0.f ? dev_alloc(m * cout * hw) : nullptr;
+    nd.res = src.C != cout ? dev_alloc(m * cout * hw) : nullptr;
+    nd.out = dev_alloc(m * cout * hw); nd.gout = dev_alloc(m * cout * hw);
+    nd.td = dev_alloc(m * cout);
+    nd.mu1 = dev_alloc(m * g1); nd.var1 = dev_alloc(m * g1); nd.mu2 = dev_alloc(m * g2); nd.var2 = dev_alloc(m * g2);
+    return add_node(n, nd);
+}
+int add_attn(bla_unet* n, const std::string& name, int in) {
+    const bla_unet_config& c = n->cfg;
+    const Node& src = n->nodes[in];
+    Node nd; nd.kind = kAttn; nd.in0 = in; nd.C = src.C; nd.side = src.side; nd.cin = src.C;
+    const double fan = (double)nd.side * nd.side;
+    // Q | K | V projections packed as the columns of one [C][3*key_dim] matrix (cifar_unet.c:1473-1482 fan-ins per block)
+    nd.wqkv = add_tensor(n, name + "/qkv", (size_t)src.C * 3 * kD, 3, fan, kD);
+    nd.wo = add_tensor(n, name + "/weight", (size_t)kD * src.C, 1, kD);
+    nd.bo = add_tensor(n, name + "/bias", src.C, 0, 0);
+    const size_t S = (size_t)nd.side * nd.side, m = c.max_imgs;
+    nd.z = dev_alloc(m * S * src.C); nd.qkv = dev_alloc(m * S * 3 * kD); nd.probs = dev_alloc(m * S * S); nd.att = dev_alloc(m * S * kD);
+    nd.out = dev_alloc(m * S * src.C); nd.gout = dev_alloc(m * S * src.C);
+    return add_node(n, nd);
+}
+int add_conv(bla_unet* n, const std::string& name, int in, int cout, int k, int stride) {
+    const Node& src = n->nodes[in];
+    Node nd; nd.kind = kConv; nd.in0 = in; nd.C = cout; nd.cin = src.C; nd.k = k; nd.stride = stride;
+    nd.side = (src.side + stride - 1) / stride;
+    // fan-in = the OUTPUT resolution's pixel count for down convs' source level... the reference passes the level's
+    // height x width (cifar_unet.c:1806-1849): down convs use the source level, up convs and the output conv the target's
+    const double fan = stride > 1 ? (double)src.side * src.side : (double)nd.side * nd.side;
+    nd.w1 = add_tensor(n, name, (size_t)cout * src.C * k * k, 1, fan);
+    const size_t m = n->cfg.max_imgs;
+    nd.out = dev_alloc(m * cout * nd.side * nd.side); nd.gout = dev_alloc(m * cout * nd.side * nd.side);
+    return add_node(n, nd);
+}
+int add_simple(bla_unet* n, Kind kind, int in0, int in1) {
+    const Node& a = n->nodes[in0];
+    Node nd; nd.kind = kind; nd.in0 = in0; nd.in1 = in1; nd.cin = a.C;
+    nd.C = kind == kCat ? a.C + n->nodes[in1].C : a.C;
+    nd.side = kind == kUp ? a.side * 2 : a.side;
+    const size_t m = n->cfg.max_imgs, e = m * nd.C * nd.side * nd.side;
+    nd.out = dev_alloc(e); nd.gout = dev_alloc(e);
+    if (kind == kGnRelu) { const int g = ceil_div(a.C, n->cfg.group_size); nd.mu1 = dev_alloc(m * g); nd.var1 = dev_alloc(m * g); }
+    return add_node(n, nd);
+}
+
+// ---- forward -------------------------------------------------------------------------------------------------------
+void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
+    const bla_unet_config& c = n->cfg;
+    const float* P = n->params;
+    const Node* a = nd.in0 >= 0 ? &n->nodes[nd.in0] : nullptr;
+    const int hw = nd.side * nd.side;
+    const int quirk = rt().quirks;
+    switch (nd.kind) {
+    case kInput: break;
+    case kRes: {   // cifar_unet.c:1044-1072
+        const size_t ein = (size_t)imgs * nd.cin * hw, eout = (size_t)imgs * nd.C * hw;
+        k_group_norm_fwd(a->out, nd.relu1, nd.var1, nd.mu1, imgs, nd.cin, hw, c.group_size, quirk, s);
+        k_relu(nd.relu1, ein, s);
+        conv2d_forward(nd.relu1, P + nd.w1, nd.conv1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s);
+        gemm_plain(false, false, imgs, nd.C, c.time_dim, n->temb, c.time_dim, P + nd.wt, nd.C, nd.td, nd.C, P + nd.bt, s);
+        k_add_tile_columns(nd.conv1, imgs * nd.C, hw, nd.td, 1, s);                       // _add_time_embedding
+        k_group_norm_fwd(nd.conv1, nd.relu2, nd.var2, nd.mu2, imgs, nd.C, hw, c.group_size, quirk, s);
+        k_relu(nd.relu2, eout, s);
+        const float* conv2_in = nd.relu2;
+        if (nd.drop && train) {
+            dropout_kernel<<<grid_for(eout, kThreads * 4), kThreads, 0, s>>>(nd.relu2, nd.drop, eout, c.seed + 7919ull * n->step + nd.id, c.dropout);
+            BLA_LAUNCH_CHECK();
+            count_launch();
+            conv2_in = nd.drop;
+        }
+        conv2d_forward(conv2_in, P + nd.w2, nd.out, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s);
+        if (nd.res) {
+            conv2d_forward(a->out, P + nd.wr, nd.res, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s);
+            k_add(nd.out, nd.res, eout, s);
+        } else {
+            k_add(nd.out, a->out, eout, s);
+        }
+        break;
+    }
+    case kAttn:
+        attn_forward(a->out, P + nd.wqkv, P + nd.wo, P + nd.bo, nd.z, nd.qkv, nd.probs, nd.att, n->sdz, nd.out, imgs, nd.C, hw, s);
+        break;
+    case kConv:
+        conv2d_forward(a->out, P + nd.w1, nd.out, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s);
+        break;
+    case kUp:
+        upsample2_kernel<<<grid_for((size_t)imgs * nd.C * a->side * a->side, kThreads), kThreads, 0, s>>>(a->out, nd.out, (size_t)imgs * nd.C,
+                                                                                                         a->side, a->side);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+        break;
+    case kCat: {   // cifar_unet.c:1088-1097
+        const Node& b2 = n->nodes[nd.in1];
+        slab(nd.out, (size_t)nd.C * hw, a->out, (size_t)a->C * hw, (size_t)a->C * hw, imgs, false, s);
+        slab(nd.out + (size_t)a->C * hw, (size_t)nd.C * hw, b2.out, (size_t)b2.C * hw, (size_t)b2.C * hw, imgs, false, s);
+        break;
+    }
+    case kGnRelu:
+        k_group_norm_fwd(a->out, nd.out, nd.var1, nd.mu1, imgs, nd.C, hw, c.group_size, quirk, s);
+        k_relu(nd.out, (size_t)imgs * nd.C * hw, s);
+        break;
+    }
+}
+
+// ---- backward ------------------------------------------------------------------------------------------------------
+// where the gradient w.r.t. a producer's output goes: straight into its gout the first time, through `scratch` + add after
+struct Sink {
+    float* dst; bool direct; Node* nd; size_t count;
+};
+Sink open_sink(bla_unet* n, int node, float* scratch, int imgs) {
+    Node& t = n->nodes[node];
+    Sink k;
+    k.nd = &t; k.count = (size_t)imgs * t.C * t.side * t.side;
+    k.direct = !t.gout_set;
+    k.dst = k.direct ? t.gout : scratch;
+    return k;
+}
+void close_sink(Sink& k, cudaStream_t s) {
+    if (!k.direct) k_add(k.nd->gout, k.dst, k.count, s);
+    k.nd->gout_set = true;
+}
+
+void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
+    const bla_unet_config& c = n->cfg;
+    const float* P = n->params;
+    float* G = n->grads;
+    Node* a = nd.in0 >= 0 ? &n->nodes[nd.in0] : nullptr;
+    const int hw = nd.side * nd.side;
+    const bool want_din = a && a->kind != kInput;
+    switch (nd.kind) {
+    case kInput: break;
+    case kRes: {   // cifar_unet.c:1181-1226
+        const size_t eout = (size_t)imgs * nd.C * hw;
+        const float* conv2_in = nd.drop ? nd.drop : nd.relu2;
+        float *t1 = n->s1, *t2 = n->s2;
+        conv2d_wgrad(conv2_in, nd.gout, G + nd.w2, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s);
+        conv2d_dgrad(nd.gout, P + nd.w2, t1, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s);
+        // _dropout_mask + multi_channel_relu_ddx in one pass: a dropped or clipped activation is 0 in conv_2's input
+        k_relu_backward(t1, conv2_in, t1, eout, s);
+        k_group_norm_bwd(t1, t2, nd.conv1, nd.mu2, nd.var2, imgs, nd.C, hw, c.group_size, s);           // t2 = d conv_1 output
+        // time embedding projection (:1192-1200)
+        plane_sum_kernel<<<grid_for((size_t)imgs * nd.C, kThreads / 32), kThreads, 0, s>>>(t2, imgs * nd.C, hw, n->sdt);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+        k_row_sum(n->sdt, imgs, nd.C, G + nd.bt, s);
+        gemm_plain(true, false, c.time_dim, nd.C, imgs, n->temb, c.time_dim, n->sdt, nd.C, G + nd.wt, nd.C, nullptr, s);
+        conv2d_wgrad(nd.relu1, t2, G + nd.w1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s);
+        if (nd.res) conv2d_wgrad(a->out, nd.gout, G + nd.wr, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s);
+        if (!want_din) break;
+        const size_t ein = (size_t)imgs * nd.cin * hw;
+        conv2d_dgrad(t2, P + nd.w1, t1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s);
+        k_relu_backward(t1, nd.relu1, t1, ein, s);
+        Sink k = open_sink(n, nd.in0, n->s3, imgs);
+        k_group_norm_bwd(t1, k.dst, a->out, nd.mu1, nd.var1, imgs, nd.cin, hw, c.group_size, s);
+        if (nd.res) {
+            conv2d_dgrad(nd.gout, P + nd.wr, t1, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s);
+            k_add(k.dst, t1, ein, s);
+        } else {
+            k_add(k.dst, nd.gout, ein, s);
+        }
+        close_sink(k, s);
+        break;
+    }
+    case kAttn: {
+        if (!want_din) {
+            attn_backward(nd.gout, P + nd.wqkv, P + nd.wo, nd.z, nd.qkv, nd.probs, nd.att, G + nd.wqkv, G + nd.wo, G + nd.bo, nullptr, n->sdz,
+                          n->s1, n->sdi, n->sq, imgs, nd.C, hw, s);
+            break;
+        }
+        Sink k = open_sink(n, nd.in0, n->s3, imgs);
+        attn_backward(nd.gout, P + nd.wqkv, P + nd.wo, nd.z, nd.qkv, nd.probs, nd.att, G + nd.wqkv, G + nd.wo, G + nd.bo, k.dst, n->sdz,
+                      n->s1, n->sdi, n->sq, imgs, nd.C, hw, s);
+        close_sink(k, s);
+        break;
+    }
+    case kConv: {
+        conv2d_wgrad(a->out, nd.gout, G + nd.w1, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s);
+        if (!want_din) break;
+        Sink k = open_sink(n, nd.in0, n->s3, imgs);
+        conv2d_dgrad(nd.gout, P + nd.w1, k.dst, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s);
+        close_sink(k, s);
+        break;
+    }
+    case kUp: {
+        const bool acc = a->gout_set;
+        upsample2_backward_kernel<<<grid_for((size_t)imgs * nd.C * a->side * a->side, kThreads), kThreads, 0, s>>>(
+            nd.gout, a->gout, (size_t)imgs * nd.C, a->side, a->side, acc ? 1 : 0);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+        a->gout_set = true;
+        break;
+    }
+    case kCat: {   // _split_concat + the skip-connection adds of backward() (:1389-1432)
+        Node& b2 = n->nodes[nd.in1];
+        slab(a->gout, (size_t)a->C * hw, nd.gout, (size_t)nd.C * hw, (size_t)a->C * hw, imgs, a->gout_set, s);
+        a->gout_set = true;
+        slab(b2.gout, (size_t)b2.C * hw, nd.gout + (size_t)a->C * hw, (size_t)nd.C * hw, (size_t)b2.C * hw, imgs, b2.gout_set, s);
+        b2.gout_set = true;
+        break;
+    }
+    case kGnRelu: {
+        const size_t e = (size_t)imgs * nd.C * hw;
+        k_relu_backward(nd.gout, nd.out, n->s1, e, s);
+        Sink k = open_sink(n, nd.in0, n->s3, imgs);
+        k_group_norm_bwd(n->s1, k.dst, a->out, nd.mu1, nd.var1, imgs, nd.C, hw, c.group_size, s);
+        close_sink(k, s);
+        break;
+    }
+    }
+}
+
+const float* stage_in(const float* src, float* staging, size_t floats, cudaStream_t s) {
+    const MemKind kind = classify(src);
+    if (kind == kDevice || kind == kManaged) return src;
+    BLA_CUDA(cudaMemcpyAsync(staging, src, floats * sizeof(float), cudaMemcpyHostToDevice, s));
+    rt().h2d_bytes += floats * sizeof(float);
+    return staging;
+}
+
+void run_forward(bla_unet* n, const float* x, const float* temb, int imgs, bool train, cudaStream_t s) {
+    const bla_unet_config& c = n->cfg;
+    if (imgs < 1 || imgs > c.max_imgs) die("bla: U-Net batch of %d images outside 1..%d, exiting", imgs, c.max_imgs);
+    const size_t px = (size_t)3 * c.image_side * c.image_side;
+    n->nodes[0].out = const_cast<float*>(stage_in(x, n->x, imgs * px, s));
+    const float* t = stage_in(temb, n->temb, (size_t)imgs * c.time_dim, s);
+    if (t != n->temb) BLA_CUDA(cudaMemcpyAsync(n->temb, t, (size_t)imgs * c.time_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    for (Node& nd : n->nodes) forward_node(n, nd, imgs, train, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+// include/bla.h "fused self attention": device pointers, asynchronous on the library stream
+void bla_attention_forward(const float* x, const float* wqkv, const float* wo, const float* bo, float* z, float* qkv, float* probs,
+                           float* att, float* out, int imgs, int channels, int tokens) {
+    cudaStream_t s = rt().stream;
+    attn_smem_opt_in(tokens);
+    float* dense = dev_alloc((size_t)imgs * tokens * channels);
+    attn_forward(x, wqkv, wo, bo, z, qkv, probs, att, dense, out, imgs, channels, tokens, s);
+    pool_free(dense);   // stream-ordered reuse
+}
+void bla_attention_backward(const float* dout, const float* wqkv, const float* wo, const float* z, const float* qkv, const float* probs,
+                            const float* att, float* dwqkv, float* dwo, float* dbo, float* dx, int imgs, int channels, int tokens) {
+    cudaStream_t s = rt().stream;
+    attn_smem_opt_in(tokens);
+    const size_t M = (size_t)imgs * tokens;
+    float *dY = dev_alloc(M * channels), *dA = dev_alloc(M * kD), *dI = dev_alloc(M * tokens), *dqkv = dev_alloc(M * 3 * kD);
+    attn_backward(dout, wqkv, wo, z, qkv, probs, att, dwqkv, dwo, dbo, dx, dY, dA, dI, dqkv, imgs, channels, tokens, s);
+    for (float* p : {dY, dA, dI, dqkv}) pool_free(p);
+}
+
+bla_unet* bla_unet_create(const bla_unet_config* cfg) {
+    rt();
+    bla_unet* n = new bla_unet();
+    n->cfg = *cfg;
+    const bla_unet_config& c = n->cfg;
+    if (c.key_dim != kD) die("bla: the U-Net attention kernels are built for key_dim %d, exiting", kD);
+    if (c.image_side % 8 || c.image_side < 8) die("bla: U-Net image side must be a multiple of 8, exiting");
+    Node in; in.kind = kInput; in.C = 3; in.side = c.image_side;
+    add_node(n, in);
+    const int* D = c.dims;
+    const int K = c.kernel_size;
+    // the node list is forward() of model/cifar_unet.c:1099-1168, in order
+    int d1r1 = add_res(n, "down_1/resnet_1", 0, D[0]);
+    int d1r2 = add_res(n, "down_1/resnet_2", d1r1, D[0]);
+    int d1c = add_conv(n, "down_1/conv", d1r2, D[1], K, 2);
+    int d2r1 = add_res(n, "down_2/resnet_1", d1c, D[1]);
+    int d2a1 = add_attn(n, "down_2/self_attention_1", d2r1);
+    int d2r2 = add_res(n, "down_2/resnet_2", d2a1, D[1]);
+    int d2a2 = add_attn(n, "down_2/self_attention_2", d2r2);
+    int d2c = add_conv(n, "down_2/conv", d2a2, D[2], K, 2);
+    int d3r1 = add_res(n, "down_3/resnet_1", d2c, D[2]);
+    int d3r2 = add_res(n, "down_3/resnet_2", d3r1, D[2]);
+    int d3c = add_conv(n, "down_3/conv", d3r2, D[3], K, 2);
+    int d4r1 = add_res(n, "down_4/resnet_1", d3c, D[3]);
+    int d4r2 = add_res(n, "down_4/resnet_2", d4r1, D[3]);
+    int m1 = add_res(n, "mid/resnet_1", d4r2, D[3]);
+    int ma = add_attn(n, "mid/self_attention", m1);
+    int m2 = add_res(n, "mid/resnet_2", ma, D[3]);
+    int u1cat = add_simple(n, kCat, m2, d4r2);
+    int u1r1 = add_res(n, "up_1/resnet_1", u1cat, D[3]);
+    int u1r2 = add_res(n, "up_1/resnet_2", u1r1, D[3]);
+    int next = add_simple(n, kUp, u1r2, -1);
+    if (D[3] != D[2]) next = add_conv(n, "up_1/conv", next, D[2], K, 1);      // skipped when the widths agree (:1131)
+    int u2cat = add_simple(n, kCat, next, d3r2);
+    int u2r1 = add_res(n, "up_2/resnet_1", u2cat, D[2]);
+    int u2r2 = add_res(n, "up_2/resnet_2", u2r1, D[2]);
+    next = add_simple(n, kUp, u2r2, -1);
+    if (D[2] != D[1]) next = add_conv(n, "up_2/conv", next, D[1], K, 1);
+    int u3cat = add_simple(n, kCat, next, d2r2);
+    int u3r1 = add_res(n, "up_3/resnet_1", u3cat, D[1]);
+    int u3a1 = add_attn(n, "up_3/self_attention_1", u3r1);
+    int u3r2 = add_res(n, "up_3/resnet_2", u3a1, D[1]);
+    int u3a2 = add_attn(n, "up_3/self_attention_2", u3r2);
+    next = add_simple(n, kUp, u3a2, -1);
+    if (D[1] != D[0]) next = add_conv(n, "up_3/conv", next, D[0], K, 1);
+    int u4cat = add_simple(n, kCat, next, d1r2);
+    int u4r1 = add_res(n, "up_4/resnet_1", u4cat, D[0]);
+    int u4r2 = add_res(n, "up_4/resnet_2", u4r1, D[0]);
+    int head = add_simple(n, kGnRelu, u4r2, -1);
+    n->out_node = add_conv(n, "output_conv", head, 3, K, 1);
+
+    n->params = dev_alloc(n->nparams);
+    n->grads = dev_alloc(n->nparams);
+    BLA_CUDA(cudaMemsetAsync(n->params, 0, n->nparams * sizeof(float), rt().stream));
+    BLA_CUDA(cudaMemsetAsync(n->grads, 0, n->nparams * sizeof(float), rt().stream));
+    size_t max_act = 0, max_tok = 0, max_ss = 0; int max_c = 0;
+    for (const Node& nd : n->nodes) {
+        const size_t e = (size_t)nd.C * nd.side * nd.side, ein = (size_t)nd.cin * nd.side * nd.side;
+        if (e > max_act) max_act = e;
+        if (ein > max_act) max_act = ein;
+        if (nd.C > max_c) max_c = nd.C;
+        if (nd.kind == kAttn) {
+            const size_t S = (size_t)nd.side * nd.side;
+            if (S * 3 * kD > max_tok) max_tok = S * 3 * kD;
+            if (S * S > max_ss) max_ss = S * S;
+        }
+    }
+    const size_t m = c.max_imgs;
+    n->s1 = dev_alloc(m * max_act); n->s2 = dev_alloc(m * max_act); n->s3 = dev_alloc(m * max_act);
+    n->sq = dev_alloc(m * max_tok); n->sdi = dev_alloc(m * max_ss); n->sdz = dev_alloc(m * max_act);
+    n->sdt = dev_alloc(m * max_c);
+    n->x = dev_alloc(m * 3 * c.image_side * c.image_side);
+    n->noise = dev_alloc(m * 3 * c.image_side * c.image_side);
+    n->temb = dev_alloc(m * c.time_dim);
+    n->loss = (double*)pool_alloc(kDevice, sizeof(double));
+    for (const Node& nd : n->nodes) if (nd.kind == kAttn) attn_smem_opt_in(nd.side * nd.side);
+    return n;
+}
+
+void bla_unet_destroy(bla_unet* n) {
+    if (!n) return;
+    BLA_CUDA(cudaStreamSynchronize(rt().stream));
+    for (Node& nd : n->nodes) {
+        float* bufs[] = {nd.kind == kInput ? nullptr : nd.out, nd.gout, nd.relu1, nd.conv1, nd.relu2, nd.drop, nd.res, nd.td, nd.mu1, nd.var1,
+                         nd.mu2, nd.var2, nd.z, nd.qkv, nd.probs, nd.att};
+        for (float* p : bufs) if (p) pool_free(p);
+    }
+    float* bufs[] = {n->params, n->grads, n->x, n->temb, n->noise, n->s1, n->s2, n->s3, n->sq, n->sdi, n->sdz, n->sdt};
+    for (float* p : bufs) if (p) pool_free(p);
+    pool_free(n->loss);
+    delete n;
+}
+
+size_t bla_unet_num_params(const bla_unet* n) { return n->nparams; }
+int bla_unet_num_tensors(const bla_unet* n) { return (int)n->tensors.size(); }
+const char* bla_unet_tensor_name(const bla_unet* n, int i) { return n->tensors[i].name.c_str(); }
+size_t bla_unet_tensor_offset(const bla_unet* n, int i) { return n->tensors[i].off; }
+size_t bla_unet_tensor_size(const bla_unet* n, int i) { return n->tensors[i].n; }
+
+// cifar_unet.c:1439-1482 + :1804-1851: He / Xavier uniform with the reference's fan-ins, from the counter-based generator
+void bla_unet_init_params(bla_unet* n, unsigned long long seed) {
+    cudaStream_t s = rt().stream;
+    BLA_CUDA(cudaMemsetAsync(n->params, 0, n->nparams * sizeof(float), s));
+    int i = 0;
+    for (const ParamT& t : n->tensors) {
+        ++i;
+        if (t.init == 0) continue;
+        if (t.init == 3) {   // packed Q | K | V: Xavier for Q and K, He for V (cifar_unet.c:1475-1477), column blocks of kD
+            const float xs = (float)sqrt(6.0 / (t.fan_in + t.fan_out)), hs = (float)sqrt(6.0 / t.fan_in);
+            std::vector<float> h(t.n);
+            bla_host_uniform(h.data(), t.n, seed + 1000003ull * i, -1.f, 1.f);
+            for (size_t e = 0; e < t.n; ++e) h[e] *= (e % (3 * kD)) < 2 * kD ? xs : hs;
+            BLA_CUDA(cudaMemcpyAsync(n->params + t.off, h.data(), t.n * sizeof(float), cudaMemcpyHostToDevice, s));
+            BLA_CUDA(cudaStreamSynchronize(s));
+            continue;
+        }
+        const float scale = (float)sqrt(6.0 / (t.init == 1 ? t.fan_in : t.fan_in + t.fan_out));
+        k_fill_uniform(n->params + t.off, t.n, seed + 1000003ull * i, -scale, scale, s);
+    }
+}
+
+void bla_unet_set_params(bla_unet* n, const float* flat) {
+    BLA_CUDA(cudaMemcpyAsync(n->params, flat, n->nparams * sizeof(float), cudaMemcpyDefault, rt().stream));
+    BLA_CUDA(cudaStreamSynchronize(rt().stream));
+}
+void bla_unet_get_params(bla_unet* n, float* flat) {
+    BLA_CUDA(cudaMemcpyAsync(flat, n->params, n->nparams * sizeof(float), cudaMemcpyDefault, rt().stream));
+    BLA_CUDA(cudaStreamSynchronize(rt().stream));
+}
+void bla_unet_get_grads(bla_unet* n, float* flat) {
+    BLA_CUDA(cudaMemcpyAsync(flat, n->grads, n->nparams * sizeof(float), cudaMemcpyDefault, rt().stream));
+    BLA_CUDA(cudaStreamSynchronize(rt().stream));
+}
+
+void bla_unet_forward(bla_unet* n, const float* x, const float* time_emb, int imgs, float* out) {
+    cudaStream_t s = rt().stream;
+    run_forward(n, x, time_emb, imgs, false, s);
+    const size_t bytes = (size_t)imgs * 3 * n->cfg.image_side * n->cfg.image_side * sizeof(float);
+    const MemKind kind = classify(out);
+    BLA_CUDA(cudaMemcpyAsync(out, n->nodes[n->out_node].out, bytes, cudaMemcpyDefault, s));
+    if (kind != kDevice) { rt().d2h_bytes += bytes; BLA_CUDA(cudaStreamSynchronize(s)); }
+}
+
+void bla_unet_train_step(bla_unet* n, const float* x, const float* time_emb, const float* noise, int imgs, float lr, double* loss_host) {
+    cudaStream_t s = rt().stream;
+    const bla_unet_config& c = n->cfg;
+    run_forward(n, x, time_emb, imgs, true, s);
+    Node& o = n->nodes[n->out_node];
+    const size_t ne = (size_t)imgs * 3 * c.image_side * c.image_side;
+    const float* nz = stage_in(noise, n->noise, ne, s);
+    BLA_CUDA(cudaMemsetAsync(n->loss, 0, sizeof(double), s));
+    mse_grad_kernel<<<grid_for(ne, kThreads * 4), kThreads, 0, s>>>(o.out, nz, o.gout, ne, 1.f / (3.f * c.image_side * c.image_side), n->loss);
+    BLA_LAUNCH_CHECK();
+    count_launch();
+    for (Node& nd : n->nodes) nd.gout_set = false;
+    o.gout_set = true;
+    for (int i = (int)n->nodes.size() - 1; i > 0; --i) backward_node(n, n->nodes[i], imgs, s);
+    if (comm_active()) {   // data parallel over images: gradients are sums over samples
+        comm_allreduce_f32_on(n->grads, n->nparams, s);
+        comm_allreduce_f64_on(n->loss, 1, s);
+    }
+    if (lr != 0.f) k_axpy(n->params, n->grads, -lr, n->nparams, s);
+    ++n->step;
+    if (loss_host) {
+        BLA_CUDA(cudaMemcpyAsync(loss_host, n->loss, sizeof(double), cudaMemcpyDeviceToHost, s));
+        rt().d2h_bytes += sizeof(double);
+        BLA_CUDA(cudaStreamSynchronize(s));
+    }
+}
+
+}  // extern "C"

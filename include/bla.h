@@ -165,6 +165,60 @@ void bla_mlp_forward(bla_mlp* net, const float* x, int batch, float* probs);
 /* {loss_sum, num_correct} accumulated on the device since the last call (then cleared). */
 void bla_mlp_read_stats(bla_mlp* net, double* stats_host);
 
+/* ---- fused self attention: _forward_attention / _backward_attention (cifar_unet.c:999-1022, :1261-1335) ---- */
+
+/* x, out [imgs][C][tokens] (tokens = H*W, key width 16 = SELF_ATTENTION_KEY_DIM); wqkv [C][48] = Q | K | V projection columns,
+ * wo [16][C], bo [C].  z [imgs*tokens][C], qkv [imgs*tokens][48], probs [imgs][tokens][tokens] (softmax output) and
+ * att [imgs*tokens][16] are written for the backward pass.  Device pointers; asynchronous on the library stream.
+ * One transpose, one GEMM for Q|K|V, ONE kernel for scores / softmax / P.V, one GEMM (+bias), one transpose. */
+void bla_attention_forward(const float* x, const float* wqkv, const float* wo, const float* bo, float* z, float* qkv,
+                           float* probs, float* att, float* out, int imgs, int channels, int tokens);
+/* Gradients of the three parameter tensors (summed over images) and, if dx != NULL, of the input.  The softmax Jacobian is
+ * taken at the softmax output (the reference feeds it the pre-softmax scores, :1299 -- SURVEY D6). */
+void bla_attention_backward(const float* dout, const float* wqkv, const float* wo, const float* z, const float* qkv,
+                            const float* probs, const float* att, float* dwqkv, float* dwo, float* dbo, float* dx, int imgs,
+                            int channels, int tokens);
+
+/* ---- CIFAR U-Net trainer: model/cifar_unet.c as one batched device-resident step ---------------- */
+
+typedef struct bla_unet bla_unet;
+typedef struct bla_unet_config {
+	int image_side;     /* IMAGE_HEIGHT = IMAGE_WIDTH = 32 (cifar_unet.c:26-27); a multiple of 8 */
+	int dims[4];        /* RESOLUTION_{1..4}_EMBED_DIM = 128, 256, 256, 256 (:29-32) */
+	int time_dim;       /* TIME_EMBED_DIM = 512 (:33) */
+	int kernel_size;    /* KERNEL_SIZE = 3 (:34) */
+	int group_size;     /* GROUP_SIZE = 32 channels per group (:35) */
+	int key_dim;        /* SELF_ATTENTION_KEY_DIM = 16 (:36) -- the fused attention kernels are built for 16 */
+	float dropout;      /* DROPOUT_RATE = 0.1 (:37); 0 disables the mask */
+	int max_imgs;       /* largest batch a step will be given (the reference has no batch axis: 1 image per forward) */
+	unsigned long long seed; /* dropout masks: element i of block b at step t is dropped iff
+	                          * bla_host_uniform(seed + 7919*t + node_id(b))[i] < dropout */
+} bla_unet_config;
+/* Builds forward()'s graph (cifar_unet.c:1099-1168): 22 ResNet blocks, 5 attention blocks, 3 stride-2 convs, nearest-
+ * neighbour up-sampling, skip concatenations, group norm + ReLU + 3-channel output conv.  Parameters are ONE flat buffer;
+ * tensor i is [offset, offset + size) with the reference's per-file layout (conv kernels [F][C][k][k], time_weight
+ * [time_dim][C], attention weight [key_dim][C]); Q, K, V projections are packed as the columns of one [C][3*key_dim]. */
+bla_unet* bla_unet_create(const bla_unet_config* cfg);
+void bla_unet_destroy(bla_unet* net);
+size_t bla_unet_num_params(const bla_unet* net);
+int bla_unet_num_tensors(const bla_unet* net);
+const char* bla_unet_tensor_name(const bla_unet* net, int i);
+size_t bla_unet_tensor_offset(const bla_unet* net, int i);
+size_t bla_unet_tensor_size(const bla_unet* net, int i);
+/* init_parameters (cifar_unet.c:1804-1851): He / Xavier uniform with the reference's fan-ins, zero biases. */
+void bla_unet_init_params(bla_unet* net, unsigned long long seed);
+void bla_unet_set_params(bla_unet* net, const float* flat);   /* host or device */
+void bla_unet_get_params(bla_unet* net, float* flat);
+void bla_unet_get_grads(bla_unet* net, float* flat);
+/* forward() on x [imgs][3][H][W] with one time embedding row per image, time_emb [imgs][time_dim] (the reference never
+ * initialises its own); out [imgs][3][H][W].  Host or device pointers; dropout off. */
+void bla_unet_forward(bla_unet* net, const float* x, const float* time_emb, int imgs, float* out);
+/* forward + compute_mse_loss (:1858) + backward (:1351) + SGD: dY = 2 (out - noise) as :1353-1365, gradients summed over
+ * the images (and all-reduced over ranks when a communicator is active), params -= lr * grads (lr = 0: gradients only).
+ * loss_host, if not NULL, receives the sum over images of the per-image MSE and forces a synchronise. */
+void bla_unet_train_step(bla_unet* net, const float* x, const float* time_emb, const float* noise, int imgs, float lr,
+                         double* loss_host);
+
 /* ---- NCCL over NVLink: one process per GPU -------------------------------------------------- */
 
 /* Rank 0 fills a 128-byte id (ncclGetUniqueId) that the launcher broadcasts out of band
