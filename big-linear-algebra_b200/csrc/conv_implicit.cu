@@ -214,36 +214,37 @@ __global__ void __launch_bounds__(256) permute_weights_dgrad(const float* __rest
     }
 }
 
-// tensor-path weight layouts: taps[f][(ki*k + kj)*C + c] = W[f][c][ki][kj]        (fprop: 16 consecutive k' = 16 channels of one tap)
-//                             flip [c][(ki*k + kj)*F + f] = W[f][c][k-1-ki][k-1-kj]   (stride-1 dgrad as a forward conv of dy)
-__global__ void __launch_bounds__(256) permute_weights_taps(const float* __restrict__ w, float* out, int F, int C, int k2, int flip) {
-    const size_t total = (size_t)F * C * k2;
+// tensor-path weight layouts over Cp >= C (Fp >= F) channels, zero weights for the padding channels:
+//   mode 0  taps [f][(ki*k + kj)*Cp + c] = W[f][c][ki][kj]              (fprop: 16 consecutive k' = 16 channels of one tap)
+//   mode 1  flip [c][(ki*k + kj)*Fp + f] = W[f][c][k-1-ki][k-1-kj]      (dgrad as a forward conv of dy; pad = Fp)
+//   mode 2  the inverse of mode 0: out [F][C][k2] <- taps [F][(tap, c)]   (weight gradient back to the reference layout)
+__global__ void __launch_bounds__(256) permute_weights_taps(const float* __restrict__ w, float* out, int F, int C, int k2, int pad, int mode) {
+    const size_t total = mode == 0 ? (size_t)F * k2 * pad : mode == 1 ? (size_t)C * k2 * pad : (size_t)F * C * k2;
     for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-        if (flip == 2) {      // inverse of the taps layout: out [F][C][k2] <- w [F][(tap, c)]
+        if (mode == 2) {
             const int tap = (int)(e % k2), c = (int)((e / k2) % C), f = (int)(e / ((size_t)C * k2));
-            out[e] = w[((size_t)f * k2 + tap) * C + c];
-        } else if (!flip) {
-            const int c = (int)(e % C), tap = (int)((e / C) % k2), f = (int)(e / ((size_t)C * k2));
-            out[e] = w[((size_t)f * C + c) * k2 + tap];
+            out[e] = w[((size_t)f * k2 + tap) * pad + c];
+        } else if (mode == 0) {
+            const int c = (int)(e % pad), tap = (int)((e / pad) % k2), f = (int)(e / ((size_t)pad * k2));
+            out[e] = c < C ? w[((size_t)f * C + c) * k2 + tap] : 0.f;
         } else {
-            const int f = (int)(e % F), tap = (int)((e / F) % k2), c = (int)(e / ((size_t)F * k2));
-            out[e] = w[((size_t)f * C + c) * k2 + (k2 - 1 - tap)];
+            const int f = (int)(e % pad), tap = (int)((e / pad) % k2), c = (int)(e / ((size_t)pad * k2));
+            out[e] = f < F ? w[((size_t)f * C + c) * k2 + (k2 - 1 - tap)] : 0.f;
         }
     }
 }
 
 bool tensor_path_wanted() { return rt().gemm_path != BLA_GEMM_FP32 && bla_tc_available(); }
 
-float* permuted_weights(const float* w, int F, int C, int k, int flip, cudaStream_t s) {
-    const size_t total = (size_t)F * C * k * k;
-    float* out = (float*)pool_alloc(kDevice, total * sizeof(float));
+void launch_permute(const float* w, float* out, int F, int C, int k2, int pad, int mode, size_t total, cudaStream_t s) {
     size_t blocks = (total + 255) / 256, cap = (size_t)rt().num_sms * 8;
     if (blocks > cap) blocks = cap;
-    permute_weights_taps<<<(int)blocks, 256, 0, s>>>(w, out, F, C, k * k, flip);
+    permute_weights_taps<<<(int)blocks, 256, 0, s>>>(w, out, F, C, k2, pad, mode);
     BLA_LAUNCH_CHECK();
     count_launch();
-    return out;
 }
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 ConvP base_params(int imgs, int C, int H, int W, int F, int k, int stride) {
     ConvP p{};
@@ -275,38 +276,39 @@ void launch(ConvP& p, int splits, cudaStream_t s) {
 
 }  // namespace
 
-void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s) {
+void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
+                    NhwcCache* cache) {
     ConvP p = base_params(imgs, C, H, W, F, k, stride);
     p.M = F; p.N = imgs * p.Ho * p.Wo; p.K = C * k * k;
     p.a = w; p.src = x; p.out = y; p.k_chunk = p.K;
     if (p.M <= 0 || p.N <= 0) return;
-    if (tensor_path_wanted() && F >= 64 && p.N >= 256 && C % 16 == 0) {
-        // tcgen05 implicit GEMM: the im2col tile is gathered by 4-D TMA boxes (gemm_tc.cu, conv mode)
-        float* wt = permuted_weights(w, F, C, k, 0, s);
-        const bool done = conv2d_tc(x, wt, y, imgs, C, H, W, 1, H, W, F, k, stride, p.pad_top, p.pad_left, s);
+    if (tensor_path_wanted() && p.N >= 256 && (long long)F * p.K >= 2048) {
+        // tcgen05 implicit GEMM: the im2col tile is gathered by 4-D TMA boxes (gemm_tc.cu, conv mode).  Channels are padded to a
+        // multiple of 32 inside the NHWC copy (16 would do for the forward pass; 32 lets the weight gradient share the copy), rows
+        // of the filter matrix beyond F are zero-filled by TMA: a 3-channel input or a 3-filter output conv runs here too.
+        const int Cp = round_up(C, 32);
+        float* wt = (float*)pool_alloc(kDevice, (size_t)F * k * k * Cp * sizeof(float));
+        launch_permute(w, wt, F, C, k * k, Cp, 0, (size_t)F * k * k * Cp, s);
+        const bool done = conv2d_tc(x, wt, y, imgs, C, Cp, H, W, 1, H, W, F, k, stride, p.pad_top, p.pad_left, cache, s);
         pool_free(wt);
         if (done) return;
     }
     launch<kFprop>(p, 1, s);
 }
 
-void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s) {
+void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
+                  NhwcCache* cache) {
     ConvP p = base_params(imgs, C, H, W, F, k, stride);
     p.M = F; p.N = C * k * k; p.K = imgs * p.Ho * p.Wo;
     p.a = dy; p.src = x; p.out = dw;
     if (p.M <= 0 || p.N <= 0) return;
-    if (tensor_path_wanted() && F >= 64 && p.K >= 1024) {
+    if (tensor_path_wanted() && p.K >= 1024 && (long long)F * p.N >= 2048) {
         // tcgen05 implicit GEMM over the output pixels into the tap-major layout, then back to [F][C][k][k]
-        const size_t total = (size_t)F * C * k * k;
+        const int Cp = round_up(C, 32);
+        const size_t total = (size_t)F * Cp * k * k;
         float* taps = (float*)pool_alloc(kDevice, total * sizeof(float));
-        const bool done = conv2d_wgrad_tc(x, dy, taps, imgs, C, H, W, F, k, stride, p.pad_top, p.pad_left, s);
-        if (done) {
-            size_t blocks = (total + 255) / 256, cap = (size_t)rt().num_sms * 8;
-            if (blocks > cap) blocks = cap;
-            permute_weights_taps<<<(int)blocks, 256, 0, s>>>(taps, dw, F, C, k * k, 2);
-            BLA_LAUNCH_CHECK();
-            count_launch();
-        }
+        const bool done = conv2d_wgrad_tc(x, dy, taps, imgs, C, Cp, H, W, F, k, stride, p.pad_top, p.pad_left, cache, s);
+        if (done) launch_permute(taps, dw, F, C, k * k, Cp, 2, (size_t)F * C * k * k, s);
         pool_free(taps);
         if (done) return;
     }
@@ -343,12 +345,14 @@ void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, i
     ConvP p = base_params(imgs, C, H, W, F, k, stride);
     p.M = C; p.N = imgs * H * W; p.K = F * k * k;
     if (p.M <= 0 || p.N <= 0) return;
-    if (tensor_path_wanted() && C >= 64 && p.N >= 256 && F % 16 == 0) {
+    if (tensor_path_wanted() && p.N >= 256 && (long long)C * p.K >= 2048) {
         // dgrad is a stride-1 convolution of dy -- spread out with stride-1 zeros between its pixels when the forward conv was
         // strided -- with the flipped, transposed filters: dx[i] = sum_ki' dyu[i - (k-1-pad) + ki'] . w[k-1-ki'].  (For stride 2
         // three quarters of the gathered values are zeros; still several times faster than the FP32 FMA kernel.)
-        float* wf = permuted_weights(w, F, C, k, 1, s);
-        const bool done = conv2d_tc(dy, wf, dx, imgs, F, p.Ho, p.Wo, stride, H, W, C, k, 1, k - 1 - p.pad_top, k - 1 - p.pad_left, s);
+        const int Fp = round_up(F, 16);
+        float* wf = (float*)pool_alloc(kDevice, (size_t)C * k * k * Fp * sizeof(float));
+        launch_permute(w, wf, F, C, k * k, Fp, 1, (size_t)C * k * k * Fp, s);
+        const bool done = conv2d_tc(dy, wf, dx, imgs, F, Fp, p.Ho, p.Wo, stride, H, W, C, k, 1, k - 1 - p.pad_top, k - 1 - p.pad_left, nullptr, s);
         pool_free(wf);
         if (done) return;
     }

@@ -630,6 +630,21 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                             }
                         }
                     }
+                    if (p.conv == 1 && p.cv_P < 32) {
+                        // small images (P = 4, 8 or 16 output pixels): the 32 columns of this chunk are 32/P whole images; lane =
+                        // filter row writes P contiguous floats per image straight from its registers (64-byte runs for 4 x 4)
+                        if (row_ok) {
+                            const int img0 = col0 / p.cv_P;
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                const int col = 4 * c4, ii = col / p.cv_P, px = col - ii * p.cv_P;
+                                if (col0 + col < p.n)
+                                    *reinterpret_cast<float4*>(p.c + ((size_t)(img0 + ii) * p.m + i) * p.cv_P + px) =
+                                        make_float4(o[col], o[col + 1], o[col + 2], o[col + 3]);
+                            }
+                        }
+                        continue;
+                    }
                     if (lane == 0) tma_store_wait_read1();     // the store that last used this staging tile has been read
                     __syncwarp();
                     float* sb = stg + sbuf * 1024;
@@ -645,8 +660,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         } else {
                             const int img = col0 / p.cv_P, pix = col0 - img * p.cv_P;
                             if (p.debug == 3) { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }   // experiment: no store
-                            else if (p.cv_P >= 32) tma_store_3d(&tma_c, pix, row_base, img, stg_u32 + sbuf * 4096);   // y as {P, F, img}
-                            else tma_store_3d(&tma_c, 0, img, row_base, stg_u32 + sbuf * 4096);                  // y as {P, img, F}
+                            else tma_store_3d(&tma_c, pix, row_base, img, stg_u32 + sbuf * 4096);   // y as {P, F, img}
                         }
                     }
                     sbuf ^= 1;
@@ -880,21 +894,14 @@ bool make_map_conv_dy(CUtensorMap* map, const float* dy, const ConvTc& cv) {
     return r == CUDA_SUCCESS;
 }
 
-// 3-D map over the conv output y [img][F][P] for the epilogue's 32 (filters) x 32 (pixels) tiles: {P, F, img} when an
-// image has at least 32 pixels, {P, img, F} when a tile spans several small images.
+// 3-D map over the conv output y [img][F][P] as {P, F, img} for the epilogue's 32 (filters) x 32 (pixels) tile stores.  Images
+// with fewer than 32 pixels are written straight from registers instead (a tile then spans several images).
 bool make_map_conv_out(CUtensorMap* map, const ConvTc& cv) {
     const int P = cv.Ho * cv.Wo;
-    cuuint64_t dims[3], strides[2];
-    cuuint32_t box[3], elem[3] = {1u, 1u, 1u};
-    if (P >= 32) {
-        dims[0] = P; dims[1] = cv.F; dims[2] = cv.imgs;
-        strides[0] = (cuuint64_t)P * 4; strides[1] = (cuuint64_t)cv.F * P * 4;
-        box[0] = 32; box[1] = 32; box[2] = 1;
-    } else {
-        dims[0] = P; dims[1] = cv.imgs; dims[2] = cv.F;
-        strides[0] = (cuuint64_t)cv.F * P * 4; strides[1] = (cuuint64_t)P * 4;
-        box[0] = P; box[1] = 32 / P; box[2] = 32;
-    }
+    const int Pd = P >= 32 ? P : 32;      // the map is not used for small images; keep it encodable
+    cuuint64_t dims[3] = {(cuuint64_t)Pd, (cuuint64_t)cv.F, (cuuint64_t)cv.imgs};
+    cuuint64_t strides[2] = {(cuuint64_t)P * 4, (cuuint64_t)cv.F * P * 4};
+    cuuint32_t box[3] = {32u, 32u, 1u}, elem[3] = {1u, 1u, 1u};
     CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)cv.out, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -1049,42 +1056,64 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     return true;
 }
 
-// NCHW -> zero-padded (and optionally zero-dilated) NHWC: xp[img][pt + i*dil][pl + j*dil][c] = x[img][c][i][j], every other
-// element of xp = 0.  One block row per padded image row; 32 x 32 (channel x padded column) tiles through shared memory so
-// that both the reads (along j) and the writes (along c) are coalesced.  The kernel writes the zeros itself (no memset pass).
-__global__ void __launch_bounds__(256) nchw_to_padded_nhwc_kernel(const float* __restrict__ x, float* __restrict__ xp, int C, int H, int W,
+// NCHW -> zero-padded (and optionally zero-dilated, channel-padded) NHWC: xp[img][pt + i*dil][pl + j*dil][c] = x[img][c][i][j], every
+// other element of xp (border, dilation holes, channels C..Cp-1) = 0 -- the kernel writes the zeros itself, no memset pass.
+// grid (tiles of 32 consecutive padded pixels, images); a block walks the channels in tiles of 32 through shared memory: loads are
+// coalesced along the image row, stores are one float4 (4 channels) per thread = full 128-byte lines per pixel.
+__global__ void __launch_bounds__(256) nchw_to_padded_nhwc_kernel(const float* __restrict__ x, float* __restrict__ xp, int C, int Cp, int H, int W,
                                                                   int Hp, int Wp, int pt, int pl, int dil) {
-    __shared__ float tile[32][33];
-    const int img = blockIdx.z, ip = blockIdx.y;
-    const int tiles_c = (C + 31) / 32, tiles_w = (Wp + 31) / 32;
+    __shared__ float tile[32][33];   // [channel][pixel]
+    const int img = blockIdx.y, q0 = blockIdx.x * 32, npix = Hp * Wp;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int di = ip - pt;
-    const int i = di / dil;
-    const bool row_ok = di >= 0 && di - i * dil == 0 && i < H;
-    for (int t = blockIdx.x; t < tiles_c * tiles_w; t += gridDim.x) {
-        const int c0 = (t / tiles_w) * 32, j0 = (t % tiles_w) * 32;
-        const int dj = j0 + tx - pl;
-        const int j = dj / dil;
-        const bool col_ok = row_ok && dj >= 0 && dj - j * dil == 0 && j < W;
-        for (int cc = ty; cc < 32; cc += 8) {
-            const int c = c0 + cc;
-            tile[cc][tx] = (col_ok && c < C) ? x[(((size_t)img * C + c) * H + i) * W + j] : 0.f;
+    const int q = q0 + tx;
+    const int ip = q / Wp, jp = q - ip * Wp;
+    const int di = ip - pt, dj = jp - pl;
+    const int i = di / dil, j = dj / dil;
+    const bool ok = q < npix && di >= 0 && dj >= 0 && i * dil == di && j * dil == dj && i < H && j < W;
+    const float* src = x + (size_t)img * C * H * W + (size_t)i * W + j;
+    const int sp = threadIdx.x >> 3, sc = (threadIdx.x & 7) * 4;   // store role: pixel, channel quad
+    float* dst = xp + ((size_t)img * npix + q0 + sp) * Cp + sc;
+    const bool st_ok = q0 + sp < npix;
+    for (int c0 = 0; c0 < Cp; c0 += 32) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = c0 + ty + 8 * cc;
+            tile[ty + 8 * cc][tx] = (ok && c < C) ? __ldg(src + (size_t)c * H * W) : 0.f;
         }
         __syncthreads();
-        for (int jj = ty; jj < 32; jj += 8) {
-            const int c = c0 + tx, jp = j0 + jj;
-            if (c < C && jp < Wp) xp[(((size_t)img * Hp + ip) * Wp + jp) * C + c] = tile[tx][jj];
-        }
+        if (st_ok && c0 + sc < Cp)
+            *reinterpret_cast<float4*>(dst + c0) = make_float4(tile[sc][sp], tile[sc + 1][sp], tile[sc + 2][sp], tile[sc + 3][sp]);
         __syncthreads();
     }
 }
 
-// the padded NHWC copy every tensor-path conv gathers from (pool block; free with pool_free, stream-ordered)
-float* padded_nhwc(const float* in, int imgs, int C, int H, int W, int Hp, int Wp, int pad_top, int pad_left, int dil, cudaStream_t s) {
-    float* xp = (float*)pool_alloc(kDevice, (size_t)imgs * Hp * Wp * C * sizeof(float));
-    int gx = (C + 31) / 32 * ((Wp + 31) / 32);
-    if (gx > 64) gx = 64;
-    nchw_to_padded_nhwc_kernel<<<dim3(gx, Hp, imgs), 256, 0, s>>>(in, xp, C, H, W, Hp, Wp, pad_top, pad_left, dil);
+void nhwc_cache_release(NhwcCache* c) {
+    if (c && c->xp) pool_free(c->xp);
+    if (c) *c = NhwcCache();
+}
+
+// the padded NHWC copy a tensor-path conv gathers from: from the cache when the same tensor was transformed before, else a fresh
+// transform into the cache's buffer (or a temporary pool block when there is no cache -- the caller frees it, stream-ordered)
+float* padded_nhwc(const float* in, int imgs, int C, int Cp, int H, int W, int Hp, int Wp, int pad_top, int pad_left, int dil, NhwcCache* cache,
+                   cudaStream_t s) {
+    const size_t need = (size_t)imgs * Hp * Wp * Cp;
+    float* xp;
+    if (cache) {
+        if (cache->valid && cache->src == in && cache->imgs == imgs && cache->C == C && cache->Cp == Cp && cache->H == H && cache->W == W &&
+            cache->Hp == Hp && cache->Wp == Wp && cache->pt == pad_top && cache->pl == pad_left && cache->dil == dil)
+            return cache->xp;
+        if (cache->cap < need) {
+            if (cache->xp) pool_free(cache->xp);
+            cache->xp = (float*)pool_alloc(kDevice, need * sizeof(float));
+            cache->cap = need;
+        }
+        cache->src = in; cache->imgs = imgs; cache->C = C; cache->Cp = Cp; cache->H = H; cache->W = W; cache->Hp = Hp; cache->Wp = Wp;
+        cache->pt = pad_top; cache->pl = pad_left; cache->dil = dil; cache->valid = true;
+        xp = cache->xp;
+    } else {
+        xp = (float*)pool_alloc(kDevice, need * sizeof(float));
+    }
+    nchw_to_padded_nhwc_kernel<<<dim3(ceil_div(Hp * Wp, 32), imgs), 256, 0, s>>>(in, xp, C, Cp, H, W, Hp, Wp, pad_top, pad_left, dil);
     BLA_LAUNCH_CHECK();
     count_launch();
     return xp;
@@ -1092,12 +1121,12 @@ float* padded_nhwc(const float* in, int imgs, int C, int H, int W, int Hp, int W
 
 // out [imgs][F][Ho][Wo] = conv(in, w): `in` is [imgs][C][Hin][Win], placed at spacing `dil` (zeros between: the transposed conv of a
 // strided dgrad) and offset (pad_top, pad_left) inside a logical image of H x W, then convolved with stride `stride`.
-bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int Hin, int Win, int dil, int H, int W, int F, int k,
-               int stride, int pad_top, int pad_left, cudaStream_t s) {
+bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int Cp, int Hin, int Win, int dil, int H, int W, int F,
+               int k, int stride, int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s) {
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const int P = Ho * Wo;
     // eligibility: whole 16-channel k-blocks, 16-byte aligned rows, and 32-pixel atoms that tile the output exactly
-    if (C % BK || ((uintptr_t)in & 15) || ((uintptr_t)out & 15) || (P % 4)) return false;
+    if (Cp % BK || Cp < C || ((uintptr_t)in & 15) || ((uintptr_t)out & 15) || (P % 4)) return false;
     const bool big = P >= 32 && P % 32 == 0 && Wo <= 32 && 32 % Wo == 0;
     const bool small = P < 32 && 32 % P == 0;
     if (!big && !small) return false;
@@ -1106,38 +1135,37 @@ bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C
     const int Hp = (Ho - 1) * stride + k > H + pad_top ? (Ho - 1) * stride + k : H + pad_top;
     const int Wp = (Wo - 1) * stride + k > W + pad_left ? (Wo - 1) * stride + k : W + pad_left;
     if (pad_top + (Hin - 1) * dil + 1 > Hp || pad_left + (Win - 1) * dil + 1 > Wp) return false;
-    float* xp = padded_nhwc(in, imgs, C, Hin, Win, Hp, Wp, pad_top, pad_left, dil, s);
-    ConvTc cv{1, xp, out, imgs, C, Hp, Wp, F, k, stride, Ho, Wo, 0, 0};
+    float* xp = padded_nhwc(in, imgs, C, Cp, Hin, Win, Hp, Wp, pad_top, pad_left, dil, cache, s);
+    ConvTc cv{1, xp, out, imgs, Cp, Hp, Wp, F, k, stride, Ho, Wo, 0, 0};
     GemmArgs g{};
-    g.m = F; g.n = imgs * P; g.k = k * k * C;
+    g.m = F; g.n = imgs * P; g.k = k * k * Cp;
     g.a = w_taps; g.lda = g.k;
     g.c = out; g.ldc = P;
     g.conv = &cv;
     const bool done = gemm_3xtf32(g, s);
-    pool_free(xp);   // stream-ordered reuse
+    if (!cache) pool_free(xp);   // stream-ordered reuse
     return done;
 }
 
 // dw_taps [F][(ki, kj, c)] = sum over images and output pixels of dy[img][f][pixel] * x[img][c][pixel*stride + tap - pad]
-bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, int C, int H, int W, int F, int k, int stride, int pad_top,
-                     int pad_left, cudaStream_t s) {
+bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, int C, int Cp, int H, int W, int F, int k, int stride,
+                     int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s) {
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const int P = Ho * Wo;
     // eligibility: 32-channel atoms, 16-pixel k-blocks inside one image that are whole box rows
-    if (C % 32 || P % BK || ((uintptr_t)x & 15) || ((uintptr_t)dy & 15) || ((uintptr_t)dw_taps & 15)) return false;
+    if (Cp % 32 || Cp < C || P % BK || ((uintptr_t)x & 15) || ((uintptr_t)dy & 15) || ((uintptr_t)dw_taps & 15)) return false;
     if (!(Wo % BK == 0 || (Wo < BK && BK % Wo == 0))) return false;
     const int Hp = (Ho - 1) * stride + k > H + pad_top ? (Ho - 1) * stride + k : H + pad_top;
     const int Wp = (Wo - 1) * stride + k > W + pad_left ? (Wo - 1) * stride + k : W + pad_left;
-    float* xp = padded_nhwc(x, imgs, C, H, W, Hp, Wp, pad_top, pad_left, 1, s);
-    ConvTc cv{2, xp, nullptr, imgs, C, Hp, Wp, F, k, stride, Ho, Wo, pad_top, pad_left};
-    cv.pad_top = 0; cv.pad_left = 0;     // the padding is inside xp
+    float* xp = padded_nhwc(x, imgs, C, Cp, H, W, Hp, Wp, pad_top, pad_left, 1, cache, s);
+    ConvTc cv{2, xp, nullptr, imgs, Cp, Hp, Wp, F, k, stride, Ho, Wo, 0, 0};   // the padding is inside xp
     GemmArgs g{};
-    g.m = F; g.n = k * k * C; g.k = imgs * P;
+    g.m = F; g.n = k * k * Cp; g.k = imgs * P;
     g.a = dy; g.lda = P;
     g.c = dw_taps; g.ldc = g.n;
     g.conv = &cv;
     const bool done = gemm_3xtf32(g, s);
-    pool_free(xp);
+    if (!cache) pool_free(xp);
     return done;
 }
 

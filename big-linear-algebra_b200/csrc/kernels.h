@@ -60,17 +60,32 @@ void gemm(const GemmArgs& g, cudaStream_t s);
 void gemm_simt(const GemmArgs& g, cudaStream_t s);
 // returns false when the shape/alignment is not eligible for the tensor path
 bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s);
-// conv2d forward on the tensor path: out = conv(in, w) with w already arranged as [F][(ki, kj, c)]; false if ineligible.
+// The padded NHWC copy of a conv input that the tensor path gathers from.  A caller that convolves the SAME tensor twice (forward,
+// then the weight gradient in the backward pass) hands the same cache to both calls: the second one skips the transform.  The
+// owner must clear `valid` whenever the source tensor changes (the U-Net does at the start of every step).
+struct NhwcCache {
+    float* xp = nullptr;      // pool block, kept across calls (release with nhwc_cache_release)
+    size_t cap = 0;           // floats
+    bool valid = false;
+    const float* src = nullptr;
+    int imgs = 0, C = 0, Cp = 0, H = 0, W = 0, Hp = 0, Wp = 0, pt = 0, pl = 0, dil = 0;
+};
+void nhwc_cache_release(NhwcCache* c);
+
+// conv2d forward on the tensor path: out = conv(in, w) with w already arranged as [F][(ki, kj, c)] over Cp >= C channels (zero
+// weights for the padding channels; Cp a multiple of 16); false if ineligible.
 // `in` [imgs][C][Hin][Win] is placed at spacing `dil` inside a logical H x W image (dil = 1, Hin = H for an ordinary conv).
-bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int Hin, int Win, int dil, int H, int W, int F, int k,
-               int stride, int pad_top, int pad_left, cudaStream_t s);
-// weight gradient on the tensor path into dw_taps [F][(ki, kj, c)]; false if ineligible
-bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, int C, int H, int W, int F, int k, int stride, int pad_top,
-                     int pad_left, cudaStream_t s);
+bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int Cp, int Hin, int Win, int dil, int H, int W, int F,
+               int k, int stride, int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s);
+// weight gradient on the tensor path into dw_taps [F][(ki, kj, c)] over Cp channels (a multiple of 32); false if ineligible
+bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, int C, int Cp, int H, int W, int F, int k, int stride,
+                     int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s);
 
 // ---- batched device-resident conv2d / group norm (conv_implicit.cu, api_norm.cu) ----------------
-void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s);
-void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s);
+void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
+                    NhwcCache* cache = nullptr);
+void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
+                  NhwcCache* cache = nullptr);
 void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s);
 void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int images, int C, int HW, int group_size, int quirk,
                       cudaStream_t s);

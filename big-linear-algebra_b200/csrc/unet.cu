@@ -339,7 +339,15 @@ void attn_backward(const float* dout, const float* wqkv, const float* wo, const 
     const int M = imgs * S;
     transpose_batched(dout, dY, imgs, Cn, S, s);
     gemm_plain(true, false, kD, Cn, M, att, kD, dY, Cn, dwo, Cn, nullptr, s);                          // dW = P^T . dY'
-    k_row_sum(dY, M, Cn, dbo, s);                                                                     // bias: column totals
+    {   // bias: column totals of dY' = per-plane totals of dout summed over the images (a column sum over imgs*S rows has only
+        // Cn/32 blocks of parallelism)
+        float* planes = (float*)pool_alloc(kDevice, (size_t)imgs * Cn * sizeof(float));
+        plane_sum_kernel<<<grid_for((size_t)imgs * Cn, kThreads / 32), kThreads, 0, s>>>(dout, imgs * Cn, S, planes);
+        BLA_LAUNCH_CHECK();
+        count_launch();
+        k_row_sum(planes, imgs, Cn, dbo, s);
+        pool_free(planes);   // stream-ordered reuse
+    }
     gemm_plain(false, true, M, kD, Cn, dY, Cn, wo, Cn, dA, kD, nullptr, s);                            // dP = dY' . W^T
     const size_t smem = ((size_t)2 * S * 17 + (kThreads / 32) * S) * sizeof(float);
     attention_backward_rows_kernel<<<dim3(ceil_div(S, kAttnRows), imgs), kThreads, smem, s>>>(qkv, probs, dA, dI, dqkv, S,
@@ -381,6 +389,7 @@ struct Node {
     float *relu1 = nullptr, *conv1 = nullptr, *relu2 = nullptr, *drop = nullptr, *res = nullptr, *td = nullptr;
     float *mu1 = nullptr, *var1 = nullptr, *mu2 = nullptr, *var2 = nullptr;
     float *z = nullptr, *qkv = nullptr, *probs = nullptr, *att = nullptr;
+    NhwcCache c1, c2, cr;     // padded NHWC copies of the conv inputs, shared by the forward conv and its weight gradient
     int id = 0;
 };
 
@@ -492,7 +501,7 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
         const size_t ein = (size_t)imgs * nd.cin * hw, eout = (size_t)imgs * nd.C * hw;
         k_group_norm_fwd(a->out, nd.relu1, nd.var1, nd.mu1, imgs, nd.cin, hw, c.group_size, quirk, s);
         k_relu(nd.relu1, ein, s);
-        conv2d_forward(nd.relu1, P + nd.w1, nd.conv1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s);
+        conv2d_forward(nd.relu1, P + nd.w1, nd.conv1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1);
         gemm_plain(false, false, imgs, nd.C, c.time_dim, n->temb, c.time_dim, P + nd.wt, nd.C, nd.td, nd.C, P + nd.bt, s);
         k_add_tile_columns(nd.conv1, imgs * nd.C, hw, nd.td, 1, s);                       // _add_time_embedding
         k_group_norm_fwd(nd.conv1, nd.relu2, nd.var2, nd.mu2, imgs, nd.C, hw, c.group_size, quirk, s);
@@ -504,9 +513,9 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
             count_launch();
             conv2_in = nd.drop;
         }
-        conv2d_forward(conv2_in, P + nd.w2, nd.out, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s);
+        conv2d_forward(conv2_in, P + nd.w2, nd.out, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2);
         if (nd.res) {
-            conv2d_forward(a->out, P + nd.wr, nd.res, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s);
+            conv2d_forward(a->out, P + nd.wr, nd.res, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, &nd.cr);
             k_add(nd.out, nd.res, eout, s);
         } else {
             k_add(nd.out, a->out, eout, s);
@@ -517,7 +526,7 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
         attn_forward(a->out, P + nd.wqkv, P + nd.wo, P + nd.bo, nd.z, nd.qkv, nd.probs, nd.att, n->sdz, nd.out, imgs, nd.C, hw, s);
         break;
     case kConv:
-        conv2d_forward(a->out, P + nd.w1, nd.out, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s);
+        conv2d_forward(a->out, P + nd.w1, nd.out, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s, &nd.c1);
         break;
     case kUp:
         upsample2_kernel<<<grid_for((size_t)imgs * nd.C * a->side * a->side, kThreads), kThreads, 0, s>>>(a->out, nd.out, (size_t)imgs * nd.C,
@@ -569,7 +578,7 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         const size_t eout = (size_t)imgs * nd.C * hw;
         const float* conv2_in = nd.drop ? nd.drop : nd.relu2;
         float *t1 = n->s1, *t2 = n->s2;
-        conv2d_wgrad(conv2_in, nd.gout, G + nd.w2, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s);
+        conv2d_wgrad(conv2_in, nd.gout, G + nd.w2, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2);
         conv2d_dgrad(nd.gout, P + nd.w2, t1, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s);
         // _dropout_mask + multi_channel_relu_ddx in one pass: a dropped or clipped activation is 0 in conv_2's input
         k_relu_backward(t1, conv2_in, t1, eout, s);
@@ -580,8 +589,8 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         count_launch();
         k_row_sum(n->sdt, imgs, nd.C, G + nd.bt, s);
         gemm_plain(true, false, c.time_dim, nd.C, imgs, n->temb, c.time_dim, n->sdt, nd.C, G + nd.wt, nd.C, nullptr, s);
-        conv2d_wgrad(nd.relu1, t2, G + nd.w1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s);
-        if (nd.res) conv2d_wgrad(a->out, nd.gout, G + nd.wr, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s);
+        conv2d_wgrad(nd.relu1, t2, G + nd.w1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1);
+        if (nd.res) conv2d_wgrad(a->out, nd.gout, G + nd.wr, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, &nd.cr);
         if (!want_din) break;
         const size_t ein = (size_t)imgs * nd.cin * hw;
         conv2d_dgrad(t2, P + nd.w1, t1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s);
@@ -610,7 +619,7 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         break;
     }
     case kConv: {
-        conv2d_wgrad(a->out, nd.gout, G + nd.w1, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s);
+        conv2d_wgrad(a->out, nd.gout, G + nd.w1, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s, &nd.c1);
         if (!want_din) break;
         Sink k = open_sink(n, nd.in0, n->s3, imgs);
         conv2d_dgrad(nd.gout, P + nd.w1, k.dst, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s);
@@ -660,6 +669,7 @@ void run_forward(bla_unet* n, const float* x, const float* temb, int imgs, bool 
     n->nodes[0].out = const_cast<float*>(stage_in(x, n->x, imgs * px, s));
     const float* t = stage_in(temb, n->temb, (size_t)imgs * c.time_dim, s);
     if (t != n->temb) BLA_CUDA(cudaMemcpyAsync(n->temb, t, (size_t)imgs * c.time_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    for (Node& nd : n->nodes) { nd.c1.valid = nd.c2.valid = nd.cr.valid = false; }   // the activations are about to change
     for (Node& nd : n->nodes) forward_node(n, nd, imgs, train, s);
 }
 
@@ -772,6 +782,7 @@ void bla_unet_destroy(bla_unet* n) {
         float* bufs[] = {nd.kind == kInput ? nullptr : nd.out, nd.gout, nd.relu1, nd.conv1, nd.relu2, nd.drop, nd.res, nd.td, nd.mu1, nd.var1,
                          nd.mu2, nd.var2, nd.z, nd.qkv, nd.probs, nd.att};
         for (float* p : bufs) if (p) pool_free(p);
+        nhwc_cache_release(&nd.c1); nhwc_cache_release(&nd.c2); nhwc_cache_release(&nd.cr);
     }
     float* bufs[] = {n->params, n->grads, n->x, n->temb, n->noise, n->s1, n->s2, n->s3, n->sq, n->sdi, n->sdz, n->sdt};
     for (float* p : bufs) if (p) pool_free(p);

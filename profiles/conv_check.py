@@ -7,7 +7,7 @@ import bla_b200 as b
 from helpers import load_oracle, ptr, rel_err
 b.bla_init(0)
 o = load_oracle(np.float64)
-for (imgs, Cin, H, W, F, k, s) in [(3, 128, 32, 32, 128, 3, 1), (4, 256, 16, 16, 256, 3, 1), (2, 128, 32, 32, 256, 3, 2), (5, 256, 8, 8, 256, 1, 1), (8, 256, 4, 4, 256, 3, 1), (9, 128, 16, 16, 128, 3, 2), (3, 256, 16, 16, 256, 1, 2), (6, 64, 8, 8, 128, 3, 1)]:
+for (imgs, Cin, H, W, F, k, s) in [(3, 128, 32, 32, 128, 3, 1), (4, 256, 16, 16, 256, 3, 1), (2, 128, 32, 32, 256, 3, 2), (5, 256, 8, 8, 256, 1, 1), (8, 256, 4, 4, 256, 3, 1), (9, 128, 16, 16, 128, 3, 2), (3, 256, 16, 16, 256, 1, 2), (6, 64, 8, 8, 128, 3, 1), (64, 256, 8, 8, 256, 3, 2), (48, 512, 4, 4, 256, 3, 1), (32, 512, 4, 4, 256, 1, 1), (64, 64, 4, 4, 128, 3, 2), (4, 3, 32, 32, 128, 3, 1), (4, 128, 32, 32, 3, 3, 1), (4, 3, 32, 32, 128, 1, 1), (5, 40, 16, 16, 72, 3, 1)]:
     rng = np.random.default_rng(1)
     Ho, Wo = -(-H // s), -(-W // s)
     x = rng.normal(size=(imgs, Cin, H, W)); kr = rng.normal(0, 0.05, (F, Cin, k, k)); dy = rng.normal(size=(imgs, F, Ho, Wo))

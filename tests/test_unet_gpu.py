@@ -12,6 +12,16 @@ import unet_ref
 
 pytestmark = pytest.mark.gpu
 
+@pytest.fixture(scope="module")
+def bla():
+    import bla_b200 as b
+    assert b.bla_device_count() >= 1
+    assert not b.MISSING
+    b.bla_set_gemm_path(b.GEMM_FP32)
+    b.bla_set_quirks(1)
+    return b
+
+
 SMALL = dict(image_side=16, dims=(32, 64, 64, 32), time_dim=24, kernel_size=3, group_size=8, key_dim=16)
 FULL = dict(image_side=32, dims=(128, 256, 256, 256), time_dim=512, kernel_size=3, group_size=32, key_dim=16)   # cifar_unet.c:26-37
 
