@@ -630,7 +630,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                             }
                         }
                     }
-                    if (p.conv == 1 && p.cv_P < 32) {
+                    if (p.conv == 1 && !p.partial && p.cv_P < 32) {
                         // small images (P = 4, 8 or 16 output pixels): the 32 columns of this chunk are 32/P whole images; lane =
                         // filter row writes P contiguous floats per image straight from its registers (64-byte runs for 4 x 4)
                         if (row_ok) {
@@ -655,7 +655,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.conv != 1) {
+                        if (p.conv != 1 || p.partial) {
                             tma_store_2d(&tma_c, col0, (p.partial ? split * p.m : 0) + row_base, stg_u32 + sbuf * 4096);
                         } else {
                             const int img = col0 / p.cv_P, pix = col0 - img * p.cv_P;
@@ -768,7 +768,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 // every thread keeps 8 independent 128-bit loads in flight, the four group sums are combined through shared memory.
 __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p) {
     const size_t total = (size_t)p.m * p.n;
-    if ((total & 3) == 0 && (p.n & 3) == 0 && p.c_vec) {
+    if ((total & 3) == 0 && (p.n & 3) == 0 && (p.c_vec || p.conv == 1)) {
         __shared__ float4 part[4][64];
         const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
         const size_t total4 = total >> 2;
@@ -791,10 +791,15 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p)
                 for (int g2 = 1; g2 < 4; ++g2) { t.x += part[g2][col].x; t.y += part[g2][col].y; t.z += part[g2][col].z; t.w += part[g2][col].w; }
                 const size_t e = e4 << 2;
                 const int i = (int)(e / p.n), j = (int)(e % p.n);
-                float4 o;
-                o.x = epilogue_value(t.x, i, j, p); o.y = epilogue_value(t.y, i, j + 1, p);
-                o.z = epilogue_value(t.z, i, j + 2, p); o.w = epilogue_value(t.w, i, j + 3, p);
-                *reinterpret_cast<float4*>(p.c + (size_t)i * p.ldc + j) = o;
+                if (p.conv == 1) {   // row i = filter, column j = (image, pixel) -> y [img][F][P]; P is a multiple of 4
+                    const int img = j / p.cv_P, pix = j - img * p.cv_P;
+                    *reinterpret_cast<float4*>(p.c + ((size_t)img * p.m + i) * p.cv_P + pix) = t;
+                } else {
+                    float4 o;
+                    o.x = epilogue_value(t.x, i, j, p); o.y = epilogue_value(t.y, i, j + 1, p);
+                    o.z = epilogue_value(t.z, i, j + 2, p); o.w = epilogue_value(t.w, i, j + 3, p);
+                    *reinterpret_cast<float4*>(p.c + (size_t)i * p.ldc + j) = o;
+                }
             }
             __syncthreads();
         }
@@ -948,13 +953,38 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         p.cv_bh = 32 / p.cv_bw < cv.Ho ? 32 / p.cv_bw : cv.Ho;
     }
     const int gran = p.cluster == 2 ? 64 : 32;   // whole 32-column epilogue chunks / MN-major atoms (per CTA half)
-    {
+    int conv_splits = 0;   // > 0: chosen together with the tile width below (conv forward only)
+    if (cmode == 1) {
+        // Convolutions over small images have few output columns (64 images of 4 x 4 pixels: 1024) but a long contraction
+        // (k*k*C up to 4608): pick tile width AND split-K together from a cycle model of one k-block -- the 3 x 2 MMAs of a
+        // 128 x bn x 8 tile (185 cycles at bn = 256) against the TMA fill of the stage (~24 B/clk/SM) -- plus the cost of
+        // writing and re-reading the partial sums.
+        const int slots = rt().num_sms / p.cluster;
+        const int m_units = p.m_tiles / p.cluster;
+        double best = -1.0;
+        int best_bn = BN, best_sp = 1;
+        for (int bn = BN; bn >= gran; bn -= gran) {
+            const long long tiles_ = (long long)m_units * ceil_div(g.n, bn);
+            const double mma = 6.0 * 185.0 * bn / 256.0, fill = (kABytes + (double)(bn / p.cluster) * BK * 4) / 24.0;
+            const double per_kb = (mma > fill ? mma : fill) + 40.0;
+            for (int sp = 1; sp <= 32; ++sp) {
+                if (sp > 1 && (p.kblocks / sp < 8 || g.m % BM != 0)) break;
+                const long long waves = (tiles_ * sp + slots - 1) / slots;
+                const int kb = ceil_div(p.kblocks, sp);
+                double cost = (double)waves * (kb * per_kb + 1500.0);                                  // + tile prologue / epilogue
+                if (sp > 1) cost += (double)(sp + 1) * g.m * g.n * 4.0 / 1500.0 + 4000.0;               // partials out and back, 2nd launch
+                if (best < 0 || cost < best) { best = cost; best_bn = bn; best_sp = sp; }
+            }
+        }
+        p.n_tiles = ceil_div(g.n, best_bn);
+        p.bn = best_bn;
+        conv_splits = best_sp;
+    } else {
         const int slots = rt().num_sms / p.cluster;
         const int m_units = p.m_tiles / p.cluster;
         double best_cost = -1.0;
         int best_bn = BN;
-        // conv has no split-K: a small batch of small images is spread over the SMs by narrower tiles instead
-        for (int bn = BN; bn >= (cmode == 1 ? gran : 192); bn -= gran) {
+        for (int bn = BN; bn >= 192; bn -= gran) {
             const long long units_ = (long long)m_units * ceil_div(g.n, bn);
             const long long waves = (units_ + slots - 1) / slots;
             // measured on B200 (square 4096): a 192-wide tile costs 1.33x more per column than a 256-wide one
@@ -981,7 +1011,9 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     const int sms = rt().num_sms;
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     int splits = 1;
-    if (cmode != 1 && tiles * 2 <= sms && p.kblocks >= 32) {
+    if (cmode == 1) {
+        splits = conv_splits;
+    } else if (tiles * 2 <= sms && p.kblocks >= 32) {
         long long want = (sms / p.cluster) / (tiles / p.cluster);          // one wave: units * splits <= cluster slots
         long long maxs = p.kblocks / 16;
         splits = (int)(want < maxs ? want : maxs);
@@ -1001,8 +1033,11 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     memset(&mc, 0, sizeof(mc));
     p.tma_store = p.c_vec && !g.epi.pre_activation && !g.epi.bias_cols &&
                   (splits == 1 || (g.m % BM == 0 && g.n % 4 == 0));
-    if (cmode == 1) {
+    if (cmode == 1 && splits == 1) {
         p.tma_store = make_map_conv_out(&mc, *g.conv);
+        if (!p.tma_store) { if (ws) pool_free(ws); return false; }
+    } else if (cmode == 1) {   // split-K partials [splits][F][imgs*P] (F a multiple of 128 here); the reduce kernel writes y
+        p.tma_store = make_map_c(&mc, ws, (long long)splits * g.m, g.n, g.n);
         if (!p.tma_store) { if (ws) pool_free(ws); return false; }
     } else if (p.tma_store) {
         p.tma_store = splits == 1 ? make_map_c(&mc, g.c, g.m, g.n, g.ldc) : make_map_c(&mc, ws, (long long)splits * g.m, g.n, g.n);

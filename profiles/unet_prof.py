@@ -10,7 +10,7 @@ imgs = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 path = sys.argv[3] if len(sys.argv) > 3 else "tc"
 b.bla_init(0)
-b.bla_set_gemm_path(b.GEMM_3XTF32 if path == "tc" else b.GEMM_FP32)
+b.bla_set_gemm_path({"tc": b.GEMM_AUTO, "tc_forced": b.GEMM_3XTF32, "fp32": b.GEMM_FP32}[path])
 b.bla_set_quirks(int(os.environ.get("BLA_QUIRKS", "1")))
 uc = b.UnetConfig(32, (C.c_int * 4)(128, 256, 256, 256), 512, 3, 32, 16, 0.1, imgs, 7)
 net = b.bla_unet_create(C.byref(uc))
