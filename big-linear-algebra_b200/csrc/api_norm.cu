@@ -459,6 +459,60 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_tma(const floa
     }
 }
 
+// ---- small slabs (<= 8192 elements: 32 channels of a 16 x 16, 8 x 8 or 4 x 4 image) ---------------------------------------
+// One 256-thread CTA per (image, group), the whole slab of x and dy in registers (read once, 12 B/elem), one shuffle + shared
+// memory reduction, no cluster: many small CTAs per SM hide each other's latency.  (The persistent cluster kernel below
+// spends ~7 us per slab on its barrier chain whatever the slab size: 50 us for 512 slabs of 2 KB.)
+constexpr int kSmallThreads = 256;
+template <int F4>
+__global__ void __launch_bounds__(kSmallThreads) group_norm_bwd_small(const float* __restrict__ dy, float* __restrict__ dx,
+                                                                      const float* __restrict__ x, const float* __restrict__ means,
+                                                                      const float* __restrict__ stdevs, GnParams p) {
+    __shared__ float red[2][kSmallThreads / 32];
+    const int g = blockIdx.x, img = blockIdx.y;
+    const int c0 = g * p.group_size;
+    const int nc = min(p.group_size, p.C - c0);
+    const int n4 = (nc * p.HW) >> 2;
+    const size_t off = ((size_t)img * p.C + c0) * p.HW;
+    const float4* xs = reinterpret_cast<const float4*>(x + off);
+    const float4* gs4 = reinterpret_cast<const float4*>(dy + off);
+    float4* ds = reinterpret_cast<float4*>(dx + off);
+    const float mu = means[(size_t)img * p.G + g], sd = stdevs[(size_t)img * p.G + g];
+    float4 w[F4], d[F4];
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = threadIdx.x + u * kSmallThreads;
+        const bool ok = i < n4;
+        w[u] = ok ? __ldg(xs + i) : make_float4(mu, mu, mu, mu);
+        d[u] = ok ? __ldg(gs4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float gs = 0.f, gw = 0.f;
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        w[u].x = (w[u].x - mu) / sd; w[u].y = (w[u].y - mu) / sd; w[u].z = (w[u].z - mu) / sd; w[u].w = (w[u].w - mu) / sd;
+        gs += (d[u].x + d[u].y) + (d[u].z + d[u].w);
+        gw += (w[u].x * d[u].x + w[u].y * d[u].y) + (w[u].z * d[u].z + w[u].w * d[u].w);
+    }
+    gs = warp_sum(gs); gw = warp_sum(gw);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = gs; red[1][threadIdx.x >> 5] = gw; }
+    __syncthreads();
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSmallThreads / 32; ++k) { t0 += red[0][k]; t1 += red[1][k]; }   // same order in every thread
+    const float inv_n = 1.f / (float)(nc * p.HW);
+    const float mean_g = t0 * inv_n, mean_gw = t1 * inv_n;
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = threadIdx.x + u * kSmallThreads;
+        if (i < n4) {
+            float4 o;
+            o.x = (d[u].x - mean_g - w[u].x * mean_gw) / sd; o.y = (d[u].y - mean_g - w[u].y * mean_gw) / sd;
+            o.z = (d[u].z - mean_g - w[u].z * mean_gw) / sd; o.w = (d[u].w - mean_g - w[u].w * mean_gw) / sd;
+            ds[i] = o;
+        }
+    }
+}
+
 // ---- persistent backward: 2-CTA clusters + TMA bulk prefetch + DSMEM sums ---------------------------------------
 // A cluster owns one (image, group) slab at a time; each CTA handles half of it.  The NEXT slab's halves of x and dy
 // are fetched into shared memory by cp.async.bulk while the current ones -- already in registers -- are reduced
@@ -630,7 +684,10 @@ void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* m
     dim3 grid(p.G, images);
     const bool vec_ok = al16(dy) && al16(dx) && al16(x) && (HW % 4 == 0);
     const bool tail_ok = (C % group_size == 0) || (((size_t)(C % group_size) * HW) % 4 == 0);
-    if (vec_ok && tail_ok && slab <= (size_t)2 * kFastThreads * 4 * 4 && slab % 8 == 0 && (long long)p.G * images >= (long long)rt().num_sms) {
+    if (vec_ok && tail_ok && slab <= (size_t)kSmallThreads * 8 * 4 && (long long)p.G * images >= 2LL * rt().num_sms) {
+        if (slab <= (size_t)kSmallThreads * 2 * 4) group_norm_bwd_small<2><<<grid, kSmallThreads, 0, s>>>(dy, dx, x, means, stdevs, p);
+        else group_norm_bwd_small<8><<<grid, kSmallThreads, 0, s>>>(dy, dx, x, means, stdevs, p);
+    } else if (vec_ok && tail_ok && slab <= (size_t)2 * kFastThreads * 4 * 4 && slab % 8 == 0 && (long long)p.G * images >= (long long)rt().num_sms) {
         // many slabs: persistent 2-CTA clusters with TMA prefetch (each CTA's half slab must be a whole number of float4)
         static bool attr = false;
         const int smem = 2 * kFastThreads * 4 * 16;   // 128 KB
