@@ -591,7 +591,40 @@ def run_extras(b, torch, stream, pk):
         out["conv"].append(row)
         for p_ in (dxp, dwp, dyp, gxp, gwp):
             b.bla_free(p_)
+    out["unet"] = run_unet(b, t, pk)
     return out
+
+
+def run_unet(b, t, pk, imgs=64):
+    """BASELINE.json configs[4]: model/cifar_unet.c (32x32x3, widths 128/256/256/256, 22 ResNet blocks, 5 attention blocks) as one
+    batched device-resident training step -- forward, MSE against the noise, full backward, SGD -- on a synthetic batch.
+    Algorithmic work: 7.13 GFLOP per image forward, 3x that for a training step.  The reference does one image
+    at a time on one core: 30.6 s per forward+backward (probed with gcc -O2)."""
+    uc = b.UnetConfig(32, (C.c_int * 4)(128, 256, 256, 256), 512, 3, 32, 16, 0.1, imgs, 7)
+    net = b.bla_unet_create(C.byref(uc))
+    b.bla_unet_init_params(net, 42)
+    n3 = imgs * 3 * 32 * 32
+    x = b.bla_malloc_device(n3 * 4); nz = b.bla_malloc_device(n3 * 4); te = b.bla_malloc_device(imgs * 512 * 4); o = b.bla_malloc_device(n3 * 4)
+    b.bla_fill_uniform(x, n3, 1, -1, 1); b.bla_fill_uniform(nz, n3, 2, -1, 1); b.bla_fill_uniform(te, imgs * 512, 3, -1, 1)
+    l0 = b.bla_launch_count()
+    loss = np.zeros(1)
+    b.bla_unet_train_step(net, x, te, nz, imgs, 1e-6, loss.ctypes.data_as(C.c_void_p))
+    launches = int(b.bla_launch_count() - l0)
+    step_ms = t(lambda: b.bla_unet_train_step(net, x, te, nz, imgs, 1e-6, None), 5, warm=2)
+    fwd_ms = t(lambda: b.bla_unet_forward(net, x, te, imgs, o), 5, warm=2)
+    peak = pk["bf16"] / 6.0
+    res = {"workload": "model/cifar_unet.c train step, batch of %d synthetic 32x32x3 images, GEMM path auto (convs: 3xTF32 tcgen05), "
+                       "BLA_QUIRKS=%d, dropout 0.1" % (imgs, b.bla_get_quirks()),
+           "images": imgs, "params": int(b.bla_unet_num_params(net)), "launches_per_step": launches,
+           "train_ms_per_step": step_ms, "train_images_per_s": imgs / (step_ms * 1e-3),
+           "train_tflops": 3 * 7.13e9 * imgs / (step_ms * 1e-3) / 1e12, "train_frac_3xtf32_peak": 3 * 7.13e9 * imgs / (step_ms * 1e-3) / 1e12 / peak,
+           "forward_ms": fwd_ms, "forward_images_per_s": imgs / (fwd_ms * 1e-3), "forward_tflops": 7.13e9 * imgs / (fwd_ms * 1e-3) / 1e12,
+           "loss_per_image": float(loss[0]) / imgs,
+           "reference_cpu_images_per_s": 1.0 / 30.6, "reference_cpu_note": "one image forward+backward, single-threaded, SURVEY 3.2 (probed)"}
+    b.bla_unet_destroy(net)
+    for p_ in (x, nz, te, o):
+        b.bla_free(p_)
+    return res
 
 
 if __name__ == "__main__":

@@ -296,6 +296,93 @@ __global__ void __launch_bounds__(kThreads) attention_backward_cols_kernel(const
     }
 }
 
+// ---- time-embedding projections of ALL ResNet blocks in one launch (cifar_unet.c:1050-1052, :1192-1200) -------------------
+// Every block projects the same [imgs][T] embedding with its own [T][C] weights: 22 GEMMs of 64 x 512 x C are launch-bound one
+// by one (18-25 us each); as one grid over (channel tile, image tile, block) they take one launch.
+struct TimeProj { const float* w; const float* b; float* out; float* gw; float* gb; const float* dtd; int C; };
+
+// out_b[img][c] = sum_t temb[img][t] w_b[t][c] + b_b[c].  CTA = 64 images x 64 channels, K in chunks of 16, 4 x 4 outputs per thread.
+__global__ void __launch_bounds__(kThreads) time_dense_forward_kernel(const TimeProj* __restrict__ table, const float* __restrict__ temb, int imgs,
+                                                                      int T) {
+    __shared__ float As[16][65], Bs[16][64];
+    const TimeProj tp = table[blockIdx.z];
+    const int c0 = blockIdx.x * 64, i0 = blockIdx.y * 64;
+    if (c0 >= tp.C) return;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, each 4 images x 4 channels
+    float acc[4][4] = {};
+    for (int t0 = 0; t0 < T; t0 += 16) {
+        for (int e = threadIdx.x; e < 64 * 16; e += kThreads) {
+            const int ii = e >> 4, tt = e & 15;
+            As[tt][ii] = (i0 + ii < imgs && t0 + tt < T) ? temb[(size_t)(i0 + ii) * T + t0 + tt] : 0.f;
+            const int t2 = e >> 6, cc = e & 63;
+            Bs[t2][cc] = (t0 + t2 < T && c0 + cc < tp.C) ? tp.w[(size_t)(t0 + t2) * tp.C + c0 + cc] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tt = 0; tt < 16; ++tt) {
+            float a[4], bq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = As[tt][ty * 4 + u]; bq[u] = Bs[tt][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], bq[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int i = i0 + ty * 4 + u, c = c0 + tx * 4 + v;
+            if (i < imgs && c < tp.C) tp.out[(size_t)i * tp.C + c] = acc[u][v] + tp.b[c];
+        }
+}
+
+// gw_b[t][c] = sum_img temb[img][t] dtd_b[img][c];  gb_b[c] = sum_img dtd_b[img][c].  CTA = 64 t x 64 channels, K = images.
+__global__ void __launch_bounds__(kThreads) time_dense_backward_kernel(const TimeProj* __restrict__ table, const float* __restrict__ temb, int imgs,
+                                                                       int T) {
+    __shared__ float As[16][65], Bs[16][64];
+    const TimeProj tp = table[blockIdx.z];
+    const int c0 = blockIdx.x * 64, t0 = blockIdx.y * 64;
+    if (c0 >= tp.C) return;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    float bsum[4] = {};
+    for (int i0 = 0; i0 < imgs; i0 += 16) {
+        for (int e = threadIdx.x; e < 64 * 16; e += kThreads) {
+            const int ii = e >> 6, tt = e & 63;
+            As[ii][tt] = (i0 + ii < imgs && t0 + tt < T) ? temb[(size_t)(i0 + ii) * T + t0 + tt] : 0.f;
+            Bs[ii][tt] = (i0 + ii < imgs && c0 + tt < tp.C) ? tp.dtd[(size_t)(i0 + ii) * tp.C + c0 + tt] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) {
+            float a[4], bq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = As[ii][ty * 4 + u]; bq[u] = Bs[ii][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                bsum[u] += bq[u];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], bq[v], acc[u][v]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int t = t0 + ty * 4 + u, c = c0 + tx * 4 + v;
+            if (t < T && c < tp.C) tp.gw[(size_t)t * tp.C + c] = acc[u][v];
+        }
+    if (blockIdx.y == 0 && ty == 0)
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+            if (c0 + tx * 4 + v < tp.C) tp.gb[c0 + tx * 4 + v] = bsum[v];
+}
+
 // ---- launch helpers ------------------------------------------------------------------------------------------------
 void slab(float* dst, size_t dpitch, const float* src, size_t spitch, size_t width, int rows, bool accumulate, cudaStream_t s) {
     if (width % 4) die("bla: U-Net slabs must be multiples of 4 floats, exiting");
@@ -386,7 +473,7 @@ struct Node {
     size_t w1 = (size_t)-1, w2 = (size_t)-1, wt = (size_t)-1, bt = (size_t)-1, wr = (size_t)-1;   // res block / conv (w1)
     size_t wqkv = (size_t)-1, wo = (size_t)-1, bo = (size_t)-1;                                   // attention
     // saved activations
-    float *relu1 = nullptr, *conv1 = nullptr, *relu2 = nullptr, *drop = nullptr, *res = nullptr, *td = nullptr;
+    float *relu1 = nullptr, *conv1 = nullptr, *relu2 = nullptr, *drop = nullptr, *res = nullptr, *td = nullptr, *dtd = nullptr;
     float *mu1 = nullptr, *var1 = nullptr, *mu2 = nullptr, *var2 = nullptr;
     float *z = nullptr, *qkv = nullptr, *probs = nullptr, *att = nullptr;
     NhwcCache c1, c2, cr;     // padded NHWC copies of the conv inputs, shared by the forward conv and its weight gradient
@@ -406,7 +493,8 @@ struct bla_unet {
     float *x = nullptr, *temb = nullptr, *noise = nullptr;   // staging for host-side batches
     float *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;        // backward scratch, each max activation size
     float *sq = nullptr, *sdi = nullptr, *sdz = nullptr;      // attention scratch: dqkv, dI, dZ / dense
-    float* sdt = nullptr;                                     // time-dense gradient [imgs][Cmax]
+    TimeProj* time_table = nullptr;                           // device table of the ResNet blocks' time projections
+    int time_blocks = 0, time_cmax = 0;
     double* loss = nullptr;
     unsigned long long step = 0;
     int out_node = -1;
@@ -447,7 +535,7 @@ int add_res(bla_unet* n, const std::string& name, int in, int cout) {
     nd.drop = c.dropout > 0.f ? dev_alloc(m * cout * hw) : nullptr;
     nd.res = src.C != cout ? dev_alloc(m * cout * hw) : nullptr;
     nd.out = dev_alloc(m * cout * hw); nd.gout = dev_alloc(m * cout * hw);
-    nd.td = dev_alloc(m * cout);
+    nd.td = dev_alloc(m * cout); nd.dtd = dev_alloc(m * cout);
     nd.mu1 = dev_alloc(m * g1); nd.var1 = dev_alloc(m * g1); nd.mu2 = dev_alloc(m * g2); nd.var2 = dev_alloc(m * g2);
     return add_node(n, nd);
 }
@@ -502,7 +590,6 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
         k_group_norm_fwd(a->out, nd.relu1, nd.var1, nd.mu1, imgs, nd.cin, hw, c.group_size, quirk, s);
         k_relu(nd.relu1, ein, s);
         conv2d_forward(nd.relu1, P + nd.w1, nd.conv1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1);
-        gemm_plain(false, false, imgs, nd.C, c.time_dim, n->temb, c.time_dim, P + nd.wt, nd.C, nd.td, nd.C, P + nd.bt, s);
         k_add_tile_columns(nd.conv1, imgs * nd.C, hw, nd.td, 1, s);                       // _add_time_embedding
         k_group_norm_fwd(nd.conv1, nd.relu2, nd.var2, nd.mu2, imgs, nd.C, hw, c.group_size, quirk, s);
         k_relu(nd.relu2, eout, s);
@@ -584,11 +671,9 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         k_relu_backward(t1, conv2_in, t1, eout, s);
         k_group_norm_bwd(t1, t2, nd.conv1, nd.mu2, nd.var2, imgs, nd.C, hw, c.group_size, s);           // t2 = d conv_1 output
         // time embedding projection (:1192-1200)
-        plane_sum_kernel<<<grid_for((size_t)imgs * nd.C, kThreads / 32), kThreads, 0, s>>>(t2, imgs * nd.C, hw, n->sdt);
+        plane_sum_kernel<<<grid_for((size_t)imgs * nd.C, kThreads / 32), kThreads, 0, s>>>(t2, imgs * nd.C, hw, nd.dtd);
         BLA_LAUNCH_CHECK();
-        count_launch();
-        k_row_sum(n->sdt, imgs, nd.C, G + nd.bt, s);
-        gemm_plain(true, false, c.time_dim, nd.C, imgs, n->temb, c.time_dim, n->sdt, nd.C, G + nd.wt, nd.C, nullptr, s);
+        count_launch();   // the projections' weight / bias gradients of all blocks follow in one launch at the end of the pass
         conv2d_wgrad(nd.relu1, t2, G + nd.w1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1);
         if (nd.res) conv2d_wgrad(a->out, nd.gout, G + nd.wr, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, &nd.cr);
         if (!want_din) break;
@@ -670,6 +755,10 @@ void run_forward(bla_unet* n, const float* x, const float* temb, int imgs, bool 
     const float* t = stage_in(temb, n->temb, (size_t)imgs * c.time_dim, s);
     if (t != n->temb) BLA_CUDA(cudaMemcpyAsync(n->temb, t, (size_t)imgs * c.time_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
     for (Node& nd : n->nodes) { nd.c1.valid = nd.c2.valid = nd.cr.valid = false; }   // the activations are about to change
+    time_dense_forward_kernel<<<dim3(ceil_div(n->time_cmax, 64), ceil_div(imgs, 64), n->time_blocks), kThreads, 0, s>>>(n->time_table, n->temb, imgs,
+                                                                                                                    c.time_dim);
+    BLA_LAUNCH_CHECK();
+    count_launch();
     for (Node& nd : n->nodes) forward_node(n, nd, imgs, train, s);
 }
 
@@ -766,7 +855,18 @@ bla_unet* bla_unet_create(const bla_unet_config* cfg) {
     const size_t m = c.max_imgs;
     n->s1 = dev_alloc(m * max_act); n->s2 = dev_alloc(m * max_act); n->s3 = dev_alloc(m * max_act);
     n->sq = dev_alloc(m * max_tok); n->sdi = dev_alloc(m * max_ss); n->sdz = dev_alloc(m * max_act);
-    n->sdt = dev_alloc(m * max_c);
+    {
+        std::vector<TimeProj> table;
+        for (const Node& nd : n->nodes)
+            if (nd.kind == kRes) {
+                table.push_back({n->params + nd.wt, n->params + nd.bt, nd.td, n->grads + nd.wt, n->grads + nd.bt, nd.dtd, nd.C});
+                if (nd.C > n->time_cmax) n->time_cmax = nd.C;
+            }
+        n->time_blocks = (int)table.size();
+        n->time_table = (TimeProj*)pool_alloc(kDevice, table.size() * sizeof(TimeProj));
+        BLA_CUDA(cudaMemcpyAsync(n->time_table, table.data(), table.size() * sizeof(TimeProj), cudaMemcpyHostToDevice, rt().stream));
+        BLA_CUDA(cudaStreamSynchronize(rt().stream));
+    }
     n->x = dev_alloc(m * 3 * c.image_side * c.image_side);
     n->noise = dev_alloc(m * 3 * c.image_side * c.image_side);
     n->temb = dev_alloc(m * c.time_dim);
@@ -779,14 +879,15 @@ void bla_unet_destroy(bla_unet* n) {
     if (!n) return;
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
     for (Node& nd : n->nodes) {
-        float* bufs[] = {nd.kind == kInput ? nullptr : nd.out, nd.gout, nd.relu1, nd.conv1, nd.relu2, nd.drop, nd.res, nd.td, nd.mu1, nd.var1,
+        float* bufs[] = {nd.kind == kInput ? nullptr : nd.out, nd.gout, nd.relu1, nd.conv1, nd.relu2, nd.drop, nd.res, nd.td, nd.dtd, nd.mu1, nd.var1,
                          nd.mu2, nd.var2, nd.z, nd.qkv, nd.probs, nd.att};
         for (float* p : bufs) if (p) pool_free(p);
         nhwc_cache_release(&nd.c1); nhwc_cache_release(&nd.c2); nhwc_cache_release(&nd.cr);
     }
-    float* bufs[] = {n->params, n->grads, n->x, n->temb, n->noise, n->s1, n->s2, n->s3, n->sq, n->sdi, n->sdz, n->sdt};
+    float* bufs[] = {n->params, n->grads, n->x, n->temb, n->noise, n->s1, n->s2, n->s3, n->sq, n->sdi, n->sdz};
     for (float* p : bufs) if (p) pool_free(p);
     pool_free(n->loss);
+    pool_free(n->time_table);
     delete n;
 }
 
@@ -854,6 +955,10 @@ void bla_unet_train_step(bla_unet* n, const float* x, const float* time_emb, con
     for (Node& nd : n->nodes) nd.gout_set = false;
     o.gout_set = true;
     for (int i = (int)n->nodes.size() - 1; i > 0; --i) backward_node(n, n->nodes[i], imgs, s);
+    time_dense_backward_kernel<<<dim3(ceil_div(n->time_cmax, 64), ceil_div(c.time_dim, 64), n->time_blocks), kThreads, 0, s>>>(n->time_table, n->temb,
+                                                                                                                            imgs, c.time_dim);
+    BLA_LAUNCH_CHECK();
+    count_launch();
     if (comm_active()) {   // data parallel over images: gradients are sums over samples
         comm_allreduce_f32_on(n->grads, n->nparams, s);
         comm_allreduce_f64_on(n->loss, 1, s);
