@@ -47,7 +47,36 @@ __device__ __forceinline__ float block_total(float v, float* sh) {
 struct GnParams {
     int C, HW, group_size, G;   // per image
     int quirk;
+    // fused neighbours (kernels.h GnFuse): forward y = dropout(relu(norm(x))), backward dy is gated by the same two masks
+    int relu;
+    float drop_rate;
+    unsigned long long drop_seed;
 };
+
+// forward epilogue on element `idx` of the whole [images][C][HW] tensor
+__device__ __forceinline__ float gn_post(float q, size_t idx, const GnParams& p) {
+    if (p.relu) q = q > 0.f ? q : 0.f;                                                     // multi_channel_relu, cifar_unet.c:235
+    if (p.drop_rate > 0.f && uniform_at(p.drop_seed, idx, 0.f, 1.f) < p.drop_rate) q = 0.f;   // _dropout, cifar_unet.c:1032
+    return q;
+}
+__device__ __forceinline__ float4 gn_post4(float4 q, size_t idx, const GnParams& p) {
+    if (p.relu | (p.drop_rate > 0.f)) { q.x = gn_post(q.x, idx, p); q.y = gn_post(q.y, idx + 1, p); q.z = gn_post(q.z, idx + 2, p); q.w = gn_post(q.w, idx + 3, p); }
+    return q;
+}
+// backward: the upstream gradient passes where the fused forward let the activation through.  relu(norm(x)) > 0 <=> x > mean
+// (the divisor is positive), so the ReLU mask needs no saved activation; the dropout mask is regenerated from its counter.
+__device__ __forceinline__ float gn_gate(float d, float xv, float mu, size_t idx, const GnParams& p) {
+    if (p.relu && !(xv > mu)) d = 0.f;                                                      // multi_channel_relu_ddx, cifar_unet.c:241
+    if (p.drop_rate > 0.f && uniform_at(p.drop_seed, idx, 0.f, 1.f) < p.drop_rate) d = 0.f;   // _dropout_mask, cifar_unet.c:1170
+    return d;
+}
+__device__ __forceinline__ float4 gn_gate4(float4 d, float4 xv, float mu, size_t idx, const GnParams& p) {
+    if (p.relu | (p.drop_rate > 0.f)) {
+        d.x = gn_gate(d.x, xv.x, mu, idx, p); d.y = gn_gate(d.y, xv.y, mu, idx + 1, p);
+        d.z = gn_gate(d.z, xv.z, mu, idx + 2, p); d.w = gn_gate(d.w, xv.w, mu, idx + 3, p);
+    }
+    return d;
+}
 
 // grid = (G, images).  x,y: [images][C][HW]; means/vars: [images][G]
 template <bool IN_SMEM>
@@ -96,10 +125,10 @@ __global__ void __launch_bounds__(kThreads) group_norm_fwd_kernel(const float* _
         for (size_t i = threadIdx.x; i < n / 4; i += kThreads) {
             float4 v = IN_SMEM ? reinterpret_cast<const float4*>(slab)[i] : reinterpret_cast<const float4*>(xs)[i];
             v.x = (v.x - mean) / denom; v.y = (v.y - mean) / denom; v.z = (v.z - mean) / denom; v.w = (v.w - mean) / denom;
-            reinterpret_cast<float4*>(ys)[i] = v;
+            reinterpret_cast<float4*>(ys)[i] = gn_post4(v, off + 4 * i, p);
         }
     } else {
-        for (size_t i = threadIdx.x; i < n; i += kThreads) ys[i] = (src[i] - mean) / denom;
+        for (size_t i = threadIdx.x; i < n; i += kThreads) ys[i] = gn_post((src[i] - mean) / denom, off + i, p);
     }
 }
 
@@ -118,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) group_norm_bwd_kernel(const float* _
     float gs = 0.f, gw = 0.f;
     for (size_t i = threadIdx.x; i < n; i += kThreads) {
         float w = (x[off + i] - mu) / sd;
-        float d = dy[off + i];
+        float d = gn_gate(dy[off + i], x[off + i], mu, off + i, p);
         if (IN_SMEM) { slab[i] = w; slab[n + i] = d; }
         gs += d;
         gw += w * d;
@@ -127,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) group_norm_bwd_kernel(const float* _
     const float mean_gw = block_total(gw, red) / (float)(int)n;
     for (size_t i = threadIdx.x; i < n; i += kThreads) {
         float w = IN_SMEM ? slab[i] : (x[off + i] - mu) / sd;
-        float d = IN_SMEM ? slab[n + i] : dy[off + i];
+        float d = IN_SMEM ? slab[n + i] : gn_gate(dy[off + i], x[off + i], mu, off + i, p);
         dx[off + i] = (d - mean_g - w * mean_gw) / sd;
     }
 }
@@ -195,7 +224,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_regs(const flo
         if (i < n4) {
             float4 o;
             o.x = (v[u].x - mean) / denom; o.y = (v[u].y - mean) / denom; o.z = (v[u].z - mean) / denom; o.w = (v[u].w - mean) / denom;
-            ys[i] = o;
+            ys[i] = gn_post4(o, off + 4 * (size_t)i, p);
         }
     }
 }
@@ -218,7 +247,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_vec(const floa
     float gs = 0.f, gw = 0.f;
 #pragma unroll 4
     for (int i = threadIdx.x; i < n4; i += kFastThreads) {
-        const float4 a = xs[i], d = gs4[i];
+        const float4 a = xs[i];
+        const float4 d = gn_gate4(gs4[i], a, mu, off + 4 * (size_t)i, p);
         gs += (d.x + d.y) + (d.z + d.w);
         gw += ((a.x - mu) / sd * d.x + (a.y - mu) / sd * d.y) + ((a.z - mu) / sd * d.z + (a.w - mu) / sd * d.w);
     }
@@ -227,7 +257,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_vec(const floa
     const float mean_gw = block_total_1024(gw, red) * inv_n;
 #pragma unroll 4
     for (int i = threadIdx.x; i < n4; i += kFastThreads) {
-        const float4 a = xs[i], d = gs4[i];
+        const float4 a = xs[i];
+        const float4 d = gn_gate4(gs4[i], a, mu, off + 4 * (size_t)i, p);
         float4 o;
         o.x = (d.x - mean_g - (a.x - mu) / sd * mean_gw) / sd; o.y = (d.y - mean_g - (a.y - mu) / sd * mean_gw) / sd;
         o.z = (d.z - mean_g - (a.z - mu) / sd * mean_gw) / sd; o.w = (d.w - mean_g - (a.w - mu) / sd * mean_gw) / sd;
@@ -314,7 +345,7 @@ __global__ void __launch_bounds__(kClThreads, 2) group_norm_fwd_cluster(const fl
         if (i < end) {
             float4 o;
             o.x = (v[u].x - mean) / denom; o.y = (v[u].y - mean) / denom; o.z = (v[u].z - mean) / denom; o.w = (v[u].w - mean) / denom;
-            ys[i] = o;
+            ys[i] = gn_post4(o, off + 4 * (size_t)i, p);
         }
     }
     cluster.sync();   // no CTA may exit while a peer can still read its shared memory
@@ -346,7 +377,7 @@ __global__ void __launch_bounds__(kClThreads, 2) group_norm_bwd_cluster(const fl
     for (int u = 0; u < F4; ++u) {
         const int i = beg + threadIdx.x + u * kClThreads;
         w[u] = i < end ? xs[i] : make_float4(mu, mu, mu, mu);
-        d[u] = i < end ? gs4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[u] = i < end ? gn_gate4(gs4[i], w[u], mu, off + 4 * (size_t)i, p) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < F4; ++u) {
@@ -453,7 +484,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_tma(const floa
             if (i < n4) {
                 float4 o;
                 o.x = (v[u].x - mean) / denom; o.y = (v[u].y - mean) / denom; o.z = (v[u].z - mean) / denom; o.w = (v[u].w - mean) / denom;
-                ys[i] = o;
+                ys[i] = gn_post4(o, off + 4 * (size_t)i, p);
             }
         }
     }
@@ -484,7 +515,7 @@ __global__ void __launch_bounds__(kSmallThreads) group_norm_bwd_small(const floa
         const int i = threadIdx.x + u * kSmallThreads;
         const bool ok = i < n4;
         w[u] = ok ? __ldg(xs + i) : make_float4(mu, mu, mu, mu);
-        d[u] = ok ? __ldg(gs4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[u] = ok ? gn_gate4(__ldg(gs4 + i), w[u], mu, off + 4 * (size_t)i, p) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float gs = 0.f, gw = 0.f;
 #pragma unroll
@@ -578,7 +609,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
             const int i = threadIdx.x + u * kFastThreads;
             const bool ok = beg + i < end;
             w[u] = ok ? reinterpret_cast<const float4*>(stage)[i] : make_float4(mu, mu, mu, mu);
-            d[u] = ok ? reinterpret_cast<const float4*>(stage + kHalfFloats)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            d[u] = ok ? gn_gate4(reinterpret_cast<const float4*>(stage + kHalfFloats)[i], w[u], mu, off + 4 * (size_t)(beg + i), p)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();                                   // shared memory is free again: prefetch the next slab
         const int next = sidx + ncl;
@@ -642,8 +674,9 @@ void launch_cluster(Kernel kernel, dim3 grid, cudaStream_t s, Args... args) {
 }  // namespace
 
 void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int images, int C, int HW, int group_size, int quirk,
-                      cudaStream_t s) {
-    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, quirk};
+                      cudaStream_t s, const GnFuse* fuse) {
+    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, quirk, 0, 0.f, 0ull};
+    if (fuse) { p.relu = fuse->relu; p.drop_rate = fuse->drop_rate; p.drop_seed = fuse->drop_seed; }
     if (images <= 0 || C <= 0 || HW <= 0) return;
     const size_t slab = (size_t)min(group_size, C) * HW;
     dim3 grid(p.G, images);
@@ -677,8 +710,9 @@ void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int i
 }
 
 void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* means, const float* stdevs, int images, int C, int HW,
-                      int group_size, cudaStream_t s) {
-    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, 1};
+                      int group_size, cudaStream_t s, const GnFuse* fuse) {
+    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, 1, 0, 0.f, 0ull};
+    if (fuse) { p.relu = fuse->relu; p.drop_rate = fuse->drop_rate; p.drop_seed = fuse->drop_seed; }
     if (images <= 0 || C <= 0 || HW <= 0) return;
     const size_t slab = (size_t)min(group_size, C) * HW;
     dim3 grid(p.G, images);

@@ -87,10 +87,14 @@ void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, i
 void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
                   NhwcCache* cache = nullptr);
 void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s);
+// Neighbours of a group norm fused into its kernels (the U-Net's group_norm -> multi_channel_relu -> _dropout chain,
+// cifar_unet.c:1046-1061): forward writes dropout(relu(norm(x))); backward gates the incoming gradient with the same masks
+// (ReLU: x > mean; dropout: element i of the tensor is dropped iff uniform_at(drop_seed, i) < drop_rate).
+struct GnFuse { int relu; float drop_rate; unsigned long long drop_seed; };
 void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int images, int C, int HW, int group_size, int quirk,
-                      cudaStream_t s);
+                      cudaStream_t s, const GnFuse* fuse = nullptr);
 void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* means, const float* stdevs, int images, int C, int HW,
-                      int group_size, cudaStream_t s);
+                      int group_size, cudaStream_t s, const GnFuse* fuse = nullptr);
 
 // counter-based generator (splitmix64 of seed + index), identical on host and device
 __host__ __device__ inline float uniform_at(unsigned long long seed, unsigned long long i, float lo, float hi) {

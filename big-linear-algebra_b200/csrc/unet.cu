@@ -476,6 +476,7 @@ struct Node {
     float *relu1 = nullptr, *conv1 = nullptr, *relu2 = nullptr, *drop = nullptr, *res = nullptr, *td = nullptr, *dtd = nullptr;
     float *mu1 = nullptr, *var1 = nullptr, *mu2 = nullptr, *var2 = nullptr;
     float *z = nullptr, *qkv = nullptr, *probs = nullptr, *att = nullptr;
+    GnFuse fuse2{1, 0.f, 0ull};   // what the second group norm of a ResNet block fused in this step's forward pass
     NhwcCache c1, c2, cr;     // padded NHWC copies of the conv inputs, shared by the forward conv and its weight gradient
     int id = 0;
 };
@@ -532,7 +533,6 @@ int add_res(bla_unet* n, const std::string& name, int in, int cout) {
     const size_t hw = (size_t)nd.side * nd.side, m = c.max_imgs;
     const int g1 = ceil_div(src.C, c.group_size), g2 = ceil_div(cout, c.group_size);
     nd.relu1 = dev_alloc(m * src.C * hw); nd.conv1 = dev_alloc(m * cout * hw); nd.relu2 = dev_alloc(m * cout * hw);
-    nd.drop = c.dropout > 0.f ? dev_alloc(m * cout * hw) : nullptr;
     nd.res = src.C != cout ? dev_alloc(m * cout * hw) : nullptr;
     nd.out = dev_alloc(m * cout * hw); nd.gout = dev_alloc(m * cout * hw);
     nd.td = dev_alloc(m * cout); nd.dtd = dev_alloc(m * cout);
@@ -586,20 +586,15 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
     switch (nd.kind) {
     case kInput: break;
     case kRes: {   // cifar_unet.c:1044-1072
-        const size_t ein = (size_t)imgs * nd.cin * hw, eout = (size_t)imgs * nd.C * hw;
-        k_group_norm_fwd(a->out, nd.relu1, nd.var1, nd.mu1, imgs, nd.cin, hw, c.group_size, quirk, s);
-        k_relu(nd.relu1, ein, s);
+        const size_t eout = (size_t)imgs * nd.C * hw;
+        const GnFuse relu_only{1, 0.f, 0ull};
+        k_group_norm_fwd(a->out, nd.relu1, nd.var1, nd.mu1, imgs, nd.cin, hw, c.group_size, quirk, s, &relu_only);   // + multi_channel_relu
         conv2d_forward(nd.relu1, P + nd.w1, nd.conv1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1);
         k_add_tile_columns(nd.conv1, imgs * nd.C, hw, nd.td, 1, s);                       // _add_time_embedding
-        k_group_norm_fwd(nd.conv1, nd.relu2, nd.var2, nd.mu2, imgs, nd.C, hw, c.group_size, quirk, s);
-        k_relu(nd.relu2, eout, s);
+        // group_norm -> multi_channel_relu -> _dropout in one pass (cifar_unet.c:1059-1061)
+        nd.fuse2 = GnFuse{1, train ? c.dropout : 0.f, c.seed + 7919ull * n->step + nd.id};
+        k_group_norm_fwd(nd.conv1, nd.relu2, nd.var2, nd.mu2, imgs, nd.C, hw, c.group_size, quirk, s, &nd.fuse2);
         const float* conv2_in = nd.relu2;
-        if (nd.drop && train) {
-            dropout_kernel<<<grid_for(eout, kThreads * 4), kThreads, 0, s>>>(nd.relu2, nd.drop, eout, c.seed + 7919ull * n->step + nd.id, c.dropout);
-            BLA_LAUNCH_CHECK();
-            count_launch();
-            conv2_in = nd.drop;
-        }
         conv2d_forward(conv2_in, P + nd.w2, nd.out, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2);
         if (nd.res) {
             conv2d_forward(a->out, P + nd.wr, nd.res, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, &nd.cr);
@@ -628,8 +623,8 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
         break;
     }
     case kGnRelu:
-        k_group_norm_fwd(a->out, nd.out, nd.var1, nd.mu1, imgs, nd.C, hw, c.group_size, quirk, s);
-        k_relu(nd.out, (size_t)imgs * nd.C * hw, s);
+        const GnFuse relu_only{1, 0.f, 0ull};
+        k_group_norm_fwd(a->out, nd.out, nd.var1, nd.mu1, imgs, nd.C, hw, c.group_size, quirk, s, &relu_only);
         break;
     }
 }
@@ -663,13 +658,13 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
     case kInput: break;
     case kRes: {   // cifar_unet.c:1181-1226
         const size_t eout = (size_t)imgs * nd.C * hw;
-        const float* conv2_in = nd.drop ? nd.drop : nd.relu2;
+        const float* conv2_in = nd.relu2;
         float *t1 = n->s1, *t2 = n->s2;
+        const GnFuse relu_only{1, 0.f, 0ull};
         conv2d_wgrad(conv2_in, nd.gout, G + nd.w2, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2);
         conv2d_dgrad(nd.gout, P + nd.w2, t1, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s);
-        // _dropout_mask + multi_channel_relu_ddx in one pass: a dropped or clipped activation is 0 in conv_2's input
-        k_relu_backward(t1, conv2_in, t1, eout, s);
-        k_group_norm_bwd(t1, t2, nd.conv1, nd.mu2, nd.var2, imgs, nd.C, hw, c.group_size, s);           // t2 = d conv_1 output
+        // _dropout_mask, multi_channel_relu_ddx and group_norm_ddx in one pass (the masks are regenerated, not stored)
+        k_group_norm_bwd(t1, t2, nd.conv1, nd.mu2, nd.var2, imgs, nd.C, hw, c.group_size, s, &nd.fuse2);   // t2 = d conv_1 output
         // time embedding projection (:1192-1200)
         plane_sum_kernel<<<grid_for((size_t)imgs * nd.C, kThreads / 32), kThreads, 0, s>>>(t2, imgs * nd.C, hw, nd.dtd);
         BLA_LAUNCH_CHECK();
@@ -679,9 +674,8 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         if (!want_din) break;
         const size_t ein = (size_t)imgs * nd.cin * hw;
         conv2d_dgrad(t2, P + nd.w1, t1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s);
-        k_relu_backward(t1, nd.relu1, t1, ein, s);
         Sink k = open_sink(n, nd.in0, n->s3, imgs);
-        k_group_norm_bwd(t1, k.dst, a->out, nd.mu1, nd.var1, imgs, nd.cin, hw, c.group_size, s);
+        k_group_norm_bwd(t1, k.dst, a->out, nd.mu1, nd.var1, imgs, nd.cin, hw, c.group_size, s, &relu_only);
         if (nd.res) {
             conv2d_dgrad(nd.gout, P + nd.wr, t1, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s);
             k_add(k.dst, t1, ein, s);
@@ -729,10 +723,9 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         break;
     }
     case kGnRelu: {
-        const size_t e = (size_t)imgs * nd.C * hw;
-        k_relu_backward(nd.gout, nd.out, n->s1, e, s);
+        const GnFuse relu_only{1, 0.f, 0ull};
         Sink k = open_sink(n, nd.in0, n->s3, imgs);
-        k_group_norm_bwd(n->s1, k.dst, a->out, nd.mu1, nd.var1, imgs, nd.C, hw, c.group_size, s);
+        k_group_norm_bwd(nd.gout, k.dst, a->out, nd.mu1, nd.var1, imgs, nd.C, hw, c.group_size, s, &relu_only);
         close_sink(k, s);
         break;
     }
