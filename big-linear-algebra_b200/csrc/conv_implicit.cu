@@ -246,6 +246,21 @@ void launch_permute(const float* w, float* out, int F, int C, int k2, int pad, i
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// every job of a table in one launch: grid (blocks per job, jobs)
+__global__ void __launch_bounds__(256) permute_weights_batch(const ConvPermuteJob* __restrict__ jobs) {
+    const ConvPermuteJob j = jobs[blockIdx.y];
+    const size_t total = j.mode == 0 ? (size_t)j.F * j.k2 * j.pad : (size_t)j.C * j.k2 * j.pad;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        if (j.mode == 0) {
+            const int c = (int)(e % j.pad), tap = (int)((e / j.pad) % j.k2), f = (int)(e / ((size_t)j.pad * j.k2));
+            j.dst[e] = c < j.C ? j.src[((size_t)f * j.C + c) * j.k2 + tap] : 0.f;
+        } else {
+            const int f = (int)(e % j.pad), tap = (int)((e / j.pad) % j.k2), c = (int)(e / ((size_t)j.pad * j.k2));
+            j.dst[e] = f < j.F ? j.src[((size_t)f * j.C + c) * j.k2 + (j.k2 - 1 - tap)] : 0.f;
+        }
+    }
+}
+
 ConvP base_params(int imgs, int C, int H, int W, int F, int k, int stride) {
     ConvP p{};
     p.imgs = imgs; p.C = C; p.H = H; p.W = W; p.F = F; p.k = k; p.stride = stride;
@@ -276,8 +291,21 @@ void launch(ConvP& p, int splits, cudaStream_t s) {
 
 }  // namespace
 
+size_t conv_taps_elems(int F, int C, int k) { return (size_t)F * k * k * round_up(C, 32); }
+size_t conv_flip_elems(int F, int C, int k) { return (size_t)C * k * k * round_up(F, 16); }
+ConvPermuteJob conv_taps_job(const float* w, float* dst, int F, int C, int k) { return {w, dst, F, C, k * k, round_up(C, 32), 0}; }
+ConvPermuteJob conv_flip_job(const float* w, float* dst, int F, int C, int k) { return {w, dst, F, C, k * k, round_up(F, 16), 1}; }
+bool conv_tensor_path_wanted() { return tensor_path_wanted(); }
+
+void conv_permute_weights_batch(const ConvPermuteJob* jobs_device, int njobs, cudaStream_t s) {
+    if (njobs <= 0) return;
+    permute_weights_batch<<<dim3(64, njobs), 256, 0, s>>>(jobs_device);
+    BLA_LAUNCH_CHECK();
+    count_launch();
+}
+
 void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
-                    NhwcCache* cache) {
+                    NhwcCache* cache, const float* w_taps) {
     ConvP p = base_params(imgs, C, H, W, F, k, stride);
     p.M = F; p.N = imgs * p.Ho * p.Wo; p.K = C * k * k;
     p.a = w; p.src = x; p.out = y; p.k_chunk = p.K;
@@ -287,10 +315,13 @@ void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, i
         // multiple of 32 inside the NHWC copy (16 would do for the forward pass; 32 lets the weight gradient share the copy), rows
         // of the filter matrix beyond F are zero-filled by TMA: a 3-channel input or a 3-filter output conv runs here too.
         const int Cp = round_up(C, 32);
-        float* wt = (float*)pool_alloc(kDevice, (size_t)F * k * k * Cp * sizeof(float));
-        launch_permute(w, wt, F, C, k * k, Cp, 0, (size_t)F * k * k * Cp, s);
-        const bool done = conv2d_tc(x, wt, y, imgs, C, Cp, H, W, 1, H, W, F, k, stride, p.pad_top, p.pad_left, cache, s);
-        pool_free(wt);
+        float* wt = nullptr;
+        if (!w_taps) {   // a caller that convolves with the same weights all step long permutes them once (conv_permute_weights_batch)
+            wt = (float*)pool_alloc(kDevice, (size_t)F * k * k * Cp * sizeof(float));
+            launch_permute(w, wt, F, C, k * k, Cp, 0, (size_t)F * k * k * Cp, s);
+        }
+        const bool done = conv2d_tc(x, w_taps ? w_taps : wt, y, imgs, C, Cp, H, W, 1, H, W, F, k, stride, p.pad_top, p.pad_left, cache, s);
+        if (wt) pool_free(wt);
         if (done) return;
     }
     launch<kFprop>(p, 1, s);
@@ -307,8 +338,9 @@ void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, i
         const int Cp = round_up(C, 32);
         const size_t total = (size_t)F * Cp * k * k;
         float* taps = (float*)pool_alloc(kDevice, total * sizeof(float));
-        const bool done = conv2d_wgrad_tc(x, dy, taps, imgs, C, Cp, H, W, F, k, stride, p.pad_top, p.pad_left, cache, s);
-        if (done) launch_permute(taps, dw, F, C, k * k, Cp, 2, (size_t)F * C * k * k, s);
+        bool final_written = false;
+        const bool done = conv2d_wgrad_tc(x, dy, taps, dw, &final_written, imgs, C, Cp, H, W, F, k, stride, p.pad_top, p.pad_left, cache, s);
+        if (done && !final_written) launch_permute(taps, dw, F, C, k * k, Cp, 2, (size_t)F * C * k * k, s);
         pool_free(taps);
         if (done) return;
     }
@@ -341,7 +373,8 @@ void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, i
     }
 }
 
-void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s) {
+void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
+                  const float* w_flip) {
     ConvP p = base_params(imgs, C, H, W, F, k, stride);
     p.M = C; p.N = imgs * H * W; p.K = F * k * k;
     if (p.M <= 0 || p.N <= 0) return;
@@ -350,10 +383,14 @@ void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, i
         // strided -- with the flipped, transposed filters: dx[i] = sum_ki' dyu[i - (k-1-pad) + ki'] . w[k-1-ki'].  (For stride 2
         // three quarters of the gathered values are zeros; still several times faster than the FP32 FMA kernel.)
         const int Fp = round_up(F, 16);
-        float* wf = (float*)pool_alloc(kDevice, (size_t)C * k * k * Fp * sizeof(float));
-        launch_permute(w, wf, F, C, k * k, Fp, 1, (size_t)C * k * k * Fp, s);
-        const bool done = conv2d_tc(dy, wf, dx, imgs, F, Fp, p.Ho, p.Wo, stride, H, W, C, k, 1, k - 1 - p.pad_top, k - 1 - p.pad_left, nullptr, s);
-        pool_free(wf);
+        float* wf = nullptr;
+        if (!w_flip) {
+            wf = (float*)pool_alloc(kDevice, (size_t)C * k * k * Fp * sizeof(float));
+            launch_permute(w, wf, F, C, k * k, Fp, 1, (size_t)C * k * k * Fp, s);
+        }
+        const bool done = conv2d_tc(dy, w_flip ? w_flip : wf, dx, imgs, F, Fp, p.Ho, p.Wo, stride, H, W, C, k, 1, k - 1 - p.pad_top,
+                                    k - 1 - p.pad_left, nullptr, s);
+        if (wf) pool_free(wf);
         if (done) return;
     }
     float* wt = (float*)pool_alloc(kDevice, (size_t)F * C * k * k * sizeof(float));

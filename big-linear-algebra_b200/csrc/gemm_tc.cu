@@ -71,6 +71,7 @@ struct TcParams {
     // conv == 2 is the weight gradient: A = dy [img][F][P] (3-D boxes, K-major, k = pixel), B[k = pixel][n = (ki, kj, c)] gathered from
     // the same padded NHWC input as MN-major atoms of 32 channels x 16 pixels; C = dW [F][(ki, kj, c)] through the plain GEMM epilogue.
     int conv, cv_P, cv_Wo, cv_stride, cv_pad_top, cv_pad_left, cv_k, cv_cblocks, cv_bw, cv_bh, cv_C;
+    int cv_final, cv_Creal;   // conv == 2 with split-K: the reduce kernel writes dW in the reference layout [F][C][k][k] (C = cv_Creal)
     int debug;               // BLA_TC_DEBUG: 1 = no split (1xTF32: hi.hi only), for bottleneck experiments
 };
 
@@ -768,7 +769,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 // every thread keeps 8 independent 128-bit loads in flight, the four group sums are combined through shared memory.
 __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p) {
     const size_t total = (size_t)p.m * p.n;
-    if ((total & 3) == 0 && (p.n & 3) == 0 && (p.c_vec || p.conv == 1)) {
+    if ((total & 3) == 0 && (p.n & 3) == 0 && (p.c_vec || p.conv == 1 || p.cv_final)) {
         __shared__ float4 part[4][64];
         const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
         const size_t total4 = total >> 2;
@@ -794,6 +795,13 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p)
                 if (p.conv == 1) {   // row i = filter, column j = (image, pixel) -> y [img][F][P]; P is a multiple of 4
                     const int img = j / p.cv_P, pix = j - img * p.cv_P;
                     *reinterpret_cast<float4*>(p.c + ((size_t)img * p.m + i) * p.cv_P + pix) = t;
+                } else if (p.cv_final) {   // weight gradient: column j = (tap, padded channel) -> dW [F][C][k*k], padding channels dropped
+                    const int tap = j / p.cv_C, c = j - tap * p.cv_C, k2 = p.cv_k * p.cv_k;
+                    float* dst = p.c + ((size_t)i * p.cv_Creal + c) * k2 + tap;
+                    if (c < p.cv_Creal) dst[0] = t.x;
+                    if (c + 1 < p.cv_Creal) dst[k2] = t.y;
+                    if (c + 2 < p.cv_Creal) dst[2 * k2] = t.z;
+                    if (c + 3 < p.cv_Creal) dst[3 * k2] = t.w;
                 } else {
                     float4 o;
                     o.x = epilogue_value(t.x, i, j, p); o.y = epilogue_value(t.y, i, j + 1, p);
@@ -1027,6 +1035,10 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     if (splits > 1) {
         ws = (float*)pool_alloc(kDevice, (size_t)splits * g.m * g.n * sizeof(float));
         p.partial = ws;
+        if (cmode == 2 && g.conv->dw_final && g.n % 4 == 0) {
+            p.cv_final = 1; p.cv_Creal = g.conv->C_real; p.c = g.conv->dw_final;
+            if (g.conv->wrote_final) *g.conv->wrote_final = true;
+        }
     }
 
     CUtensorMap mc;
@@ -1183,8 +1195,9 @@ bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C
 }
 
 // dw_taps [F][(ki, kj, c)] = sum over images and output pixels of dy[img][f][pixel] * x[img][c][pixel*stride + tap - pad]
-bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, int C, int Cp, int H, int W, int F, int k, int stride,
-                     int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s) {
+bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, float* dw_final, bool* wrote_final, int imgs, int C, int Cp, int H, int W,
+                     int F, int k, int stride, int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s) {
+    *wrote_final = false;
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const int P = Ho * Wo;
     // eligibility: 32-channel atoms, 16-pixel k-blocks inside one image that are whole box rows
@@ -1194,6 +1207,7 @@ bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, 
     const int Wp = (Wo - 1) * stride + k > W + pad_left ? (Wo - 1) * stride + k : W + pad_left;
     float* xp = padded_nhwc(x, imgs, C, Cp, H, W, Hp, Wp, pad_top, pad_left, 1, cache, s);
     ConvTc cv{2, xp, nullptr, imgs, Cp, Hp, Wp, F, k, stride, Ho, Wo, 0, 0};   // the padding is inside xp
+    cv.dw_final = dw_final; cv.C_real = C; cv.wrote_final = wrote_final;
     GemmArgs g{};
     g.m = F; g.n = k * k * Cp; g.k = imgs * P;
     g.a = dy; g.lda = P;

@@ -44,6 +44,8 @@ struct ConvTc {
     const float* in;      // padded NHWC input [imgs][H][W][C]
     float* out;           // [imgs][F][Ho][Wo]
     int imgs, C, H, W, F, k, stride, Ho, Wo, pad_top, pad_left;
+    // weight gradient only: when the GEMM is split along K, its reduction writes dW straight in the reference layout [F][C_real][k][k]
+    float* dw_final = nullptr; int C_real = 0; bool* wrote_final = nullptr;
 };
 
 struct GemmArgs {
@@ -77,16 +79,27 @@ void nhwc_cache_release(NhwcCache* c);
 // `in` [imgs][C][Hin][Win] is placed at spacing `dil` inside a logical H x W image (dil = 1, Hin = H for an ordinary conv).
 bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int Cp, int Hin, int Win, int dil, int H, int W, int F,
                int k, int stride, int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s);
-// weight gradient on the tensor path into dw_taps [F][(ki, kj, c)] over Cp channels (a multiple of 32); false if ineligible
-bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, int imgs, int C, int Cp, int H, int W, int F, int k, int stride,
-                     int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s);
+// weight gradient on the tensor path: into dw_final [F][C][k][k] when the split-K reduction could write it (*wrote_final), else into
+// dw_taps [F][(ki, kj, c)] over Cp channels (a multiple of 32) for the caller to un-permute; false if ineligible
+bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, float* dw_final, bool* wrote_final, int imgs, int C, int Cp, int H, int W,
+                     int F, int k, int stride, int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s);
 
 // ---- batched device-resident conv2d / group norm (conv_implicit.cu, api_norm.cu) ----------------
+// Filters re-laid for the tensor path (taps: forward, flip: dgrad).  A caller whose weights change once per step builds a device
+// table of jobs, runs conv_permute_weights_batch once after the update and hands the results to conv2d_forward / conv2d_dgrad.
+struct ConvPermuteJob { const float* src; float* dst; int F, C, k2, pad, mode; };
+size_t conv_taps_elems(int F, int C, int k);
+size_t conv_flip_elems(int F, int C, int k);
+ConvPermuteJob conv_taps_job(const float* w, float* dst, int F, int C, int k);
+ConvPermuteJob conv_flip_job(const float* w, float* dst, int F, int C, int k);
+void conv_permute_weights_batch(const ConvPermuteJob* jobs_device, int njobs, cudaStream_t s);
+bool conv_tensor_path_wanted();
 void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
-                    NhwcCache* cache = nullptr);
+                    NhwcCache* cache = nullptr, const float* w_taps = nullptr);
 void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
                   NhwcCache* cache = nullptr);
-void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s);
+void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
+                  const float* w_flip = nullptr);
 // Neighbours of a group norm fused into its kernels (the U-Net's group_norm -> multi_channel_relu -> _dropout chain,
 // cifar_unet.c:1046-1061): forward writes dropout(relu(norm(x))); backward gates the incoming gradient with the same masks
 // (ReLU: x > mean; dropout: element i of the tensor is dropped iff uniform_at(drop_seed, i) < drop_rate).

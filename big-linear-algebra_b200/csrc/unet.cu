@@ -477,6 +477,8 @@ struct Node {
     float *mu1 = nullptr, *var1 = nullptr, *mu2 = nullptr, *var2 = nullptr;
     float *z = nullptr, *qkv = nullptr, *probs = nullptr, *att = nullptr;
     GnFuse fuse2{1, 0.f, 0ull};   // what the second group norm of a ResNet block fused in this step's forward pass
+    float *t1 = nullptr, *t2 = nullptr, *tr = nullptr;   // tensor-path filter layouts of w1 / w2 / wr: taps (forward) ...
+    float *f1 = nullptr, *f2 = nullptr, *fr = nullptr;   // ... and flipped (dgrad); rebuilt once per step, nullptr = not used
     NhwcCache c1, c2, cr;     // padded NHWC copies of the conv inputs, shared by the forward conv and its weight gradient
     int id = 0;
 };
@@ -494,6 +496,9 @@ struct bla_unet {
     float *x = nullptr, *temb = nullptr, *noise = nullptr;   // staging for host-side batches
     float *s1 = nullptr, *s2 = nullptr, *s3 = nullptr;        // backward scratch, each max activation size
     float *sq = nullptr, *sdi = nullptr, *sdz = nullptr;      // attention scratch: dqkv, dI, dZ / dense
+    ConvPermuteJob* permute_jobs = nullptr;                   // device table: every conv's filters in the tensor path's two layouts
+    int permute_njobs = 0;
+    bool permuted = false;                                    // this step's forward pass ran the table (tensor path wanted)
     TimeProj* time_table = nullptr;                           // device table of the ResNet blocks' time projections
     int time_blocks = 0, time_cmax = 0;
     double* loss = nullptr;
@@ -589,15 +594,15 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
         const size_t eout = (size_t)imgs * nd.C * hw;
         const GnFuse relu_only{1, 0.f, 0ull};
         k_group_norm_fwd(a->out, nd.relu1, nd.var1, nd.mu1, imgs, nd.cin, hw, c.group_size, quirk, s, &relu_only);   // + multi_channel_relu
-        conv2d_forward(nd.relu1, P + nd.w1, nd.conv1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1);
+        conv2d_forward(nd.relu1, P + nd.w1, nd.conv1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1, n->permuted ? nd.t1 : nullptr);
         k_add_tile_columns(nd.conv1, imgs * nd.C, hw, nd.td, 1, s);                       // _add_time_embedding
         // group_norm -> multi_channel_relu -> _dropout in one pass (cifar_unet.c:1059-1061)
         nd.fuse2 = GnFuse{1, train ? c.dropout : 0.f, c.seed + 7919ull * n->step + nd.id};
         k_group_norm_fwd(nd.conv1, nd.relu2, nd.var2, nd.mu2, imgs, nd.C, hw, c.group_size, quirk, s, &nd.fuse2);
         const float* conv2_in = nd.relu2;
-        conv2d_forward(conv2_in, P + nd.w2, nd.out, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2);
+        conv2d_forward(conv2_in, P + nd.w2, nd.out, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2, n->permuted ? nd.t2 : nullptr);
         if (nd.res) {
-            conv2d_forward(a->out, P + nd.wr, nd.res, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, &nd.cr);
+            conv2d_forward(a->out, P + nd.wr, nd.res, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, &nd.cr, n->permuted ? nd.tr : nullptr);
             k_add(nd.out, nd.res, eout, s);
         } else {
             k_add(nd.out, a->out, eout, s);
@@ -608,7 +613,7 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
         attn_forward(a->out, P + nd.wqkv, P + nd.wo, P + nd.bo, nd.z, nd.qkv, nd.probs, nd.att, n->sdz, nd.out, imgs, nd.C, hw, s);
         break;
     case kConv:
-        conv2d_forward(a->out, P + nd.w1, nd.out, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s, &nd.c1);
+        conv2d_forward(a->out, P + nd.w1, nd.out, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s, &nd.c1, n->permuted ? nd.t1 : nullptr);
         break;
     case kUp:
         upsample2_kernel<<<grid_for((size_t)imgs * nd.C * a->side * a->side, kThreads), kThreads, 0, s>>>(a->out, nd.out, (size_t)imgs * nd.C,
@@ -662,7 +667,7 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         float *t1 = n->s1, *t2 = n->s2;
         const GnFuse relu_only{1, 0.f, 0ull};
         conv2d_wgrad(conv2_in, nd.gout, G + nd.w2, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2);
-        conv2d_dgrad(nd.gout, P + nd.w2, t1, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s);
+        conv2d_dgrad(nd.gout, P + nd.w2, t1, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, n->permuted ? nd.f2 : nullptr);
         // _dropout_mask, multi_channel_relu_ddx and group_norm_ddx in one pass (the masks are regenerated, not stored)
         k_group_norm_bwd(t1, t2, nd.conv1, nd.mu2, nd.var2, imgs, nd.C, hw, c.group_size, s, &nd.fuse2);   // t2 = d conv_1 output
         // time embedding projection (:1192-1200)
@@ -673,11 +678,11 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         if (nd.res) conv2d_wgrad(a->out, nd.gout, G + nd.wr, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, &nd.cr);
         if (!want_din) break;
         const size_t ein = (size_t)imgs * nd.cin * hw;
-        conv2d_dgrad(t2, P + nd.w1, t1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s);
+        conv2d_dgrad(t2, P + nd.w1, t1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, n->permuted ? nd.f1 : nullptr);
         Sink k = open_sink(n, nd.in0, n->s3, imgs);
         k_group_norm_bwd(t1, k.dst, a->out, nd.mu1, nd.var1, imgs, nd.cin, hw, c.group_size, s, &relu_only);
         if (nd.res) {
-            conv2d_dgrad(nd.gout, P + nd.wr, t1, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s);
+            conv2d_dgrad(nd.gout, P + nd.wr, t1, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, n->permuted ? nd.fr : nullptr);
             k_add(k.dst, t1, ein, s);
         } else {
             k_add(k.dst, nd.gout, ein, s);
@@ -701,7 +706,7 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         conv2d_wgrad(a->out, nd.gout, G + nd.w1, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s, &nd.c1);
         if (!want_din) break;
         Sink k = open_sink(n, nd.in0, n->s3, imgs);
-        conv2d_dgrad(nd.gout, P + nd.w1, k.dst, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s);
+        conv2d_dgrad(nd.gout, P + nd.w1, k.dst, imgs, nd.cin, a->side, a->side, nd.C, nd.k, nd.stride, s, n->permuted ? nd.f1 : nullptr);
         close_sink(k, s);
         break;
     }
@@ -748,6 +753,8 @@ void run_forward(bla_unet* n, const float* x, const float* temb, int imgs, bool 
     const float* t = stage_in(temb, n->temb, (size_t)imgs * c.time_dim, s);
     if (t != n->temb) BLA_CUDA(cudaMemcpyAsync(n->temb, t, (size_t)imgs * c.time_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
     for (Node& nd : n->nodes) { nd.c1.valid = nd.c2.valid = nd.cr.valid = false; }   // the activations are about to change
+    n->permuted = conv_tensor_path_wanted();
+    if (n->permuted) conv_permute_weights_batch(n->permute_jobs, n->permute_njobs, s);   // the weights changed with the last update
     time_dense_forward_kernel<<<dim3(ceil_div(n->time_cmax, 64), ceil_div(imgs, 64), n->time_blocks), kThreads, 0, s>>>(n->time_table, n->temb, imgs,
                                                                                                                     c.time_dim);
     BLA_LAUNCH_CHECK();
@@ -849,6 +856,31 @@ bla_unet* bla_unet_create(const bla_unet_config* cfg) {
     n->s1 = dev_alloc(m * max_act); n->s2 = dev_alloc(m * max_act); n->s3 = dev_alloc(m * max_act);
     n->sq = dev_alloc(m * max_tok); n->sdi = dev_alloc(m * max_ss); n->sdz = dev_alloc(m * max_act);
     {
+        std::vector<ConvPermuteJob> jobs;
+        auto add = [&](size_t woff, int F, int Cin, int k, float*& taps, float*& flip, bool need_flip) {
+            taps = dev_alloc(conv_taps_elems(F, Cin, k));
+            jobs.push_back(conv_taps_job(n->params + woff, taps, F, Cin, k));
+            if (need_flip) {
+                flip = dev_alloc(conv_flip_elems(F, Cin, k));
+                jobs.push_back(conv_flip_job(n->params + woff, flip, F, Cin, k));
+            }
+        };
+        for (Node& nd : n->nodes) {
+            const bool din = nd.in0 >= 0 && n->nodes[nd.in0].kind != kInput;   // the input image needs no gradient
+            if (nd.kind == kRes) {
+                add(nd.w1, nd.C, nd.cin, nd.k, nd.t1, nd.f1, din);
+                add(nd.w2, nd.C, nd.C, nd.k, nd.t2, nd.f2, true);
+                if (nd.res) add(nd.wr, nd.C, nd.cin, 1, nd.tr, nd.fr, din);
+            } else if (nd.kind == kConv) {
+                add(nd.w1, nd.C, nd.cin, nd.k, nd.t1, nd.f1, din);
+            }
+        }
+        n->permute_njobs = (int)jobs.size();
+        n->permute_jobs = (ConvPermuteJob*)pool_alloc(kDevice, jobs.size() * sizeof(ConvPermuteJob));
+        BLA_CUDA(cudaMemcpyAsync(n->permute_jobs, jobs.data(), jobs.size() * sizeof(ConvPermuteJob), cudaMemcpyHostToDevice, rt().stream));
+        BLA_CUDA(cudaStreamSynchronize(rt().stream));
+    }
+    {
         std::vector<TimeProj> table;
         for (const Node& nd : n->nodes)
             if (nd.kind == kRes) {
@@ -873,7 +905,7 @@ void bla_unet_destroy(bla_unet* n) {
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
     for (Node& nd : n->nodes) {
         float* bufs[] = {nd.kind == kInput ? nullptr : nd.out, nd.gout, nd.relu1, nd.conv1, nd.relu2, nd.drop, nd.res, nd.td, nd.dtd, nd.mu1, nd.var1,
-                         nd.mu2, nd.var2, nd.z, nd.qkv, nd.probs, nd.att};
+                         nd.mu2, nd.var2, nd.z, nd.qkv, nd.probs, nd.att, nd.t1, nd.t2, nd.tr, nd.f1, nd.f2, nd.fr};
         for (float* p : bufs) if (p) pool_free(p);
         nhwc_cache_release(&nd.c1); nhwc_cache_release(&nd.c2); nhwc_cache_release(&nd.cr);
     }
@@ -881,6 +913,7 @@ void bla_unet_destroy(bla_unet* n) {
     for (float* p : bufs) if (p) pool_free(p);
     pool_free(n->loss);
     pool_free(n->time_table);
+    pool_free(n->permute_jobs);
     delete n;
 }
 
