@@ -414,8 +414,9 @@ def main():
         extras = run_extras(b, torch, stream, pk)
     if not args.no_extras and world > 1:
         sharded = run_sharded_gemm(b, torch, dist, stream, rank, world, barrier)
+        unet_dp = run_unet_dp(b, torch, dist, stream, world, barrier)
         if rank == 0:
-            extras = {"gemm_sweep_row_sharded": sharded}
+            extras = {"gemm_sweep_row_sharded": sharded, "unet_data_parallel": unet_dp}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -489,6 +490,35 @@ def run_sharded_gemm(b, torch, dist, stream, rank, world, barrier):
             b.bla_free(p_)
     b.bla_set_gemm_path(b.GEMM_AUTO)
     return out
+
+
+def run_unet_dp(b, torch, dist, stream, world, barrier, imgs=64):
+    """BASELINE.json configs[4] on N GPUs, weak scaling: every rank steps its own 64 synthetic images, the 23.9 M-float gradient is
+    all-reduced over NVLink inside bla_unet_train_step (the communicator is active).  Aggregate images/s, max over ranks."""
+    uc = b.UnetConfig(32, (C.c_int * 4)(128, 256, 256, 256), 512, 3, 32, 16, 0.1, imgs, 7)
+    net = b.bla_unet_create(C.byref(uc))
+    b.bla_unet_init_params(net, 42)
+    n3 = imgs * 3 * 32 * 32
+    x = b.bla_malloc_device(n3 * 4); nz = b.bla_malloc_device(n3 * 4); te = b.bla_malloc_device(imgs * 512 * 4)
+    b.bla_fill_uniform(x, n3, 1, -1, 1); b.bla_fill_uniform(nz, n3, 2, -1, 1); b.bla_fill_uniform(te, imgs * 512, 3, -1, 1)
+    for _ in range(3):
+        b.bla_unet_train_step(net, x, te, nz, imgs, 1e-6, None)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    e0.record(stream)
+    for _ in range(iters):
+        b.bla_unet_train_step(net, x, te, nz, imgs, 1e-6, None)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    b.bla_unet_destroy(net)
+    for p_ in (x, nz, te):
+        b.bla_free(p_)
+    return {"workload": "model/cifar_unet.c train step, %d images per GPU, gradient all-reduce of 23.9 M floats per step" % imgs,
+            "images_per_gpu": imgs, "n_gpus": world, "ms_per_step": ms, "images_per_s": imgs * world / (ms * 1e-3), "scaling": "weak"}
 
 
 def run_extras(b, torch, stream, pk):

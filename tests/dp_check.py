@@ -78,6 +78,33 @@ def main():
     dist.all_gather(flags, torch.tensor([1.0 if gemm_ok else 0.0], device="cuda"))
     if rank == 0:
         print("SHARDED_GEMM_OK" if all(f.item() == 1.0 for f in flags) else "SHARDED_GEMM_FAIL", flush=True)
+    # U-Net (BASELINE.json configs[4]) data-parallel over images: every rank steps its shard, gradients are all-reduced inside
+    # bla_unet_train_step; the result must equal the float64 full-batch gradient (tests/unet_ref.py) on every rank
+    import unet_ref
+    import test_unet_gpu as T
+    b.bla_set_quirks(0)
+    cfg, imgs_total = T.SMALL, 2 * world
+    unet, tensors = T.make_net(b, cfg, imgs_total)
+    flat = unet_ref.synthetic_params(cfg, tensors, imgs_total, 5)
+    b.bla_unet_set_params(unet, ptr(flat))
+    x, temb, noise = T.inputs(cfg, imgs_total, 3)                       # identical on every rank
+    lo, hi = 2 * rank, 2 * rank + 2
+    loss = np.zeros(1)
+    b.bla_unet_train_step(unet, ptr(np.ascontiguousarray(x[lo:hi])), ptr(np.ascontiguousarray(temb[lo:hi])),
+                          ptr(np.ascontiguousarray(noise[lo:hi])), 2, 0.0, ptr(loss))
+    g = np.empty(flat.size, np.float32)
+    b.bla_unet_get_grads(unet, ptr(g))
+    _, want_loss, want_g = unet_ref.reference_step(cfg, tensors, flat, x, temb, noise, 0)
+    tolu = 1e-5 if path == b.GEMM_FP32 else 1e-4
+    worst = max(rel_err(g[o:o + c], want_g[o:o + c]) for _, o, c in tensors)
+    unet_ok = worst <= tolu and abs(loss[0] - want_loss) <= 1e-4 * abs(want_loss)
+    flags = [torch.zeros(1, device="cuda") for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([1.0 if unet_ok else 0.0], device="cuda"))
+    if rank == 0:
+        print("UNET_DP_OK" if all(f.item() == 1.0 for f in flags) else "UNET_DP_FAIL", "worst grad err %.2e" % worst, "loss", loss[0], want_loss,
+              flush=True)
+    b.bla_unet_destroy(unet)
+    b.bla_set_quirks(1)
     b.bla_mlp_destroy(net)
     b.bla_comm_destroy()
     dist.destroy_process_group()

@@ -29,3 +29,4 @@ def test_data_parallel_step_matches_oracle(path, batch):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert "DP_CHECK_OK" in p.stdout, (p.stdout[-3000:], p.stderr[-3000:])
     assert "SHARDED_GEMM_OK" in p.stdout, (p.stdout[-3000:], p.stderr[-3000:])
+    assert "UNET_DP_OK" in p.stdout, (p.stdout[-3000:], p.stderr[-3000:])
