@@ -198,6 +198,12 @@ __global__ void __launch_bounds__(kThreads) col_sum_stage1(const float* __restri
             const size_t n4 = n >> 2;
             float a0 = 0.f, a1 = 0.f;
             size_t i = threadIdx.x;
+            const float4* p4 = reinterpret_cast<const float4*>(ptr);
+            for (; i + 3 * kThreads < n4; i += 4 * kThreads) {   // four independent 128-bit loads in flight per thread
+                const float4 u = __ldg(p4 + i), w = __ldg(p4 + i + kThreads), y = __ldg(p4 + i + 2 * kThreads), z = __ldg(p4 + i + 3 * kThreads);
+                a0 += ((u.x + u.y) + (u.z + u.w)) + ((y.x + y.y) + (y.z + y.w));
+                a1 += ((w.x + w.y) + (w.z + w.w)) + ((z.x + z.y) + (z.z + z.w));
+            }
             for (; i + kThreads < n4; i += 2 * kThreads) {
                 const float4 u = reinterpret_cast<const float4*>(ptr)[i], w = reinterpret_cast<const float4*>(ptr)[i + kThreads];
                 a0 += (u.x + u.y) + (u.z + u.w);

@@ -561,13 +561,20 @@ def _host(b, d, shape):
 
 @pytest.mark.parametrize("imgs,Cin,H,W,F,k,s", [(3, 128, 32, 32, 128, 3, 1), (2, 128, 32, 32, 256, 3, 2), (4, 3, 32, 32, 128, 3, 1),
                                                 (5, 256, 8, 8, 256, 1, 1), (7, 256, 4, 4, 256, 3, 1), (2, 5, 9, 7, 6, 3, 2),
-                                                (1, 128, 32, 32, 3, 3, 1), (4, 256, 16, 16, 256, 3, 1), (9, 128, 16, 16, 128, 3, 2)])
+                                                (1, 128, 32, 32, 3, 3, 1), (4, 256, 16, 16, 256, 3, 1), (9, 128, 16, 16, 128, 3, 2),
+                                                # tensor-path corner cases: images under 32 pixels (register stores, split-K), channel
+                                                # padding (3 -> 32, 40 -> 64), 3 filters (TMA zero-fills the other 125 rows), 1x1
+                                                (64, 256, 4, 4, 256, 3, 1), (32, 512, 4, 4, 256, 1, 1), (4, 3, 32, 32, 128, 3, 1),
+                                                (4, 128, 32, 32, 3, 3, 1), (5, 40, 16, 16, 72, 3, 1), (64, 64, 4, 4, 128, 3, 2),
+                                                (16, 256, 8, 8, 256, 3, 2)])
 @pytest.mark.parametrize("path", ["fp32", "3xtf32"])
 def test_implicit_conv_batched_vs_oracle(bla, imgs, Cin, H, W, F, k, s, path):
     b = bla
     b.bla_set_gemm_path(b.GEMM_FP32 if path == "fp32" else b.GEMM_3XTF32)
     try:
-        _implicit_conv_check(b, imgs, Cin, H, W, F, k, s, FP32_TOL if path == "fp32" else 2e-5)
+        # 3xTF32: <= 1e-3 is the contract; 5e-5 is asserted so that a silent 1xTF32 regression (~5e-4) cannot pass (the tensor
+        # core's truncating FP32 accumulation makes the error grow with the contraction length: 2.5e-5 at K = 4608 unsplit)
+        _implicit_conv_check(b, imgs, Cin, H, W, F, k, s, FP32_TOL if path == "fp32" else 5e-5)
     finally:
         b.bla_set_gemm_path(b.GEMM_FP32)
 
