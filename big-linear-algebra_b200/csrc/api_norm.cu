@@ -544,6 +544,67 @@ __global__ void __launch_bounds__(kSmallThreads) group_norm_bwd_small(const floa
     }
 }
 
+// forward twin of group_norm_bwd_small: the slab of x in registers (read once, 8 B/elem), mean and centred second moment by two
+// shuffle + shared-memory reductions, ReLU / dropout fused on the way out
+template <int F4>
+__global__ void __launch_bounds__(kSmallThreads) group_norm_fwd_small(const float* __restrict__ x, float* __restrict__ y, float* vars, float* means,
+                                                                      GnParams p) {
+    __shared__ float red[2][kSmallThreads / 32];
+    const int g = blockIdx.x, img = blockIdx.y;
+    const int c0 = g * p.group_size;
+    const int nc = min(p.group_size, p.C - c0);
+    const int n4 = (nc * p.HW) >> 2;
+    const size_t off = ((size_t)img * p.C + c0) * p.HW;
+    const float4* xs = reinterpret_cast<const float4*>(x + off);
+    float4* ys = reinterpret_cast<float4*>(y + off);
+    float4 v[F4];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = threadIdx.x + u * kSmallThreads;
+        v[u] = i < n4 ? __ldg(xs + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    }
+    const float inv_n = 1.f / (float)(4 * n4);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSmallThreads / 32; ++k) t += red[0][k];
+    const float mean = t * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = threadIdx.x + u * kSmallThreads;
+        if (i < n4) {
+            const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = q;
+    __syncthreads();
+    t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSmallThreads / 32; ++k) t += red[1][k];
+    const float var = t * inv_n;
+    const float denom = p.quirk ? var : sqrtf(var + 1e-8f);
+    if (threadIdx.x == 0) {
+        means[(size_t)img * p.G + g] = mean;
+        vars[(size_t)img * p.G + g] = p.quirk ? var : denom;
+    }
+#pragma unroll
+    for (int u = 0; u < F4; ++u) {
+        const int i = threadIdx.x + u * kSmallThreads;
+        if (i < n4) {
+            float4 o;
+            o.x = (v[u].x - mean) / denom; o.y = (v[u].y - mean) / denom; o.z = (v[u].z - mean) / denom; o.w = (v[u].w - mean) / denom;
+            ys[i] = gn_post4(o, off + 4 * (size_t)i, p);
+        }
+    }
+}
+
 // ---- persistent backward: 2-CTA clusters + TMA bulk prefetch + DSMEM sums ---------------------------------------
 // A cluster owns one (image, group) slab at a time; each CTA handles half of it.  The NEXT slab's halves of x and dy
 // are fetched into shared memory by cp.async.bulk while the current ones -- already in registers -- are reduced
@@ -554,14 +615,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
                                                                       const float* __restrict__ stdevs, GnParams p, int images) {
     constexpr int F4 = 4;                                  // float4 per thread per tensor: 2 CTAs x 1024 x 4 x 4 = 32768 elements
     extern __shared__ __align__(128) float stage[];        // [x half | dy half], each up to 16384 floats
-    __shared__ float red[32];
-    __shared__ float slots[2];
+    __shared__ float red2[2][32];
+    __shared__ float slots2[2][2];
     __shared__ __align__(8) unsigned long long bar;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int slabs = p.G * images;
     const uint32_t bar_a = gn_smem_u32(&bar), st_a = gn_smem_u32(stage);
     constexpr int kHalfFloats = kFastThreads * F4 * 4;     // 16384
+    int par = 0;
     auto slab_info = [&](int sidx, size_t& off, int& beg, int& end) {
         const int g = sidx % p.G, img = sidx / p.G;
         const int c0 = g * p.group_size;
@@ -622,18 +684,22 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
             gs += (d[u].x + d[u].y) + (d[u].z + d[u].w);
             gw += (w[u].x * d[u].x + w[u].y * d[u].y) + (w[u].z * d[u].z + w[u].w * d[u].w);
         }
-        // CTA totals -> slots, exchanged through DSMEM (same summation order in both CTAs)
+        // CTA totals of both sums in ONE shuffle + shared-memory pass -> slots, exchanged through DSMEM (same summation order in
+        // both CTAs).  The slots alternate between two pairs: a CTA can be at most one cluster barrier ahead of its peer, so
+        // the pair written in iteration k+2 has been read by the peer in iteration k -- one cluster barrier per slab, not two.
         float tot[2];
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-            float v = which == 0 ? gs : gw;
-            v = block_total_1024(v, red);
-            if (threadIdx.x == 0) slots[which] = v;
+        gs = warp_sum(gs); gw = warp_sum(gw);
+        if ((threadIdx.x & 31) == 0) { red2[0][threadIdx.x >> 5] = gs; red2[1][threadIdx.x >> 5] = gw; }
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            float v = red2[threadIdx.x >> 5][threadIdx.x & 31];
+            v = warp_sum(v);
+            if ((threadIdx.x & 31) == 0) slots2[par][threadIdx.x >> 5] = v;
         }
         cluster.sync();
-        tot[0] = *cluster.map_shared_rank(&slots[0], 0) + *cluster.map_shared_rank(&slots[0], 1);
-        tot[1] = *cluster.map_shared_rank(&slots[1], 0) + *cluster.map_shared_rank(&slots[1], 1);
-        cluster.sync();                                    // both CTAs have read before anyone overwrites the slots
+        tot[0] = *cluster.map_shared_rank(&slots2[par][0], 0) + *cluster.map_shared_rank(&slots2[par][0], 1);
+        tot[1] = *cluster.map_shared_rank(&slots2[par][1], 0) + *cluster.map_shared_rank(&slots2[par][1], 1);
+        par ^= 1;
         const int g = sidx % p.G;
         const int nc = min(p.group_size, p.C - g * p.group_size);
         const float inv_n = 1.f / (float)(nc * p.HW);
@@ -682,7 +748,12 @@ void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int i
     dim3 grid(p.G, images);
     // every group slab starts 16-byte aligned and has a multiple of 4 elements?
     const bool vec_ok = al16(x) && al16(y) && (HW % 4 == 0) && (C % group_size == 0 || ((size_t)(C % group_size) * HW) % 4 == 0);
-    if (vec_ok && slab <= (size_t)kFastThreads * kFastF4 * 4 && (long long)p.G * images >= 2LL * rt().num_sms) {
+    if (vec_ok && slab <= (size_t)kSmallThreads * 8 * 4 && (long long)p.G * images >= 2LL * rt().num_sms) {
+        // many small slabs: one small register-resident CTA each (the persistent kernel's per-slab barrier chain costs more than
+        // these slabs' transfer time)
+        if (slab <= (size_t)kSmallThreads * 2 * 4) group_norm_fwd_small<2><<<grid, kSmallThreads, 0, s>>>(x, y, vars, means, p);
+        else group_norm_fwd_small<8><<<grid, kSmallThreads, 0, s>>>(x, y, vars, means, p);
+    } else if (vec_ok && slab <= (size_t)kFastThreads * kFastF4 * 4 && (long long)p.G * images >= 2LL * rt().num_sms) {
         // many slabs: persistent CTAs with a TMA prefetch of the next slab
         static bool attr = false;
         if (!attr) {
