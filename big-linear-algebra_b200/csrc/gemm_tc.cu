@@ -961,7 +961,8 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         p.cv_bh = 32 / p.cv_bw < cv.Ho ? 32 / p.cv_bw : cv.Ho;
     }
     const int gran = p.cluster == 2 ? 64 : 32;   // whole 32-column epilogue chunks / MN-major atoms (per CTA half)
-    int conv_splits = 0;   // > 0: chosen together with the tile width below (conv forward only)
+    int conv_splits = 0;   // > 0: chosen together with the tile width below (conv forward only: measured on B200, the same model
+                           // LOSES for the weight gradient (U-Net step 13.7 -> 13.9 ms) and for small plain GEMMs (1024^3: 70 -> 61 TFLOP/s))
     if (cmode == 1) {
         // Convolutions over small images have few output columns (64 images of 4 x 4 pixels: 1024) but a long contraction
         // (k*k*C up to 4608): pick tile width AND split-K together from a cycle model of one k-block -- the 3 x 2 MMAs of a
@@ -976,7 +977,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
             const double mma = 6.0 * 185.0 * bn / 256.0, fill = (kABytes + (double)(bn / p.cluster) * BK * 4) / 24.0;
             const double per_kb = (mma > fill ? mma : fill) + 40.0;
             for (int sp = 1; sp <= 32; ++sp) {
-                if (sp > 1 && (p.kblocks / sp < 8 || g.m % BM != 0)) break;
+                if (sp > 1 && (p.kblocks / sp < 8 || (cmode == 1 && g.m % BM != 0))) break;
                 const long long waves = (tiles_ * sp + slots - 1) / slots;
                 const int kb = ceil_div(p.kblocks, sp);
                 double cost = (double)waves * (kb * per_kb + 1500.0);                                  // + tile prologue / epilogue
@@ -1019,7 +1020,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     const int sms = rt().num_sms;
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     int splits = 1;
-    if (cmode == 1) {
+    if (conv_splits > 0) {
         splits = conv_splits;
     } else if (tiles * 2 <= sms && p.kblocks >= 32) {
         long long want = (sms / p.cluster) / (tiles / p.cluster);          // one wave: units * splits <= cluster slots
