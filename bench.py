@@ -622,7 +622,42 @@ def run_extras(b, torch, stream, pk):
         for p_ in (dxp, dwp, dyp, gxp, gwp):
             b.bla_free(p_)
     out["unet"] = run_unet(b, t, pk)
+    out["csv_codec"] = run_csv_codec(b)
     return out
+
+
+def run_csv_codec(b):
+    """the checkpoint text format (lib/csv.c).  One 256 x 784 float tensor per file is the MLP's largest; timed on
+    8 of them (1.6 M values, ~15 MB of text) from DEVICE memory through the pinned staging, beside the reference's own codec
+    (oracle/_ref, compiled reference) on the same values from host memory -- a reported CPU baseline."""
+    import tempfile
+    rows, cols = 2048, 784
+    n = rows * cols
+    d = b.bla_malloc_device(n * 4)
+    b.bla_fill_uniform(d, n, 11, -0.1, 0.1)
+    res = {"values": n}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "w.csv").encode()
+        t0 = time.perf_counter(); b.bla_csv_save(path, d, cols, rows); tw = time.perf_counter() - t0
+        size = os.path.getsize(path)
+        t0 = time.perf_counter(); b.bla_csv_load(path, d, n); tr = time.perf_counter() - t0
+        res.update({"file_mb": size / 1e6, "save_mb_per_s": size / tw / 1e6, "load_mb_per_s": size / tr / 1e6,
+                    "host_threads": os.cpu_count()})
+        ref_so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libref_f32.so")
+        if os.path.exists(ref_so):
+            ref = C.CDLL(ref_so)
+            ref.read_csv_contents.restype = C.c_void_p; ref.read_csv_contents.argtypes = [C.c_char_p]
+            ref.write_csv_contents.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+            h = np.empty(n // 8, np.float32)              # an eighth of the values: the reference codec runs at ~10-20 MB/s
+            b.bla_copy_d2h(h.ctypes.data_as(C.c_void_p), d, h.nbytes); b.bla_sync()
+            rp = os.path.join(tmp, "r.csv").encode()
+            t0 = time.perf_counter(); ref.write_csv_contents(rp, h.ctypes.data_as(C.c_void_p), cols, rows // 8); rw = time.perf_counter() - t0
+            rsize = os.path.getsize(rp)
+            t0 = time.perf_counter(); ref.read_csv_contents(rp); rr = time.perf_counter() - t0
+            res.update({"reference_save_mb_per_s": rsize / rw / 1e6, "reference_load_mb_per_s": rsize / rr / 1e6,
+                        "reference_note": "lib/csv.c compiled from the reference (oracle/_ref), single-threaded, %d values" % h.size})
+    b.bla_free(d)
+    return res
 
 
 def run_unet(b, t, pk, imgs=64):

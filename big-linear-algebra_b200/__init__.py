@@ -155,6 +155,13 @@ PROTOTYPES = {
     "bla_conv2d_dgrad": (None, [C.c_void_p] * 3 + [C.c_int] * 7),
     "bla_group_norm": (None, [C.c_void_p] * 4 + [C.c_int] * 4),
     "bla_group_norm_ddx": (None, [C.c_void_p] * 5 + [C.c_int] * 4),
+    # include/lib/csv.h + include/bla.h -- CSV checkpoint codec
+    "read_csv_contents": (C.POINTER(C.c_float), [C.c_char_p]),
+    "write_csv_contents": (None, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
+    "bla_csv_parse": (C.c_size_t, [C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(C.c_float))]),
+    "bla_csv_format": (C.c_size_t, [C.c_void_p, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]),
+    "bla_csv_save": (None, [C.c_char_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "bla_csv_load": (None, [C.c_char_p, C.c_void_p, C.c_size_t]),
     # include/bla.h -- fused self attention
     "bla_attention_forward": (None, [C.c_void_p] * 9 + [C.c_int] * 3),
     "bla_attention_backward": (None, [C.c_void_p] * 11 + [C.c_int] * 3),
@@ -170,6 +177,8 @@ PROTOTYPES = {
     "bla_unet_set_params": (None, [C.c_void_p, C.c_void_p]),
     "bla_unet_get_params": (None, [C.c_void_p, C.c_void_p]),
     "bla_unet_get_grads": (None, [C.c_void_p, C.c_void_p]),
+    "bla_unet_save_csv": (None, [C.c_void_p, C.c_char_p]),
+    "bla_unet_load_csv": (None, [C.c_void_p, C.c_char_p]),
     "bla_unet_forward": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "bla_unet_train_step": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     # include/bla.h -- MNIST MLP trainer
@@ -177,6 +186,8 @@ PROTOTYPES = {
     "bla_mlp_destroy": (None, [C.c_void_p]),
     "bla_mlp_set_params": (None, [C.c_void_p] * 7),
     "bla_mlp_get_params": (None, [C.c_void_p] * 7),
+    "bla_mlp_save_csv": (None, [C.c_void_p, C.c_char_p]),
+    "bla_mlp_load_csv": (None, [C.c_void_p, C.c_char_p]),
     "bla_mlp_init_params": (None, [C.c_void_p, C.c_ulonglong]),
     "bla_mlp_train_step": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "bla_mlp_train_step_u8": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),

@@ -1,0 +1,310 @@
+// csv_codec.cu -- lib/csv.h: the reference's checkpoint / data format, byte-compatible and parallel.
+//
+// The reference writes every parameter tensor as text, `fprintf(f, "%f,", v)` per value with a newline after each row
+// (lib/csv.c:56-67), and reads it back one fgetc at a time into atof (lib/csv.c:28-54): 1.9 MB for the MLP's first layer,
+// ~450 MB for the U-Net.  Here the file is read (or produced) as one buffer, split at value boundaries across the host
+// cores, and converted with exact integer arithmetic:
+//   format : a float is m * 2^e with a 24-bit m, so round_half_even(v * 10^6) is a 64-bit shift with a remainder test --
+//            the same digits glibc's correctly rounded printf("%f") prints, without its big-number path;
+//   parse  : std::from_chars<double> (correctly rounded, as strtod/atof) then the reference's implicit double -> float
+//            conversion; tokens that are not plain decimals (spaces, inf, nan, hex) go through strtod itself.
+// Same tokenisation as the reference, quirks included: a value ends at ',' (an empty field is 0), at '\n' only if the field
+// is not empty, '\r' is skipped, characters after the last terminator are dropped, *num_values is the number of commas.
+// Device-resident tensors are staged through pinned memory (bla_csv_save_device / bla_csv_load_device).
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/bla.h"
+#include "../../include/lib/csv.h"
+#include "runtime.h"
+
+namespace {
+
+int worker_count(size_t bytes) {
+    if (bytes < (1u << 20)) return 1;
+    unsigned hc = std::thread::hardware_concurrency();
+    int n = hc ? (int)hc : 4;
+    if (n > 32) n = 32;
+    const int by_size = (int)(bytes >> 19);   // at least 512 KB of text per thread
+    return std::max(1, std::min(n, by_size));
+}
+
+template <class Fn>
+void parallel_for(int n, Fn fn) {
+    if (n <= 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(n - 1);
+    for (int i = 1; i < n; ++i) th.emplace_back(fn, i);
+    fn(0);
+    for (auto& t : th) t.join();
+}
+
+// ---- "%f," ----------------------------------------------------------------------------------------------------------
+inline char* put_u64(char* p, uint64_t v) {
+    char tmp[20];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+// appends printf("%f,", (double)x) to p (at most 48 bytes for |x| < 2^63; larger magnitudes, inf and nan go through snprintf)
+inline char* format_value(char* p, float x) {
+    uint32_t bits;
+    memcpy(&bits, &x, 4);
+    const uint32_t E = (bits >> 23) & 0xFF;
+    uint64_t M = bits & 0x7FFFFFu;
+    if (E == 0xFF || E >= 150 + 39) {   // inf / nan / >= 2^62: glibc's general path
+        return p + snprintf(p, 64, "%f,", (double)x);
+    }
+    int e;
+    if (E == 0) e = -149; else { M |= 0x800000u; e = (int)E - 150; }
+    if (bits >> 31) *p++ = '-';
+    uint64_t N;   // round_half_even(|x| * 10^6)
+    if (e >= 0) {
+        N = 0;     // integer: handled below without the 10^6 factor
+        p = put_u64(p, M << e);
+        memcpy(p, ".000000,", 8);
+        return p + 8;
+    }
+    const int s = -e;
+    const uint64_t P = M * 1000000ull;   // < 2^44
+    if (s >= 45) {
+        N = 0;                            // P < 2^44 <= half of 2^s
+    } else {
+        N = P >> s;
+        const uint64_t rem = P & ((1ull << s) - 1), half = 1ull << (s - 1);
+        if (rem > half || (rem == half && (N & 1))) ++N;
+    }
+    p = put_u64(p, N / 1000000ull);
+    uint32_t frac = (uint32_t)(N % 1000000ull);
+    *p++ = '.';
+    for (int d = 5; d >= 0; --d) { p[d] = (char)('0' + frac % 10); frac /= 10; }
+    p += 6;
+    *p++ = ',';
+    return p;
+}
+
+void format_rows(const float* data, int cols, size_t row0, size_t row1, std::vector<char>& out) {
+    out.resize((row1 - row0) * ((size_t)cols * 50 + 1) + 64);
+    char* p = out.data();
+    for (size_t r = row0; r < row1; ++r) {
+        const float* v = data + r * cols;
+        for (int c = 0; c < cols; ++c) p = format_value(p, v[c]);
+        *p++ = '\n';
+    }
+    out.resize((size_t)(p - out.data()));
+}
+
+// ---- atof ------------------------------------------------------------------------------------------------------------
+inline float parse_token(const char* b, const char* e) {
+    // the reference: atof on the field (leading blanks skipped, trailing junk ignored, "" -> 0)
+    const char* q = b;
+    bool plain = true;
+    if (q < e && *q == '+') { ++q; plain = !(q < e && (*q == '+' || *q == '-')); }   // strtod("+-1") is 0, not -1
+    double v = 0.0;
+    if (plain) {
+        auto r = std::from_chars(q, e, v);
+        if (r.ec == std::errc() && r.ptr == e) return (float)v;
+    }
+    char tmp[1100];
+    size_t n = std::min((size_t)(e - b), sizeof(tmp) - 1);
+    memcpy(tmp, b, n);
+    tmp[n] = '\0';
+    return (float)atof(tmp);
+}
+
+struct Scan { size_t values = 0, commas = 0; };
+
+// Walks [b, e) with the reference's state machine.  `pending` = the field open at b is non-empty (chunk boundaries are placed
+// right after a terminator, so it is false there).  With out != nullptr the values are stored.
+Scan scan(const char* b, const char* e, float* out) {
+    Scan s;
+    const char* tok = b;        // start of the current field
+    bool has_cr = false;
+    for (const char* p = b; p < e; ++p) {
+        const char c = *p;
+        if (c == ',' || c == '\n') {
+            bool nonempty = p > tok;
+            if (has_cr) {       // rare: strip the '\r's into a scratch copy
+                char tmp[1100];
+                size_t n = 0;
+                for (const char* q = tok; q < p && n < sizeof(tmp) - 1; ++q) if (*q != '\r') tmp[n++] = *q;
+                nonempty = n > 0;
+                if (c == ',' || nonempty) { if (out) out[s.values] = parse_token(tmp, tmp + n); ++s.values; }
+            } else if (c == ',' || nonempty) {
+                if (out) out[s.values] = parse_token(tok, p);
+                ++s.values;
+            }
+            if (c == ',') ++s.commas;
+            tok = p + 1;
+            has_cr = false;
+        } else if (c == '\r') {
+            has_cr = true;
+        }
+    }
+    return s;
+}
+
+float* parse_buffer(const char* text, size_t len, int* num_values, size_t* count_out) {
+    const int T = worker_count(len);
+    std::vector<size_t> cut(T + 1, 0);
+    cut[T] = len;
+    for (int i = 1; i < T; ++i) {   // boundaries right after a terminator
+        size_t p = len / T * i;
+        while (p < len && text[p] != ',' && text[p] != '\n') ++p;
+        cut[i] = std::min(len, p + 1);
+    }
+    for (int i = 1; i <= T; ++i) cut[i] = std::max(cut[i], cut[i - 1]);
+    std::vector<Scan> counts(T);
+    parallel_for(T, [&](int i) { counts[i] = scan(text + cut[i], text + cut[i + 1], nullptr); });
+    size_t total = 0, commas = 0;
+    std::vector<size_t> first(T);
+    for (int i = 0; i < T; ++i) { first[i] = total; total += counts[i].values; commas += counts[i].commas; }
+    // the reference sizes its buffer by the comma count (lib/csv.c:29-35) and overflows it when rows lack the trailing comma
+    // (SURVEY D8); here the buffer always holds every value
+    float* out = (float*)malloc(std::max<size_t>(std::max(total, commas), 1) * sizeof(float));
+    if (!out) bla::die("bla: out of memory parsing a CSV of %zu bytes, exiting", len);
+    parallel_for(T, [&](int i) { scan(text + cut[i], text + cut[i + 1], out + first[i]); });
+    if (num_values) *num_values = (int)commas;
+    if (count_out) *count_out = total;
+    return out;
+}
+
+std::vector<char> slurp(FILE* f) {
+    std::vector<char> buf;
+    rewind(f);
+    if (fseek(f, 0, SEEK_END) == 0) {
+        long n = ftell(f);
+        rewind(f);
+        if (n > 0) {
+            buf.resize((size_t)n);
+            size_t got = fread(buf.data(), 1, buf.size(), f);
+            buf.resize(got);
+            return buf;
+        }
+    }
+    char tmp[1 << 16];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    return buf;
+}
+
+void write_text(const char* filepath, const float* data, int cols, size_t rows) {
+    FILE* f = fopen(filepath, "w");
+    if (!f) bla::die("bla: cannot open CSV file %s for writing, exiting", filepath);
+    const int T = std::max(1, std::min(worker_count(rows * (size_t)cols * 10), (int)std::max<size_t>(rows, 1)));
+    std::vector<std::vector<char>> parts(T);
+    parallel_for(T, [&](int i) { format_rows(data, cols, rows * i / T, rows * (i + 1) / T, parts[i]); });
+    for (auto& p : parts)
+        if (!p.empty() && fwrite(p.data(), 1, p.size(), f) != p.size()) bla::die("bla: short write to %s, exiting", filepath);
+    fflush(f);
+    fclose(f);
+}
+
+}  // namespace
+
+extern "C" {
+
+// lib/csv.c:18-25
+float* read_csv_contents(const char* filepath) {
+    FILE* f = fopen(filepath, "r");
+    if (!f) bla::die("bla: cannot open CSV file %s, exiting", filepath);
+    return read_csv_contents_file(f, nullptr);
+}
+
+// lib/csv.c:28-54.  Side-effect (as the reference): closes f.  The result is malloc'd: callers free() it or hand it to make_matrix.
+float* read_csv_contents_file(FILE* f, int* num_values) {
+    std::vector<char> buf = slurp(f);
+    fclose(f);
+    return parse_buffer(buf.data(), buf.size(), num_values, nullptr);
+}
+
+// lib/csv.c:56-67
+void write_csv_contents(const char* filepath, float* data, int cols, int rows) {
+    if (cols <= 0 || rows <= 0) { FILE* f = fopen(filepath, "w"); if (f) fclose(f); return; }
+    write_text(filepath, data, cols, (size_t)rows);
+}
+
+// lib/csv.c:70-89
+int count_num_lines(FILE* f) {
+    char buffer[65536];
+    int count = 0;
+    for (;;) {
+        size_t got = fread(buffer, 1, sizeof(buffer), f);
+        if (ferror(f)) return -1;
+        for (size_t i = 0; i < got; ++i) count += buffer[i] == '\n';
+        if (feof(f)) break;
+    }
+    return count;
+}
+
+// ---- additive (include/bla.h "CSV checkpoint codec") --------------------------------------------------------------
+size_t bla_csv_parse(const char* text, size_t len, float** values_out) {
+    size_t n = 0;
+    *values_out = parse_buffer(text, len, nullptr, &n);
+    return n;
+}
+
+size_t bla_csv_format(const float* data, int cols, size_t rows, char* out, size_t cap) {
+    const int T = std::max(1, std::min(worker_count(rows * (size_t)cols * 10), (int)std::max<size_t>(rows, 1)));
+    std::vector<std::vector<char>> parts(T);
+    parallel_for(T, [&](int i) { format_rows(data, cols, rows * i / T, rows * (i + 1) / T, parts[i]); });
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    if (out && total <= cap) {
+        char* q = out;
+        for (auto& p : parts) { memcpy(q, p.data(), p.size()); q += p.size(); }
+    }
+    return total;
+}
+
+// a [rows x cols] tensor in any memory (device, managed, host) -> the reference's CSV
+void bla_csv_save(const char* filepath, const float* data, int cols, size_t rows) {
+    using namespace bla;
+    const size_t n = rows * (size_t)cols;
+    if (classify(data) == kDevice) {
+        float* pin = (float*)pool_alloc(kPinned, n * sizeof(float));
+        BLA_CUDA(cudaMemcpyAsync(pin, data, n * sizeof(float), cudaMemcpyDeviceToHost, rt().stream));
+        BLA_CUDA(cudaStreamSynchronize(rt().stream));
+        rt().d2h_bytes += n * sizeof(float);
+        write_text(filepath, pin, cols, rows);
+        pool_free(pin);
+    } else {
+        if (rt_initialised()) BLA_CUDA(cudaStreamSynchronize(rt().stream));
+        write_text(filepath, data, cols, rows);
+    }
+}
+
+// the reference's CSV -> `count` floats at dst (device, managed or host); exits if the file holds fewer values
+void bla_csv_load(const char* filepath, float* dst, size_t count) {
+    using namespace bla;
+    FILE* f = fopen(filepath, "r");
+    if (!f) die("bla: cannot open CSV file %s, exiting", filepath);
+    std::vector<char> buf = slurp(f);
+    fclose(f);
+    size_t n = 0;
+    float* v = parse_buffer(buf.data(), buf.size(), nullptr, &n);
+    if (n < count) die("bla: CSV file %s holds %zu values, %zu expected, exiting", filepath, n, count);
+    if (classify(dst) == kDevice) {
+        float* pin = (float*)pool_alloc(kPinned, count * sizeof(float));
+        memcpy(pin, v, count * sizeof(float));
+        BLA_CUDA(cudaMemcpyAsync(dst, pin, count * sizeof(float), cudaMemcpyHostToDevice, rt().stream));
+        BLA_CUDA(cudaStreamSynchronize(rt().stream));
+        rt().h2d_bytes += count * sizeof(float);
+        pool_free(pin);
+    } else {
+        memcpy(dst, v, count * sizeof(float));
+    }
+    free(v);
+}
+
+}  // extern "C"

@@ -12,6 +12,7 @@
 // Activations are features x batch (batch = columns), exactly the reference's layout, so a
 // data-parallel shard is a column range and gradients are plain sums over ranks.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -549,6 +550,27 @@ void bla_mlp_get_params(bla_mlp* m, float* w1, float* b1, float* w2, float* b2, 
         if (b[l]) BLA_CUDA(cudaMemcpyAsync(b[l], Bv(m, l), (size_t)m->n[l + 1] * sizeof(float), cudaMemcpyDefault, rt().stream));
     }
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
+}
+
+// model/mnist_nn.c:97-144, :344-376 and :400-440: the six checkpoint files weights_{1,2,3}.csv ([n_l x n_{l-1}], one row per
+// output unit) and biases_{1,2,3}.csv (one value per row) under `dir` ("data/mnist_nn" in the reference), in lib/csv.c's format
+void bla_mlp_save_csv(bla_mlp* m, const char* dir) {
+    char path[1024];
+    for (int l = 0; l < 3; ++l) {
+        snprintf(path, sizeof(path), "%s/weights_%d.csv", dir, l + 1);
+        bla_csv_save(path, W(m, l), m->n[l], (size_t)m->n[l + 1]);
+        snprintf(path, sizeof(path), "%s/biases_%d.csv", dir, l + 1);
+        bla_csv_save(path, Bv(m, l), 1, (size_t)m->n[l + 1]);
+    }
+}
+void bla_mlp_load_csv(bla_mlp* m, const char* dir) {
+    char path[1024];
+    for (int l = 0; l < 3; ++l) {
+        snprintf(path, sizeof(path), "%s/weights_%d.csv", dir, l + 1);
+        bla_csv_load(path, W(m, l), (size_t)m->n[l + 1] * m->n[l]);
+        snprintf(path, sizeof(path), "%s/biases_%d.csv", dir, l + 1);
+        bla_csv_load(path, Bv(m, l), (size_t)m->n[l + 1]);
+    }
 }
 
 void bla_mlp_init_params(bla_mlp* m, unsigned long long seed) {

@@ -23,6 +23,9 @@
 #include <string>
 #include <vector>
 
+#include <sys/stat.h>
+#include <sys/types.h>
+
 #include "kernels.h"
 #include "runtime.h"
 
@@ -956,6 +959,79 @@ void bla_unet_get_params(bla_unet* n, float* flat) {
 void bla_unet_get_grads(bla_unet* n, float* flat) {
     BLA_CUDA(cudaMemcpyAsync(flat, n->grads, n->nparams * sizeof(float), cudaMemcpyDefault, rt().stream));
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
+}
+
+// save_parameters / load_parameters (cifar_unet.c:1484-1802): one CSV per tensor under `dir` ("data/cifar_unet" in the reference)
+// with the reference's directory and file names -- <level>/resnet_<i>/{conv_1,conv_2,conv_3 (residual),time_weight,time_bias}.csv,
+// <level>/self_attention_<i>/{query,key,value,weight,bias}.csv, <level>/conv_0.csv, output_conv.csv -- conv kernels as
+// [F*C rows][k*k columns] (_save_conv_kernels, :1493), matrices as [rows][cols] (_save_matrix, :1484).
+namespace {
+struct CsvFile { std::string path; size_t off; int cols; size_t rows; int col0, ld; };   // ld != cols: a column slice of a packed tensor
+
+void mkdirs(const std::string& path) {
+    for (size_t i = 1; i <= path.size(); ++i)
+        if (i == path.size() || path[i] == '/') mkdir(path.substr(0, i).c_str(), 0777);
+}
+
+std::vector<CsvFile> csv_files(const bla_unet* n, const std::string& dir) {
+    std::vector<CsvFile> files;
+    const int k2 = n->cfg.kernel_size * n->cfg.kernel_size;
+    auto ends = [](const std::string& s, const char* suf) { const size_t l = strlen(suf); return s.size() >= l && s.compare(s.size() - l, l, suf) == 0; };
+    for (const ParamT& t : n->tensors) {
+        const std::string base = dir + "/" + t.name;
+        const std::string parent = base.substr(0, base.rfind('/'));
+        if (ends(t.name, "/qkv")) {   // packed Q | K | V: three [C][key_dim] files
+            const size_t C = t.n / (3 * kD);
+            const char* names[3] = {"query", "key", "value"};
+            for (int q = 0; q < 3; ++q) files.push_back({parent + "/" + names[q] + ".csv", t.off, kD, C, q * kD, 3 * kD});
+        } else if (ends(t.name, "/residual_conv")) {
+            files.push_back({parent + "/conv_3.csv", t.off, 1, t.n, 0, 1});
+        } else if (ends(t.name, "/conv_1") || ends(t.name, "/conv_2") || t.name == "output_conv") {
+            files.push_back({base + ".csv", t.off, k2, t.n / k2, 0, k2});
+        } else if (ends(t.name, "/conv")) {
+            files.push_back({parent + "/conv_0.csv", t.off, k2, t.n / k2, 0, k2});
+        } else if (ends(t.name, "/time_weight")) {
+            const int C = (int)(t.n / n->cfg.time_dim);
+            files.push_back({base + ".csv", t.off, C, (size_t)n->cfg.time_dim, 0, C});
+        } else if (ends(t.name, "/weight")) {
+            const int C = (int)(t.n / kD);
+            files.push_back({base + ".csv", t.off, C, (size_t)kD, 0, C});
+        } else {   // time_bias, bias: one row
+            files.push_back({base + ".csv", t.off, (int)t.n, 1, 0, (int)t.n});
+        }
+    }
+    return files;
+}
+}  // namespace
+
+void bla_unet_save_csv(bla_unet* n, const char* dir) {
+    std::vector<float> host(n->nparams), tmp;
+    bla_unet_get_params(n, host.data());
+    for (const CsvFile& f : csv_files(n, dir)) {
+        mkdirs(f.path.substr(0, f.path.rfind('/')));
+        const float* src = host.data() + f.off;
+        if (f.ld != f.cols) {
+            tmp.resize(f.rows * f.cols);
+            for (size_t r = 0; r < f.rows; ++r) memcpy(&tmp[r * f.cols], src + r * f.ld + f.col0, f.cols * sizeof(float));
+            src = tmp.data();
+        }
+        bla_csv_save(f.path.c_str(), src, f.cols, f.rows);
+    }
+}
+
+void bla_unet_load_csv(bla_unet* n, const char* dir) {
+    std::vector<float> host(n->nparams, 0.f), tmp;
+    for (const CsvFile& f : csv_files(n, dir)) {
+        float* dst = host.data() + f.off;
+        if (f.ld != f.cols) {
+            tmp.resize(f.rows * f.cols);
+            bla_csv_load(f.path.c_str(), tmp.data(), tmp.size());
+            for (size_t r = 0; r < f.rows; ++r) memcpy(dst + r * f.ld + f.col0, &tmp[r * f.cols], f.cols * sizeof(float));
+        } else {
+            bla_csv_load(f.path.c_str(), dst, f.rows * f.cols);
+        }
+    }
+    bla_unet_set_params(n, host.data());
 }
 
 void bla_unet_forward(bla_unet* n, const float* x, const float* time_emb, int imgs, float* out) {

@@ -150,6 +150,9 @@ void bla_mlp_set_params(bla_mlp* net, const float* w1, const float* b1, const fl
 void bla_mlp_get_params(bla_mlp* net, float* w1, float* b1, float* w2, float* b2, float* w3, float* b3);
 /* He-uniform weights / zero biases as model/mnist_nn.c:97-144 (`init`), from the counter-based generator. */
 void bla_mlp_init_params(bla_mlp* net, unsigned long long seed);
+/* The reference's six checkpoint files weights_{1,2,3}.csv / biases_{1,2,3}.csv under `dir` (model/mnist_nn.c:30-35, :344-376). */
+void bla_mlp_save_csv(bla_mlp* net, const char* dir);
+void bla_mlp_load_csv(bla_mlp* net, const char* dir);
 /* One SGD step on x [inputs x batch] RAW pixel values (the 1/255.0F scaling of :218 is fused) and
  * one-hot y [classes x batch]; x/y may be device memory (asynchronous) or host memory (staged).
  * global_batch/col_offset describe the shard (global_batch == batch, col_offset == 0 on one GPU).
@@ -164,6 +167,17 @@ void bla_mlp_train_step_u8(bla_mlp* net, const unsigned char* x_u8, const float*
 void bla_mlp_forward(bla_mlp* net, const float* x, int batch, float* probs);
 /* {loss_sum, num_correct} accumulated on the device since the last call (then cleared). */
 void bla_mlp_read_stats(bla_mlp* net, double* stats_host);
+
+/* ---- CSV checkpoint codec (lib/csv.c; include/lib/csv.h has the reference's four functions) ---------------- */
+
+/* Parse a CSV text held in memory with the reference's tokenisation (lib/csv.c:28-54); *values_out is malloc'd. */
+size_t bla_csv_parse(const char* text, size_t len, float** values_out);
+/* Format rows x cols floats exactly as write_csv_contents would write them; returns the byte count (nothing is stored if
+ * it exceeds cap or out is NULL). */
+size_t bla_csv_format(const float* data, int cols, size_t rows, char* out, size_t cap);
+/* A [rows x cols] tensor in device, managed or host memory <-> the reference's file format, staged through pinned memory. */
+void bla_csv_save(const char* filepath, const float* data, int cols, size_t rows);
+void bla_csv_load(const char* filepath, float* dst, size_t count);
 
 /* ---- fused self attention: _forward_attention / _backward_attention (cifar_unet.c:999-1022, :1261-1335) ---- */
 
@@ -210,6 +224,10 @@ void bla_unet_init_params(bla_unet* net, unsigned long long seed);
 void bla_unet_set_params(bla_unet* net, const float* flat);   /* host or device */
 void bla_unet_get_params(bla_unet* net, float* flat);
 void bla_unet_get_grads(bla_unet* net, float* flat);
+/* save_parameters / load_parameters (cifar_unet.c:1484-1802): the reference's directory of CSV files (one per tensor,
+ * data/cifar_unet/<level>/resnet_<i>/conv_1.csv ...; Q, K, V unpacked into query / key / value.csv), lib/csv.c's format. */
+void bla_unet_save_csv(bla_unet* net, const char* dir);
+void bla_unet_load_csv(bla_unet* net, const char* dir);
 /* forward() on x [imgs][3][H][W] with one time embedding row per image, time_emb [imgs][time_dim] (the reference never
  * initialises its own); out [imgs][3][H][W].  Host or device pointers; dropout off. */
 void bla_unet_forward(bla_unet* net, const float* x, const float* time_emb, int imgs, float* out);

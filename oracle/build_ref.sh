@@ -91,6 +91,10 @@ if [ -f "$BLA_DIR/libbla.so" ]; then
   sed 's/^#define SGD_BATCH_SIZE 64/#define SGD_BATCH_SIZE 512/' "$REF/model/mnist_nn.c" > "$t/model/mnist_nn_b512.c"
   $CC $HOSTFLAGS -o "$OUT/bin/bla_mnist_nn_b512"  "$t/model/mnist_nn_b512.c" "$t/lib/csv.c" "$t/lib/mnist_csv2.c" $LINK
   $CC $HOSTFLAGS -o "$OUT/bin/bla_cifar_unet"     "$t/model/cifar_unet.c" "$t/lib/csv.c" "$t/lib/cifar10.c" "$t/lib/bmp.c" $LINK
+  # the same programs WITHOUT the reference's csv.c: read_csv_contents / write_csv_contents / read_csv_contents_file come from
+  # libbla.so's parallel codec (csrc/csv_codec.cu), also underneath the reference's own mnist_csv2.c loader
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_main_nocsv"          "$t/model/main.c" -I"$t" $LINK
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_mnist_nn_b512_nocsv" "$t/model/mnist_nn_b512.c" "$t/lib/mnist_csv2.c" $LINK
   # the reference's own U-Net build (double, as shipped) for comparison runs
   $CC $CFLAGS -o "$OUT/bin/ref_cifar_unet_f64" "$GEN/f64/model/cifar_unet.c" "$GEN/f64/lib/matrix.c" "$GEN/f64/lib/csv.c" \
       "$GEN/f64/lib/cifar10.c" "$GEN/f64/lib/bmp.c" "$GEN/f64/lib/conv.c" "$GEN/f64/lib/norm.c" "$GEN/f64/lib/util.c" -lm

@@ -1,0 +1,88 @@
+"""GPU tests of the checkpoint path: device-resident parameters <-> the reference's CSV files (lib/csv.c format,
+model/mnist_nn.c:30-35 and model/cifar_unet.c:1484-1802 file layouts), staged through pinned memory by csrc/csv_codec.cu."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import load_ref, ptr, ref_available
+from test_csv_cpu import py_format
+import test_unet_gpu as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bla():
+    import bla_b200 as b
+    assert b.bla_device_count() >= 1
+    return b
+
+
+def six_decimals(a):
+    return np.array([np.float32(float("%f" % float(v))) for v in a.ravel()], np.float32).reshape(a.shape)
+
+
+def test_mlp_checkpoint_round_trip_in_the_reference_format(bla, tmp_path):
+    b = bla
+    dims = (C.c_int * 4)(784, 256, 128, 10)
+    rng = np.random.default_rng(3)
+    shapes = ((256, 784), (256,), (128, 256), (128,), (10, 128), (10,))
+    p32 = [np.ascontiguousarray(rng.normal(0, 0.05, s), np.float32) for s in shapes]
+    net = b.bla_mlp_create(dims, 64)
+    b.bla_mlp_set_params(net, *[ptr(p) for p in p32])
+    d0 = b.bla_d2h_bytes()
+    b.bla_mlp_save_csv(net, str(tmp_path).encode())
+    assert b.bla_d2h_bytes() - d0 == sum(p.nbytes for p in p32)           # device -> pinned -> text
+    for l in range(3):
+        w, bias = p32[2 * l], p32[2 * l + 1]
+        assert (tmp_path / f"weights_{l + 1}.csv").read_bytes() == py_format(w)                    # one row per output unit
+        assert (tmp_path / f"biases_{l + 1}.csv").read_bytes() == py_format(bias.reshape(-1, 1))   # mnist_nn.c:127: cols = 1
+    if ref_available("f32"):                                                # the reference's own reader sees the same values
+        ref = load_ref("f32")
+        ref.read_csv_contents.restype = C.POINTER(C.c_float)
+        ref.read_csv_contents.argtypes = [C.c_char_p]
+        got = np.ctypeslib.as_array(ref.read_csv_contents(str(tmp_path / "weights_1.csv").encode()), shape=(256 * 784,))
+        assert np.array_equal(got, six_decimals(p32[0]).ravel())
+    net2 = b.bla_mlp_create(dims, 64)
+    b.bla_mlp_load_csv(net2, str(tmp_path).encode())
+    back = [np.empty_like(p) for p in p32]
+    b.bla_mlp_get_params(net2, *[ptr(g) for g in back])
+    for g, p in zip(back, p32):
+        assert np.array_equal(g, six_decimals(p))
+    b.bla_mlp_destroy(net); b.bla_mlp_destroy(net2)
+
+
+def test_unet_checkpoint_uses_the_reference_directory_layout(bla, tmp_path):
+    b = bla
+    cfg = T.SMALL
+    net, tensors = T.make_net(b, cfg, 1)
+    b.bla_unet_init_params(net, 9)
+    n = b.bla_unet_num_params(net)
+    flat = np.empty(n, np.float32)
+    b.bla_unet_get_params(net, ptr(flat))
+    b.bla_unet_save_csv(net, str(tmp_path).encode())
+    k2 = cfg["kernel_size"] ** 2
+    by_name = {name: (off, cnt) for name, off, cnt in tensors}
+    # cifar_unet.c:1493-1545: conv kernels as [F*C][k*k], residual conv = conv_3.csv, down / up convs = conv_0.csv
+    off, cnt = by_name["down_1/resnet_1/conv_1"]
+    assert (tmp_path / "down_1/resnet_1/conv_1.csv").read_bytes() == py_format(flat[off:off + cnt].reshape(-1, k2))
+    off, cnt = by_name["down_1/resnet_1/residual_conv"]
+    assert (tmp_path / "down_1/resnet_1/conv_3.csv").read_bytes() == py_format(flat[off:off + cnt].reshape(-1, 1))
+    off, cnt = by_name["down_1/conv"]
+    assert (tmp_path / "down_1/conv_0.csv").read_bytes() == py_format(flat[off:off + cnt].reshape(-1, k2))
+    off, cnt = by_name["mid/self_attention/qkv"]
+    qkv = flat[off:off + cnt].reshape(-1, 48)
+    for i, nm in enumerate(("query", "key", "value")):
+        assert (tmp_path / f"mid/self_attention/{nm}.csv").read_bytes() == py_format(np.ascontiguousarray(qkv[:, 16 * i:16 * i + 16]))
+    off, cnt = by_name["up_4/resnet_2/time_weight"]
+    assert (tmp_path / "up_4/resnet_2/time_weight.csv").read_bytes() == py_format(flat[off:off + cnt].reshape(cfg["time_dim"], -1))
+    assert os.path.exists(tmp_path / "output_conv.csv") and os.path.exists(tmp_path / "up_3/self_attention_2/bias.csv")
+    net2, _ = T.make_net(b, cfg, 1)
+    b.bla_unet_load_csv(net2, str(tmp_path).encode())
+    back = np.empty(n, np.float32)
+    b.bla_unet_get_params(net2, ptr(back))
+    for name, off, cnt in tensors:
+        assert np.array_equal(back[off:off + cnt], six_decimals(flat[off:off + cnt])), name
+    b.bla_unet_destroy(net); b.bla_unet_destroy(net2)

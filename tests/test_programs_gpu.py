@@ -149,6 +149,35 @@ def test_mnist_nn_loss_curve_and_checkpoint_match(tmp_path):
     assert "Epoch 0" in run("bla_mnist_nn", rb, "train", "1")
 
 
+@pytest.mark.skipif(not have("ref_mnist_nn_f64_b512", "bla_mnist_nn_b512_nocsv", "ref_main_f32", "bla_main_nocsv"),
+                    reason="oracle/_ref programs not built")
+def test_programs_linked_without_the_reference_csv_codec(tmp_path):
+    """the same unchanged model sources linked WITHOUT lib/csv.c -- checkpoints and the MNIST loader
+    (lib/mnist_csv2.c:14 -> read_csv_contents_file) go through libbla.so's codec: byte-identical `init` checkpoint, the
+    same loss curve, main.c's CSV round trip unchanged."""
+    def fill(d):
+        (d / "data" / "mnist_nn").mkdir(parents=True)
+        (d / "data" / "mnist").mkdir()
+        mnist_csv(d / "data" / "mnist" / "mnist_train.csv", 1024, 3)
+        mnist_csv(d / "data" / "mnist" / "mnist_test.csv", 100, 4)
+        (d / "data" / "a.csv").write_text("1,2.3,3,\n4,509,6,\n7,8,9.0,")
+        (d / "data" / "inputs.csv").write_text("3,\n7,\n9,")
+        (d / "data" / "weights.csv").write_text("1,2,3,\n4,5,6,")
+        (d / "data" / "biases.csv").write_text("0.1,\n0.2,")
+    ra, rb = twin_dirs(tmp_path, fill)
+    assert run("bla_main_nocsv", rb) == run("ref_main_f32", ra)
+    run("ref_mnist_nn_f64_b512", ra, "init"); run("bla_mnist_nn_b512_nocsv", rb, "init")
+    for f in os.listdir(os.path.join(ra, "data/mnist_nn")):
+        assert open(os.path.join(ra, "data/mnist_nn", f), "rb").read() == open(os.path.join(rb, "data/mnist_nn", f), "rb").read(), f
+    want = run("ref_mnist_nn_f64_b512", ra, "train", "2")
+    got = run("bla_mnist_nn_b512_nocsv", rb, "train", "2")
+    pat = r"Epoch (\d+):\s+Avg accuracy: ([0-9.]+)\s+Avg loss: ([0-9.]+)"
+    pw, pg = re.findall(pat, want), re.findall(pat, got)
+    assert len(pw) == 2 and len(pg) == 2
+    for (e1, a1, l1), (e2, a2, l2) in zip(pw, pg):
+        assert e1 == e2 and abs(float(a1) - float(a2)) <= 2e-3 and abs(float(l1) - float(l2)) <= 1e-4 * max(1.0, float(l1))
+
+
 @pytest.mark.skipif(not have("bla_cifar_unet"), reason="oracle/_ref programs not built")
 def test_cifar_unet_relinks_and_runs_to_completion(tmp_path):
     """BASELINE.json configs[4]: the WIP U-Net program (one image, forward + backward, 46 conv() calls, 36
