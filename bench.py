@@ -623,7 +623,55 @@ def run_extras(b, torch, stream, pk):
             b.bla_free(p_)
     out["unet"] = run_unet(b, t, pk)
     out["csv_codec"] = run_csv_codec(b)
+    out["data_pipeline"] = run_data_pipeline(b)
     return out
+
+
+def run_data_pipeline(b):
+    """one epoch of model/mnist_nn.c:181-342 over a device-resident synthetic MNIST (60,000 x 784), sampler +
+    gather + SGD steps, at the shipped batch size (64), at 512 and at one 60,000-sample batch; and the sampler alone beside the
+    reference's O(examples) scan per draw (lib/mnist_csv2.c:41-62, compiled reference, a reported CPU baseline)."""
+    n = 60000
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 256, (n, 784)).astype(np.float32)
+    y = rng.integers(0, 10, n).astype(np.float32)
+    store = b.bla_mnist_from_arrays(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), n, 784)
+    res = {"examples": n}
+    dims = (C.c_int * 4)(*DIMS)
+    for bs in (64, 512, 60000):
+        net = b.bla_mlp_create(dims, bs)
+        b.bla_mlp_init_params(net, 42)
+        stats = np.zeros(2)
+        b.bla_mlp_train_epoch(net, store, bs, LR, stats.ctypes.data_as(C.c_void_p))     # warm-up epoch
+        t0 = time.perf_counter()
+        b.bla_mlp_train_epoch(net, store, bs, LR, stats.ctypes.data_as(C.c_void_p))
+        dt = time.perf_counter() - t0
+        res[f"epoch_batch_{bs}"] = {"seconds": dt, "samples_per_s": n / dt, "steps": -(-n // bs)}
+        b.bla_mlp_destroy(net)
+    idx = np.empty(n, np.int32)
+    b.bla_mnist_reset(store)
+    t0 = time.perf_counter(); b.bla_mnist_sample_take(store, n, idx.ctypes.data_as(C.c_void_p)); dt = time.perf_counter() - t0
+    res["sampler_draws_per_s"] = n / dt
+    ref_so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libref_data.so")
+    if os.path.exists(ref_so):
+        class MnistCSV(C.Structure):
+            _fields_ = [("file", C.c_void_p), ("X", C.c_void_p), ("y", C.c_void_p), ("num_examples", C.c_int), ("num_sampled", C.c_int),
+                        ("sampled", C.c_void_p)]
+
+        class MnistExample(C.Structure):
+            _fields_ = [("X", C.c_void_p), ("y", C.c_float), ("num_examples", C.c_int)]
+        ref = C.CDLL(ref_so)
+        ref.get_random_data_take.restype = MnistExample
+        flags = np.zeros(n + 8, np.uint8)
+        csv = MnistCSV(None, x.ctypes.data, y.ctypes.data, n, 0, flags.ctypes.data)
+        draws = 6000                                        # the first tenth of an epoch: the scan gets longer as the epoch goes on
+        t0 = time.perf_counter()
+        for _ in range(draws):
+            ref.get_random_data_take(C.byref(csv))
+        res["reference_sampler_draws_per_s"] = draws / (time.perf_counter() - t0)
+        res["reference_note"] = "lib/mnist_csv2.c get_random_data_take compiled from the reference, first %d draws of an epoch" % draws
+    b.bla_mnist_destroy(store)
+    return res
 
 
 def run_csv_codec(b):

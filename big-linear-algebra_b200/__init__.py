@@ -155,6 +155,20 @@ PROTOTYPES = {
     "bla_conv2d_dgrad": (None, [C.c_void_p] * 3 + [C.c_int] * 7),
     "bla_group_norm": (None, [C.c_void_p] * 4 + [C.c_int] * 4),
     "bla_group_norm_ddx": (None, [C.c_void_p] * 5 + [C.c_int] * 4),
+    # include/bla.h -- data pipeline
+    "bla_mnist_from_csv": (C.c_void_p, [C.c_char_p]),
+    "bla_mnist_from_arrays": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "bla_mnist_destroy": (None, [C.c_void_p]),
+    "bla_mnist_num_examples": (C.c_int, [C.c_void_p]),
+    "bla_mnist_reset": (None, [C.c_void_p]),
+    "bla_mnist_sample_take": (None, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bla_mnist_gather": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "bla_mlp_train_epoch": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "bla_cifar_open": (C.c_void_p, [C.c_char_p]),
+    "bla_cifar_destroy": (None, [C.c_void_p]),
+    "bla_cifar_num_examples": (C.c_int, [C.c_void_p]),
+    "bla_cifar_sample": (None, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bla_cifar_gather": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     # include/lib/csv.h + include/bla.h -- CSV checkpoint codec
     "read_csv_contents": (C.POINTER(C.c_float), [C.c_char_p]),
     "write_csv_contents": (None, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),

@@ -2,7 +2,7 @@
  * bla.h -- additive C-ABI of libbla.so (big-linear-algebra on B200).
  *
  * The drop-in boundary is the reference's own link line: include/lib/{matrix,layer,conv,norm,util}.h
- * declare exactly the symbols that the reference's lib/*.o export and model/*.c import
+ * declare exactly the symbols that the reference's lib objects export and its model programs import
  * (SURVEY.md section 8b).  This header adds what a *device-resident* caller needs on top of that,
  * with plain pointers and sizes only (no C++ or torch types):
  *   - device / pinned allocation and explicit transfers, so that a `struct Matrix` can live in HBM
@@ -167,6 +167,38 @@ void bla_mlp_train_step_u8(bla_mlp* net, const unsigned char* x_u8, const float*
 void bla_mlp_forward(bla_mlp* net, const float* x, int batch, float* probs);
 /* {loss_sum, num_correct} accumulated on the device since the last call (then cleared). */
 void bla_mlp_read_stats(bla_mlp* net, double* stats_host);
+
+/* ---- data pipeline: lib/mnist_csv2.c and lib/cifar10.c with the dataset resident in HBM ------------------- */
+
+typedef struct bla_mnist bla_mnist;
+/* mnist_csv_init (lib/mnist_csv2.c:13-34): rows of `label, 784 pixels,`; parsed by the CSV codec, uploaded once. */
+bla_mnist* bla_mnist_from_csv(const char* filepath);
+/* The same store from memory: x [examples][features] (sample-major), labels [examples]; host or device pointers. */
+bla_mnist* bla_mnist_from_arrays(const float* x_sample_major, const float* labels, int examples, int features);
+void bla_mnist_destroy(bla_mnist* data);
+int bla_mnist_num_examples(const bla_mnist* data);
+/* memset(sampled, 0) + num_sampled = 0 (model/mnist_nn.c:189-190). */
+void bla_mnist_reset(bla_mnist* data);
+/* get_random_data_take (lib/mnist_csv2.c:41-62) `count` times: the same libc rand() stream and the same index rule (the
+ * element after the n-th unsampled one), found with a Fenwick tree in O(log examples) instead of the reference's scan. */
+void bla_mnist_sample_take(bla_mnist* data, int count, int* indices_out);
+/* The batch matrices of model/mnist_nn.c:199-217 gathered on the device: x_out [features x count] (raw pixel values),
+ * y_out [classes x count] one-hot (may be NULL).  Only the indices cross PCIe. */
+void bla_mnist_gather(bla_mnist* data, const int* indices_host, int count, float* x_out, float* y_out, int classes);
+/* One epoch of model/mnist_nn.c:181-342 (sampler, batch assembly, SGD steps) on the device; stats_host = {average accuracy,
+ * average loss} as the reference prints them (:340-341).  The net must have been created with max_batch >= batch_size. */
+void bla_mlp_train_epoch(bla_mlp* net, bla_mnist* data, int batch_size, float lr_mult, double* stats_host);
+
+typedef struct bla_cifar bla_cifar;
+/* One CIFAR-10 binary batch file (10,000 records of 1 label + 3072 pixel bytes, lib/cifar10.c:6-11) uploaded as bytes. */
+bla_cifar* bla_cifar_open(const char* filepath);
+void bla_cifar_destroy(bla_cifar* data);
+int bla_cifar_num_examples(const bla_cifar* data);
+/* fill_random_data's draw (lib/cifar10.c:14) `count` times, libc rand(). */
+void bla_cifar_sample(bla_cifar* data, int count, int* indices_out);
+/* load_example (model/cifar_unet.c:221-233) for a batch: rows flipped bottom-up as lib/cifar10.c:24-31 does, pixels mapped to
+ * [-1, 1]; x_out [count][3][32][32] on the device. */
+void bla_cifar_gather(bla_cifar* data, const int* indices_host, int count, float* x_out);
 
 /* ---- CSV checkpoint codec (lib/csv.c; include/lib/csv.h has the reference's four functions) ---------------- */
 

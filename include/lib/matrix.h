@@ -1,7 +1,7 @@
 /*
  * matrix.h -- drop-in replacement for the reference's lib/matrix.h (damians13/big-linear-algebra).
  *
- * Same type, same 19 function signatures, so model/*.c relink unchanged against libbla.so.
+ * Same type, same 19 function signatures, so the model programs relink unchanged against libbla.so.
  * Behind every function is a hand-written sm_100a CUDA kernel (big-linear-algebra_b200/csrc);
  * there is no CPU fallback: the first compute call prints an error and exit(1)s if no CUDA
  * device is usable.

@@ -54,6 +54,8 @@ build_lib() {          # $1 = variant, $2 = with layer.c? (0/1)
 }
 
 mk_tree f64 double 0;          build_lib f64 0
+# the reference's data readers / samplers (lib/mnist_csv2.c, lib/cifar10.c) for the data-pipeline parity tests
+$CC $CFLAGS -shared -Wl,-Bsymbolic -o "$OUT/libref_data.so" "$GEN/f64/lib/mnist_csv2.c" "$GEN/f64/lib/cifar10.c" "$GEN/f64/lib/csv.c" -lm
 mk_tree f64_convfix double 1;  build_lib f64_convfix 0
 mk_tree f32 float 0;           build_lib f32 1
 mk_tree f32_convfix float 1;   build_lib f32_convfix 1
