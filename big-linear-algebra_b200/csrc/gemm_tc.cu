@@ -580,9 +580,16 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             int split, m0, n0;
             decode(tile, split, m0, n0);
             const int n_end = min(p.n, n0 + p.bn);
+            const int row_base = m0 + 32 * q;
+            if (p.epi.gate && !p.partial && row_base + lane < p.m) {
+                // The relu' gate is one 128-byte row segment per lane and 32-column chunk.  Loaded on demand it exposes a DRAM
+                // round trip per chunk (the K = 128 dgrad of the MLP spent 21 us per tile here); asked for now, while this
+                // tile's MMAs are still running, it is an L2 hit by the time the accumulator is ready.
+                const float* grow = p.epi.gate + (size_t)(row_base + lane) * p.ldc;
+                for (int col0 = n0; col0 < n_end; col0 += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + col0));
+            }
             mbar_wait(bar_acc_full(acc), acc_phase);
             tcgen05_fence_after();
-            const int row_base = m0 + 32 * q;
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 const int col0 = n0 + 32 * ch;
@@ -997,8 +1004,9 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
             const long long units_ = (long long)m_units * ceil_div(g.n, bn);
             const long long waves = (units_ + slots - 1) / slots;
             // measured on B200 (square 4096): a 192-wide tile costs 1.33x more per column than a 256-wide one
-            // (the A tile and its split are amortised over fewer columns)
-            const double cost = (double)waves * bn * (1.0 + 0.33 * (BN - bn) / 64.0);
+            // (the A tile and its split are amortised over fewer columns).  Short contractions (K <= 256: the MLP's layer-2
+            // forward and dgrad) are bound by the epilogue, whose cost is proportional to the width: no penalty there.
+            const double cost = (double)waves * bn * (p.kblocks <= 16 ? 1.0 : 1.0 + 0.33 * (BN - bn) / 64.0);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
         }
         p.n_tiles = ceil_div(g.n, best_bn);
