@@ -316,8 +316,10 @@ void gemm(const GemmArgs& g, cudaStream_t s) {
     const int path = rt().gemm_path;
     if (path != BLA_GEMM_FP32) {
         const bool forced = path == BLA_GEMM_3XTF32;
-        // AUTO: tensor path only where a 128x256 tcgen05 tile is not mostly padding
-        const bool worthwhile = g.m >= 128 && g.n >= 128 && g.k >= 64;
+        // AUTO: tensor path where a 128x256 tcgen05 tile is not mostly padding, or where a skinny product is long enough that
+        // even a mostly empty tile beats the FP32 FMA kernel (the U-Net's attention projections: 16384 x 48 x 256 and their
+        // weight gradients 256 x 48 x 16384)
+        const bool worthwhile = g.k >= 64 && ((g.m >= 128 && g.n >= 128) || (g.m >= 16 && g.n >= 16 && (double)g.m * g.n * g.k >= 1.0e8));
         if ((forced || worthwhile) && gemm_3xtf32(g, s)) return;
     }
     gemm_simt(g, s);
