@@ -1001,14 +1001,30 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         double best_cost = -1.0;
         int best_bn = BN;
         for (int bn = BN; bn >= 192; bn -= gran) {
-            const long long units_ = (long long)m_units * ceil_div(g.n, bn);
-            const long long waves = (units_ + slots - 1) / slots;
+            const int nt = ceil_div(g.n, bn);
+            int w = (ceil_div(g.n, nt) + gran - 1) / gran * gran;             // the width this choice ends up with (shrunk below)
+            if (w > BN) w = BN;
+            const long long units_ = (long long)m_units * nt;
+            // split-K as decided further down: few tiles and a long contraction -> up to 64 slices, one wave
+            long long sp = 1;
+            if (units_ * p.cluster * 2 <= rt().num_sms && p.kblocks >= 32) {
+                sp = slots / units_;
+                if (sp > p.kblocks / 16) sp = p.kblocks / 16;
+                if (sp > 64) sp = 64;
+                if (sp < 1) sp = 1;
+            }
+            const long long waves = (units_ * sp + slots - 1) / slots;
+            const long long kb = (p.kblocks + sp - 1) / sp;
             // measured on B200 (square 4096): a 192-wide tile costs 1.33x more per column than a 256-wide one
             // (the A tile and its split are amortised over fewer columns).  Short contractions (K <= 256: the MLP's layer-2
             // forward and dgrad) are bound by the epilogue, whose cost is proportional to the width: no penalty there.
-            const double cost = (double)waves * bn * (p.kblocks <= 16 ? 1.0 : 1.0 + 0.33 * (BN - bn) / 64.0);
+            // With split-K the slices per tile and the 64-slice cap enter too: 256 x 784 x 60000 is faster as 4 x 256 columns
+            // x 18 slices (124 us) than as 5 x 192 x 14 (148 us), 128 x 256 x 60000 faster as 2 x 128 x 64 than as 1 x 256 x 64.
+            const double cost = (double)waves * (double)kb * w * (p.kblocks <= 16 ? 1.0 : 1.0 + 0.33 * (BN - w) / 64.0);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
         }
+        { static int force = -1; if (force < 0) { const char* e = getenv("BLA_TC_BN"); force = e ? atoi(e) : 0; }   // tuning probe
+          if (force >= gran && force <= BN && force % gran == 0) best_bn = force; }
         p.n_tiles = ceil_div(g.n, best_bn);
         p.bn = (ceil_div(g.n, p.n_tiles) + gran - 1) / gran * gran;
         if (p.bn > BN) p.bn = BN;
