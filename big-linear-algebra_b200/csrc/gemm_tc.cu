@@ -1043,6 +1043,30 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
 
     const int sms = rt().num_sms;
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
+    if (cmode == 0 && !g.no_tail_split && p.kblocks >= 32) {
+        // Wave quantisation: 235 units on 74 CTA pairs are 3.18 waves but cost 4.  When the last wave would be less than half
+        // full, the columns of the full waves and the tail are issued as two GEMMs: the tail then has few tiles and takes the
+        // split-K path, so its SMs are all busy for a fraction of a wave instead of 18 % of them for a whole one.
+        const long long slots = sms / p.cluster, units = tiles / p.cluster, m_units = p.m_tiles / p.cluster;
+        const long long full = units / slots, rem = units - full * slots;
+        const long long main_tiles = m_units > 0 ? full * slots / m_units : 0;
+        if (full >= 1 && rem > 0 && rem * 2 <= slots && main_tiles >= 1 && main_tiles < p.n_tiles) {
+            const int n_main = (int)(main_tiles * p.bn);
+            GemmArgs lo = g, hi = g;
+            lo.no_tail_split = hi.no_tail_split = true;
+            lo.n = n_main;
+            hi.n = g.n - n_main;
+            hi.b = g.tb ? g.b + (size_t)n_main * g.ldb : g.b + n_main;
+            hi.c = g.c + n_main;
+            if (g.epi.bias_cols) hi.epi.bias_cols = g.epi.bias_cols + n_main;
+            if (g.epi.gate) hi.epi.gate = g.epi.gate + n_main;
+            if (g.epi.pre_activation) hi.epi.pre_activation = g.epi.pre_activation + n_main;
+            if (gemm_3xtf32(lo, s)) {
+                if (!gemm_3xtf32(hi, s)) gemm_simt(hi, s);
+                return true;
+            }
+        }
+    }
     int splits = 1;
     if (conv_splits > 0) {
         splits = conv_splits;
