@@ -1043,7 +1043,9 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
 
     const int sms = rt().num_sms;
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
-    if (cmode == 0 && !g.no_tail_split && p.kblocks >= 32) {
+    static int tail_on = -1;
+    if (tail_on < 0) { const char* e = getenv("BLA_TC_TAIL"); tail_on = e ? atoi(e) : 1; }
+    if (cmode == 0 && tail_on && !g.no_tail_split && p.kblocks >= 32) {
         // Wave quantisation: 235 units on 74 CTA pairs are 3.18 waves but cost 4.  When the last wave would be less than half
         // full, the columns of the full waves and the tail are issued as two GEMMs: the tail then has few tiles and takes the
         // split-K path, so its SMs are all busy for a fraction of a wave instead of 18 % of them for a whole one.

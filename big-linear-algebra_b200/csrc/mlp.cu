@@ -121,11 +121,14 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
                                                            float* dz, float* probs, float scale, double* stats) {
     // block = 64 sample columns x 4 groups of hidden units: four times the loads in flight of a thread-per-column
     // layout (the kernel only streams A2: 4 B/elem), partial logits combined through shared memory
-    extern __shared__ float w_s[];   // [hidden][NC]  (transposed so one k gives NC consecutive floats)
+    // [hidden][NCP]: transposed so one k gives the NC weights as consecutive floats, rows padded to whole float4 so that they are
+    // read with 128-bit broadcast loads (10 scalar LDS per k made the kernel shared-memory-issue bound: 28 us for 31 MB)
+    constexpr int NCP = (NC + 3) / 4 * 4;
+    extern __shared__ __align__(16) float w_s[];
     __shared__ float part[3][64][NC + 1];
-    for (int e = threadIdx.x; e < hidden * NC; e += 256) {
-        const int k = e / NC, r = e % NC;
-        w_s[e] = W3[(size_t)r * hidden + k];
+    for (int e = threadIdx.x; e < hidden * NCP; e += 256) {
+        const int k = e / NCP, r = e % NCP;
+        w_s[e] = r < NC ? W3[(size_t)r * hidden + k] : 0.f;
     }
     __syncthreads();
     const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -144,14 +147,21 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
 #pragma unroll
                 for (int u = 0; u < 8; ++u) a[u] = A2[(size_t)(k + u) * B + c];     // 8 coalesced rows in flight
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int u = 0; u < 8; ++u) {
+                    float wr[NCP];
 #pragma unroll
-                    for (int r = 0; r < NC; ++r) acc[r] = fmaf(w_s[(k + u) * NC + r], a[u], acc[r]);
+                    for (int q = 0; q < NCP / 4; ++q) {
+                        const float4 t = reinterpret_cast<const float4*>(w_s + (k + u) * NCP)[q];
+                        wr[4 * q] = t.x; wr[4 * q + 1] = t.y; wr[4 * q + 2] = t.z; wr[4 * q + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int r = 0; r < NC; ++r) acc[r] = fmaf(wr[r], a[u], acc[r]);
+                }
             }
             for (; k < kend; ++k) {
                 const float a = A2[(size_t)k * B + c];
 #pragma unroll
-                for (int r = 0; r < NC; ++r) acc[r] = fmaf(w_s[k * NC + r], a, acc[r]);
+                for (int r = 0; r < NC; ++r) acc[r] = fmaf(w_s[k * NCP + r], a, acc[r]);
             }
         }
         if (grp > 0) {
@@ -209,7 +219,8 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict
                                                          int cols_per_cta, float* partial) {
     constexpr int STEP = 64;
     __shared__ float a_s[128][STEP + 1];          // [hidden unit (128 per pass)][column in step]
-    __shared__ __align__(16) float d_s[STEP][NC];  // [column in step][class]
+    constexpr int NCP = (NC + 3) / 4 * 4;          // rows padded to whole float4: 128-bit broadcast reads in the inner loop
+    __shared__ __align__(16) float d_s[STEP][NCP];  // [column in step][class]
     const int cbeg = blockIdx.x * cols_per_cta;
     const int cend = min(B, cbeg + cols_per_cta);
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -237,8 +248,14 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict
 #pragma unroll 8
             for (int cc = half * (STEP / 2); cc < (half + 1) * (STEP / 2); ++cc) {
                 const float a = a_s[threadIdx.x & 127][cc];
+                float dr[NCP];
 #pragma unroll
-                for (int r = 0; r < NC; ++r) acc[r] = fmaf(d_s[cc][r], a, acc[r]);
+                for (int q = 0; q < NCP / 4; ++q) {
+                    const float4 t = reinterpret_cast<const float4*>(&d_s[cc][0])[q];
+                    dr[4 * q] = t.x; dr[4 * q + 1] = t.y; dr[4 * q + 2] = t.z; dr[4 * q + 3] = t.w;
+                }
+#pragma unroll
+                for (int r = 0; r < NC; ++r) acc[r] = fmaf(dr[r], a, acc[r]);
             }
             __syncthreads();
         }
@@ -352,7 +369,7 @@ void head_forward(bla_mlp* m, const float* y, int B, float* dz, float* probs, cu
     int blocks = ceil_div(B, 64);
     const int cap = rt().num_sms * 8;
     if (blocks > cap) blocks = cap;
-    const size_t smem = (size_t)m->n[2] * m->n[3] * sizeof(float);
+    const size_t smem = (size_t)m->n[2] * ((m->n[3] + 3) / 4 * 4) * sizeof(float);
     BLA_DISPATCH_NC(m->n[3], head_forward_kernel<NC><<<blocks, 256, smem, s>>>(m->params + m->off_w[2], m->params + m->off_b[2], m->a2, y,
                                                                                   m->n[2], B, dz, probs, (float)(1.0 / (double)m->n[0]),
                                                                                   y ? m->stats : nullptr));
