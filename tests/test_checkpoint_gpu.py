@@ -86,3 +86,21 @@ def test_unet_checkpoint_uses_the_reference_directory_layout(bla, tmp_path):
     for name, off, cnt in tensors:
         assert np.array_equal(back[off:off + cnt], six_decimals(flat[off:off + cnt])), name
     b.bla_unet_destroy(net); b.bla_unet_destroy(net2)
+
+
+def test_codec_edge_cases(bla, tmp_path):
+    """empty file, a single value without a terminator (dropped, as lib/csv.c:44-52 does), rows without the trailing comma (the
+    reference overflows its buffer there, SURVEY D8: here every value is returned), zero-sized writes"""
+    b = bla
+    out = C.POINTER(C.c_float)()
+    assert b.bla_csv_parse(b"", 0, C.byref(out)) == 0
+    assert b.bla_csv_parse(b"42", 2, C.byref(out)) == 0
+    n = b.bla_csv_parse(b"1,2\n3,4\n", 8, C.byref(out))
+    assert n == 4 and [out[i] for i in range(4)] == [1.0, 2.0, 3.0, 4.0]
+    p = tmp_path / "empty.csv"
+    v = np.zeros((0, 4), np.float32)
+    b.write_csv_contents(str(p).encode(), ptr(np.zeros(1, np.float32)), 4, 0)
+    assert p.read_bytes() == b""
+    d = b.bla_malloc_device(16)
+    b.bla_csv_save(str(tmp_path / "one.csv").encode(), d, 1, 0)
+    b.bla_free(d)

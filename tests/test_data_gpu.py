@@ -138,3 +138,29 @@ def test_cifar_gather_matches_fill_random_data_and_load_example(bla, tmp_path):
             assert np.array_equal(got[k], want)
         os.close(fd)
     b.bla_free(xd); b.bla_cifar_destroy(store)
+
+
+def test_sampler_and_gather_edge_cases(bla):
+    """a batch of one, a ragged last batch (mnist_nn.c:194-195), more draws than examples (the sampler starts over, mnist_csv2.c:43-46)"""
+    b = bla
+    n = 37
+    rng = np.random.default_rng(2)
+    x = rng.integers(0, 256, (n, 784)).astype(np.float32); y = rng.integers(0, 10, n).astype(np.float32)
+    store = b.bla_mnist_from_arrays(ptr(x), ptr(y), n, 784)
+    idx = np.empty(100, np.int32)
+    libc.srand(7)
+    b.bla_mnist_sample_take(store, 100, ptr(idx))
+    assert idx.tolist() == reference_take_sequence(n, 100, 7)
+    xd = b.bla_malloc_device(784 * 4); yd = b.bla_malloc_device(10 * 4)
+    b.bla_mnist_gather(store, ptr(idx), 1, xd, yd, 10)
+    X = np.empty((784, 1), np.float32)
+    b.bla_copy_d2h(ptr(X), xd, X.nbytes); b.bla_sync()
+    assert np.array_equal(X[:, 0], x[idx[0]])
+    b.bla_mnist_gather(store, ptr(idx), 0, xd, yd, 10)          # nothing to do, nothing launched
+    dims = (C.c_int * 4)(784, 256, 128, 10)
+    net = b.bla_mlp_create(dims, 16)
+    b.bla_mlp_init_params(net, 1)
+    stats = np.zeros(2)
+    b.bla_mlp_train_epoch(net, store, 16, 0.02, ptr(stats))     # 37 = 16 + 16 + 5
+    assert 0.0 <= stats[0] <= 1.0 and np.isfinite(stats[1])
+    b.bla_free(xd); b.bla_free(yd); b.bla_mlp_destroy(net); b.bla_mnist_destroy(store)

@@ -200,3 +200,27 @@ def test_fused_attention_vs_autograd(bla, imgs, Cn, S):
     finally:
         for d in [xd, wq, wod, bod, dd] + bufs:
             b.bla_free(d)
+
+
+def test_unet_single_image_and_host_or_device_inputs(bla):
+    """the reference's own batch size (one image per forward) and device-resident inputs give the same result as host inputs"""
+    b = bla
+    b.bla_set_quirks(1)
+    net, tensors = make_net(b, SMALL, 2)
+    try:
+        b.bla_unet_init_params(net, 3)
+        x, temb, noise = inputs(SMALL, 2, 9)
+        both = np.empty_like(x)
+        b.bla_unet_forward(net, ptr(x), ptr(temb), 2, ptr(both))
+        one = np.empty_like(x[:1])
+        b.bla_unet_forward(net, ptr(np.ascontiguousarray(x[1:])), ptr(np.ascontiguousarray(temb[1:])), 1, ptr(one))
+        assert rel_err(one[0], both[1]) <= 1e-6                    # images are independent: no batch statistics anywhere
+        xd, td, od = _dev(b, x), _dev(b, temb), b.bla_malloc_device(x.nbytes)
+        h0 = b.bla_h2d_bytes()
+        b.bla_unet_forward(net, xd, td, 2, od)
+        assert b.bla_h2d_bytes() == h0                             # nothing staged
+        assert np.array_equal(_host(b, od, x.shape), both)
+        for d in (xd, td, od):
+            b.bla_free(d)
+    finally:
+        b.bla_unet_destroy(net)
