@@ -305,7 +305,7 @@ void conv_permute_weights_batch(const ConvPermuteJob* jobs_device, int njobs, cu
 }
 
 void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
-                    NhwcCache* cache, const float* w_taps) {
+                    NhwcCache* cache, const float* w_taps, const float* bias, const float* addend) {
     ConvP p = base_params(imgs, C, H, W, F, k, stride);
     p.M = F; p.N = imgs * p.Ho * p.Wo; p.K = C * k * k;
     p.a = w; p.src = x; p.out = y; p.k_chunk = p.K;
@@ -320,11 +320,14 @@ void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, i
             wt = (float*)pool_alloc(kDevice, (size_t)F * k * k * Cp * sizeof(float));
             launch_permute(w, wt, F, C, k * k, Cp, 0, (size_t)F * k * k * Cp, s);
         }
-        const bool done = conv2d_tc(x, w_taps ? w_taps : wt, y, imgs, C, Cp, H, W, 1, H, W, F, k, stride, p.pad_top, p.pad_left, cache, s);
+        const bool done = conv2d_tc(x, w_taps ? w_taps : wt, y, imgs, C, Cp, H, W, 1, H, W, F, k, stride, p.pad_top, p.pad_left, cache, s,
+                                    bias, addend);
         if (wt) pool_free(wt);
         if (done) return;
     }
     launch<kFprop>(p, 1, s);
+    if (bias) k_add_tile_columns(y, imgs * F, p.Ho * p.Wo, bias, 1, s);
+    if (addend) k_add(y, addend, (size_t)imgs * F * p.Ho * p.Wo, s);
 }
 
 void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,

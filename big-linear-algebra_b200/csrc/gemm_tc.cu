@@ -71,6 +71,8 @@ struct TcParams {
     // conv == 2 is the weight gradient: A = dy [img][F][P] (3-D boxes, K-major, k = pixel), B[k = pixel][n = (ki, kj, c)] gathered from
     // the same padded NHWC input as MN-major atoms of 32 channels x 16 pixels; C = dW [F][(ki, kj, c)] through the plain GEMM epilogue.
     int conv, cv_P, cv_Wo, cv_stride, cv_pad_top, cv_pad_left, cv_k, cv_cblocks, cv_bw, cv_bh, cv_C;
+    const float* cv_bias;     // conv == 1: + bias[img][filter]   (the U-Net's time-embedding add, cifar_unet.c:1024-1030)
+    const float* cv_add;      // conv == 1: + addend[img][filter][pixel]   (the residual connection, cifar_unet.c:1067-1071)
     int cv_final, cv_Creal;   // conv == 2 with split-K: the reduce kernel writes dW in the reference layout [F][C][k][k] (C = cv_Creal)
     int debug;               // BLA_TC_DEBUG: 1 = no split (1xTF32: hi.hi only), for bottleneck experiments
 };
@@ -638,6 +640,29 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                             }
                         }
                     }
+                    if (p.conv == 1 && !p.partial && (p.cv_bias || p.cv_add) && row_ok) {
+                        // fused neighbours of the U-Net's convolutions: y += bias[img][filter] and / or y += addend[img][filter][pixel]
+                        // (every group of 4 columns lies inside one image: P is a multiple of 4)
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {   // four 128-bit addend loads in flight at a time (register budget)
+                            float4 a4[4];
+                            if (p.cv_add) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const int col = col0 + 4 * (4 * half + q), img = col / p.cv_P, px = col - img * p.cv_P;
+                                    a4[q] = col < p.n ? __ldg(reinterpret_cast<const float4*>(p.cv_add + ((size_t)img * p.m + i) * p.cv_P + px))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int c4 = 4 * half + q, col = col0 + 4 * c4, img = col / p.cv_P;
+                                const float tb = (p.cv_bias && col < p.n) ? __ldg(p.cv_bias + (size_t)img * p.m + i) : 0.f;
+                                o[4 * c4] += tb; o[4 * c4 + 1] += tb; o[4 * c4 + 2] += tb; o[4 * c4 + 3] += tb;
+                                if (p.cv_add) { o[4 * c4] += a4[q].x; o[4 * c4 + 1] += a4[q].y; o[4 * c4 + 2] += a4[q].z; o[4 * c4 + 3] += a4[q].w; }
+                            }
+                        }
+                    }
                     if (p.conv == 1 && !p.partial && p.cv_P < 32) {
                         // small images (P = 4, 8 or 16 output pixels): the 32 columns of this chunk are 32/P whole images; lane =
                         // filter row writes P contiguous floats per image straight from its registers (64-byte runs for 4 x 4)
@@ -801,7 +826,10 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p)
                 const int i = (int)(e / p.n), j = (int)(e % p.n);
                 if (p.conv == 1) {   // row i = filter, column j = (image, pixel) -> y [img][F][P]; P is a multiple of 4
                     const int img = j / p.cv_P, pix = j - img * p.cv_P;
-                    *reinterpret_cast<float4*>(p.c + ((size_t)img * p.m + i) * p.cv_P + pix) = t;
+                    const size_t at = ((size_t)img * p.m + i) * p.cv_P + pix;
+                    if (p.cv_bias) { const float tb = p.cv_bias[(size_t)img * p.m + i]; t.x += tb; t.y += tb; t.z += tb; t.w += tb; }
+                    if (p.cv_add) { const float4 a = *reinterpret_cast<const float4*>(p.cv_add + at); t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w; }
+                    *reinterpret_cast<float4*>(p.c + at) = t;
                 } else if (p.cv_final) {   // weight gradient: column j = (tap, padded channel) -> dW [F][C][k*k], padding channels dropped
                     const int tap = j / p.cv_C, c = j - tap * p.cv_C, k2 = p.cv_k * p.cv_k;
                     float* dst = p.c + ((size_t)i * p.cv_Creal + c) * k2 + tap;
@@ -962,6 +990,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
       p.cluster = (en && p.m_tiles >= 2 && p.m_tiles % 2 == 0 && g.k >= 512) ? 2 : 1; }
     if (g.conv) {
         const ConvTc& cv = *g.conv;
+        p.cv_bias = cmode == 1 ? cv.bias : nullptr; p.cv_add = cmode == 1 ? cv.addend : nullptr;
         p.conv = cmode; p.cv_C = cv.C; p.cv_P = cv.Ho * cv.Wo; p.cv_Wo = cv.Wo; p.cv_stride = cv.stride; p.cv_pad_top = cv.pad_top; p.cv_pad_left = cv.pad_left;
         p.cv_k = cv.k; p.cv_cblocks = cv.C / BK;
         p.cv_bw = cv.Wo < 32 ? cv.Wo : 32;
@@ -1220,7 +1249,7 @@ float* padded_nhwc(const float* in, int imgs, int C, int Cp, int H, int W, int H
 // out [imgs][F][Ho][Wo] = conv(in, w): `in` is [imgs][C][Hin][Win], placed at spacing `dil` (zeros between: the transposed conv of a
 // strided dgrad) and offset (pad_top, pad_left) inside a logical image of H x W, then convolved with stride `stride`.
 bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int Cp, int Hin, int Win, int dil, int H, int W, int F,
-               int k, int stride, int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s) {
+               int k, int stride, int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s, const float* bias, const float* addend) {
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const int P = Ho * Wo;
     // eligibility: whole 16-channel k-blocks, 16-byte aligned rows, and 32-pixel atoms that tile the output exactly
@@ -1235,6 +1264,8 @@ bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C
     if (pad_top + (Hin - 1) * dil + 1 > Hp || pad_left + (Win - 1) * dil + 1 > Wp) return false;
     float* xp = padded_nhwc(in, imgs, C, Cp, Hin, Win, Hp, Wp, pad_top, pad_left, dil, cache, s);
     ConvTc cv{1, xp, out, imgs, Cp, Hp, Wp, F, k, stride, Ho, Wo, 0, 0};
+    cv.bias = bias; cv.addend = addend;
+    if (addend && ((uintptr_t)addend & 15)) { if (!cache) pool_free(xp); return false; }
     GemmArgs g{};
     g.m = F; g.n = imgs * P; g.k = k * k * Cp;
     g.a = w_taps; g.lda = g.k;

@@ -46,6 +46,8 @@ struct ConvTc {
     int imgs, C, H, W, F, k, stride, Ho, Wo, pad_top, pad_left;
     // weight gradient only: when the GEMM is split along K, its reduction writes dW straight in the reference layout [F][C_real][k][k]
     float* dw_final = nullptr; int C_real = 0; bool* wrote_final = nullptr;
+    // forward only: fused y += bias[img][filter] and y += addend[img][filter][pixel]
+    const float* bias = nullptr; const float* addend = nullptr;
 };
 
 struct GemmArgs {
@@ -79,7 +81,8 @@ void nhwc_cache_release(NhwcCache* c);
 // weights for the padding channels; Cp a multiple of 16); false if ineligible.
 // `in` [imgs][C][Hin][Win] is placed at spacing `dil` inside a logical H x W image (dil = 1, Hin = H for an ordinary conv).
 bool conv2d_tc(const float* in, const float* w_taps, float* out, int imgs, int C, int Cp, int Hin, int Win, int dil, int H, int W, int F,
-               int k, int stride, int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s);
+               int k, int stride, int pad_top, int pad_left, NhwcCache* cache, cudaStream_t s, const float* bias = nullptr,
+               const float* addend = nullptr);
 // weight gradient on the tensor path: into dw_final [F][C][k][k] when the split-K reduction could write it (*wrote_final), else into
 // dw_taps [F][(ki, kj, c)] over Cp channels (a multiple of 32) for the caller to un-permute; false if ineligible
 bool conv2d_wgrad_tc(const float* x, const float* dy, float* dw_taps, float* dw_final, bool* wrote_final, int imgs, int C, int Cp, int H, int W,
@@ -95,8 +98,10 @@ ConvPermuteJob conv_taps_job(const float* w, float* dst, int F, int C, int k);
 ConvPermuteJob conv_flip_job(const float* w, float* dst, int F, int C, int k);
 void conv_permute_weights_batch(const ConvPermuteJob* jobs_device, int njobs, cudaStream_t s);
 bool conv_tensor_path_wanted();
+// bias [imgs][F] and addend [imgs][F][Ho][Wo] (either may be NULL) are added to the result: in the tensor kernel's epilogue, by
+// two elementwise launches after the FP32 kernel.
 void conv2d_forward(const float* x, const float* w, float* y, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
-                    NhwcCache* cache = nullptr, const float* w_taps = nullptr);
+                    NhwcCache* cache = nullptr, const float* w_taps = nullptr, const float* bias = nullptr, const float* addend = nullptr);
 void conv2d_wgrad(const float* x, const float* dy, float* dw, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,
                   NhwcCache* cache = nullptr);
 void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, int H, int W, int F, int k, int stride, cudaStream_t s,

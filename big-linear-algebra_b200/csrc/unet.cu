@@ -597,19 +597,21 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
         const size_t eout = (size_t)imgs * nd.C * hw;
         const GnFuse relu_only{1, 0.f, 0ull};
         k_group_norm_fwd(a->out, nd.relu1, nd.var1, nd.mu1, imgs, nd.cin, hw, c.group_size, quirk, s, &relu_only);   // + multi_channel_relu
-        conv2d_forward(nd.relu1, P + nd.w1, nd.conv1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1, n->permuted ? nd.t1 : nullptr);
-        k_add_tile_columns(nd.conv1, imgs * nd.C, hw, nd.td, 1, s);                       // _add_time_embedding
+        // conv_1 + _add_time_embedding (the projection of all blocks was computed up front into nd.td)
+        conv2d_forward(nd.relu1, P + nd.w1, nd.conv1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1, n->permuted ? nd.t1 : nullptr,
+                       nd.td, nullptr);
         // group_norm -> multi_channel_relu -> _dropout in one pass (cifar_unet.c:1059-1061)
         nd.fuse2 = GnFuse{1, train ? c.dropout : 0.f, c.seed + 7919ull * n->step + nd.id};
         k_group_norm_fwd(nd.conv1, nd.relu2, nd.var2, nd.mu2, imgs, nd.C, hw, c.group_size, quirk, s, &nd.fuse2);
         const float* conv2_in = nd.relu2;
-        conv2d_forward(conv2_in, P + nd.w2, nd.out, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2, n->permuted ? nd.t2 : nullptr);
+        // conv_2 + the residual connection (through the 1x1 conv when the widths differ), added in conv_2's epilogue
+        const float* residual = a->out;
         if (nd.res) {
             conv2d_forward(a->out, P + nd.wr, nd.res, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, &nd.cr, n->permuted ? nd.tr : nullptr);
-            k_add(nd.out, nd.res, eout, s);
-        } else {
-            k_add(nd.out, a->out, eout, s);
+            residual = nd.res;
         }
+        conv2d_forward(conv2_in, P + nd.w2, nd.out, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2, n->permuted ? nd.t2 : nullptr, nullptr,
+                       residual);
         break;
     }
     case kAttn:
