@@ -622,6 +622,9 @@ def run_extras(b, torch, stream, pk):
         for p_ in (dxp, dwp, dyp, gxp, gwp):
             b.bla_free(p_)
     out["unet"] = run_unet(b, t, pk)
+    big = run_unet(b, t, pk, imgs=256)          # SURVEY 8(d) config 5 names batches of 1, 64 and 256 images
+    out["unet"]["batch_256"] = {k: big[k] for k in ("images", "train_ms_per_step", "train_images_per_s", "train_tflops", "forward_ms",
+                                                    "forward_images_per_s")}
     out["csv_codec"] = run_csv_codec(b)
     out["data_pipeline"] = run_data_pipeline(b)
     return out

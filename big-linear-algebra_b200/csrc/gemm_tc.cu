@@ -1201,7 +1201,7 @@ __global__ void __launch_bounds__(256) nchw_to_padded_nhwc_kernel(const float* _
     const int sp = threadIdx.x >> 3, sc = (threadIdx.x & 7) * 4;   // store role: pixel, channel quad
     float* dst = xp + ((size_t)img * npix + q0 + sp) * Cp + sc;
     const bool st_ok = q0 + sp < npix;
-    for (int c0 = 0; c0 < Cp; c0 += 32) {
+    for (int c0 = blockIdx.z * 32; c0 < Cp; c0 += gridDim.z * 32) {   // small images: the channel tiles are spread over blockIdx.z too
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const int c = c0 + ty + 8 * cc;
@@ -1240,7 +1240,11 @@ float* padded_nhwc(const float* in, int imgs, int C, int Cp, int H, int W, int H
     } else {
         xp = (float*)pool_alloc(kDevice, need * sizeof(float));
     }
-    nchw_to_padded_nhwc_kernel<<<dim3(ceil_div(Hp * Wp, 32), imgs), 256, 0, s>>>(in, xp, C, Cp, H, W, Hp, Wp, pad_top, pad_left, dil);
+    const int px_tiles = ceil_div(Hp * Wp, 32), c_tiles = ceil_div(Cp, 32);
+    int gz = ceil_div(4LL * rt().num_sms, (long long)px_tiles * imgs);     // enough blocks for ~4 per SM
+    if (gz > c_tiles) gz = c_tiles;
+    if (gz < 1) gz = 1;
+    nchw_to_padded_nhwc_kernel<<<dim3(px_tiles, imgs, gz), 256, 0, s>>>(in, xp, C, Cp, H, W, Hp, Wp, pad_top, pad_left, dil);
     BLA_LAUNCH_CHECK();
     count_launch();
     return xp;
