@@ -165,34 +165,68 @@ constexpr int kD = 16;          // SELF_ATTENTION_KEY_DIM (cifar_unet.c:36)
 constexpr int kAttnRows = 32;   // query rows per CTA
 
 // qkv [imgs*S][3*kD] (Q | K | V), probs [imgs][S][S] (softmax output, kept for the backward pass), att [imgs*S][kD].
-// grid (S / kAttnRows, imgs), 256 threads: K and V of the image sit in shared memory (rows padded to 17 floats), one warp
-// per query row: lane j scores keys j, j+32, ..., warp-shuffle max / sum, then lane (half, d) sums P.V over half the keys.
+// grid (S / kAttnRows, imgs), 256 threads: K and V of the image sit in shared memory with rows padded to kRow = 20 floats -- 16-byte
+// aligned, and 8 consecutive rows cover all 32 banks, so every 128-bit row read is conflict free.  One warp per query row: lane j
+// scores keys j, j+32, ... (4 LDS.128 + 16 FMA per key), warp-shuffle max / sum, then lane (key subset jj = lane / 4, dims 4*(lane % 4)..)
+// accumulates P.V over its keys (1 + 1 loads per 4 FMA) and the 8 subsets are folded with shuffles.
+constexpr int kRow = 20;
+
+__device__ __forceinline__ float dot16(const float (&q)[kD], const float* row) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float4 v = r4[t];
+        s = fmaf(q[4 * t], v.x, s); s = fmaf(q[4 * t + 1], v.y, s); s = fmaf(q[4 * t + 2], v.z, s); s = fmaf(q[4 * t + 3], v.w, s);
+    }
+    return s;
+}
+// out[d] (d = 4*(lane % 4) ..+3, complete in every lane after the folds) = sum_j w[j] * M[j][d]
+__device__ __forceinline__ float4 weighted_rows(const float* w, const float* M, int S, int lane) {
+    const int d4 = (lane & 3) * 4;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = lane >> 2; j < S; j += 8) {
+        const float pj = w[j];
+        const float4 v = *reinterpret_cast<const float4*>(M + j * kRow + d4);
+        o.x = fmaf(pj, v.x, o.x); o.y = fmaf(pj, v.y, o.y); o.z = fmaf(pj, v.z, o.z); o.w = fmaf(pj, v.w, o.w);
+    }
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+        o.x += __shfl_xor_sync(0xffffffffu, o.x, off); o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
+        o.z += __shfl_xor_sync(0xffffffffu, o.z, off); o.w += __shfl_xor_sync(0xffffffffu, o.w, off);
+    }
+    return o;
+}
+__device__ __forceinline__ void load_kv(const float* base, float* Ks, float* Vs, int S) {
+    for (int e = threadIdx.x; e < S * (kD / 4); e += kThreads) {       // one float4 of K and of V per thread and step
+        const int j = e / (kD / 4), q = e - j * (kD / 4);
+        *reinterpret_cast<float4*>(Ks + j * kRow + 4 * q) = *reinterpret_cast<const float4*>(base + (size_t)j * (3 * kD) + kD + 4 * q);
+        *reinterpret_cast<float4*>(Vs + j * kRow + 4 * q) = *reinterpret_cast<const float4*>(base + (size_t)j * (3 * kD) + 2 * kD + 4 * q);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) attention_forward_kernel(const float* __restrict__ qkv, float* __restrict__ probs,
                                                                      float* __restrict__ att, int S, float scale) {
-    extern __shared__ float sm[];
-    float* Ks = sm;                       // [S][17]
-    float* Vs = Ks + (size_t)S * 17;      // [S][17]
-    float* Ps = Vs + (size_t)S * 17;      // [8 warps][S]
+    extern __shared__ __align__(16) float sm[];
+    float* Ks = sm;                         // [S][kRow]
+    float* Vs = Ks + (size_t)S * kRow;      // [S][kRow]
+    float* Ps = Vs + (size_t)S * kRow;      // [8 warps][S]
     const int img = blockIdx.y, r0 = blockIdx.x * kAttnRows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* base = qkv + (size_t)img * S * (3 * kD);
-    for (int e = threadIdx.x; e < S * kD; e += kThreads) {
-        const int j = e / kD, d = e - j * kD;
-        Ks[j * 17 + d] = base[(size_t)j * (3 * kD) + kD + d];
-        Vs[j * 17 + d] = base[(size_t)j * (3 * kD) + 2 * kD + d];
-    }
+    load_kv(base, Ks, Vs, S);
     __syncthreads();
     float* P = Ps + warp * S;
     for (int r = r0 + warp; r < min(S, r0 + kAttnRows); r += kThreads / 32) {
         float q[kD];
 #pragma unroll
-        for (int d = 0; d < kD; ++d) q[d] = base[(size_t)r * (3 * kD) + d];
+        for (int t = 0; t < 4; ++t) {
+            const float4 v = *reinterpret_cast<const float4*>(base + (size_t)r * (3 * kD) + 4 * t);
+            q[4 * t] = v.x; q[4 * t + 1] = v.y; q[4 * t + 2] = v.z; q[4 * t + 3] = v.w;
+        }
         float mx = -INFINITY;
         for (int j = lane; j < S; j += 32) {
-            float s = 0.f;
-#pragma unroll
-            for (int d = 0; d < kD; ++d) s = fmaf(q[d], Ks[j * 17 + d], s);
-            s *= scale;
+            const float s = dot16(q, Ks + j * kRow) * scale;
             P[j] = s;
             mx = fmaxf(mx, s);
         }
@@ -204,11 +238,8 @@ __global__ void __launch_bounds__(kThreads) attention_forward_kernel(const float
         float* prow = probs + ((size_t)img * S + r) * S;
         for (int j = lane; j < S; j += 32) { const float pv = P[j] * inv; P[j] = pv; prow[j] = pv; }
         __syncwarp();
-        const int d = lane & 15, half = lane >> 4;
-        float o = 0.f;
-        for (int j = half; j < S; j += 2) o = fmaf(P[j], Vs[j * 17 + d], o);
-        o += __shfl_xor_sync(0xffffffffu, o, 16);
-        if (lane < kD) att[((size_t)img * S + r) * kD + d] = o;
+        const float4 o = weighted_rows(P, Vs, S, lane);
+        if (lane < 4) *reinterpret_cast<float4*>(att + ((size_t)img * S + r) * kD + 4 * lane) = o;
         __syncwarp();
     }
 }
@@ -220,30 +251,27 @@ __global__ void __launch_bounds__(kThreads) attention_forward_kernel(const float
 __global__ void __launch_bounds__(kThreads) attention_backward_rows_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
                                                                            const float* __restrict__ dA, float* __restrict__ dI,
                                                                            float* __restrict__ dqkv, int S, float scale) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     float* Ks = sm;
-    float* Vs = Ks + (size_t)S * 17;
-    float* Ps = Vs + (size_t)S * 17;
+    float* Vs = Ks + (size_t)S * kRow;
+    float* Ps = Vs + (size_t)S * kRow;
     const int img = blockIdx.y, r0 = blockIdx.x * kAttnRows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* base = qkv + (size_t)img * S * (3 * kD);
-    for (int e = threadIdx.x; e < S * kD; e += kThreads) {
-        const int j = e / kD, d = e - j * kD;
-        Ks[j * 17 + d] = base[(size_t)j * (3 * kD) + kD + d];
-        Vs[j * 17 + d] = base[(size_t)j * (3 * kD) + 2 * kD + d];
-    }
+    load_kv(base, Ks, Vs, S);
     __syncthreads();
     float* T = Ps + warp * S;
     for (int r = r0 + warp; r < min(S, r0 + kAttnRows); r += kThreads / 32) {
         float g[kD];
 #pragma unroll
-        for (int d = 0; d < kD; ++d) g[d] = dA[((size_t)img * S + r) * kD + d];
+        for (int t = 0; t < 4; ++t) {
+            const float4 v = *reinterpret_cast<const float4*>(dA + ((size_t)img * S + r) * kD + 4 * t);
+            g[4 * t] = v.x; g[4 * t + 1] = v.y; g[4 * t + 2] = v.z; g[4 * t + 3] = v.w;
+        }
         const float* prow = probs + ((size_t)img * S + r) * S;
         float dot = 0.f;
         for (int j = lane; j < S; j += 32) {
-            float ds = 0.f;
-#pragma unroll
-            for (int d = 0; d < kD; ++d) ds = fmaf(g[d], Vs[j * 17 + d], ds);
+            const float ds = dot16(g, Vs + j * kRow);
             T[j] = ds;
             dot = fmaf(prow[j], ds, dot);
         }
@@ -251,11 +279,8 @@ __global__ void __launch_bounds__(kThreads) attention_backward_rows_kernel(const
         float* irow = dI + ((size_t)img * S + r) * S;
         for (int j = lane; j < S; j += 32) { const float v = prow[j] * (T[j] - dot) * scale; T[j] = v; irow[j] = v; }
         __syncwarp();
-        const int d = lane & 15, half = lane >> 4;
-        float o = 0.f;
-        for (int j = half; j < S; j += 2) o = fmaf(T[j], Ks[j * 17 + d], o);
-        o += __shfl_xor_sync(0xffffffffu, o, 16);
-        if (lane < kD) dqkv[((size_t)img * S + r) * (3 * kD) + d] = o;
+        const float4 o = weighted_rows(T, Ks, S, lane);
+        if (lane < 4) *reinterpret_cast<float4*>(dqkv + ((size_t)img * S + r) * (3 * kD) + 4 * lane) = o;
         __syncwarp();
     }
 }
@@ -413,7 +438,7 @@ void attn_forward(const float* x, const float* wqkv, const float* wo, const floa
                   float* dense, float* out, int imgs, int Cn, int S, cudaStream_t s) {
     transpose_batched(x, z, imgs, Cn, S, s);                                                          // (C, H*W) -> (H*W, C)
     gemm_plain(false, false, imgs * S, 3 * kD, Cn, z, Cn, wqkv, 3 * kD, qkv, 3 * kD, nullptr, s);
-    const size_t smem = ((size_t)2 * S * 17 + (kThreads / 32) * S) * sizeof(float);
+    const size_t smem = ((size_t)2 * S * kRow + (kThreads / 32) * S) * sizeof(float);
     attention_forward_kernel<<<dim3(ceil_div(S, kAttnRows), imgs), kThreads, smem, s>>>(qkv, probs, att, S, 1.f / sqrtf((float)kD));
     BLA_LAUNCH_CHECK();
     count_launch();
@@ -439,7 +464,7 @@ void attn_backward(const float* dout, const float* wqkv, const float* wo, const 
         pool_free(planes);   // stream-ordered reuse
     }
     gemm_plain(false, true, M, kD, Cn, dY, Cn, wo, Cn, dA, kD, nullptr, s);                            // dP = dY' . W^T
-    const size_t smem = ((size_t)2 * S * 17 + (kThreads / 32) * S) * sizeof(float);
+    const size_t smem = ((size_t)2 * S * kRow + (kThreads / 32) * S) * sizeof(float);
     attention_backward_rows_kernel<<<dim3(ceil_div(S, kAttnRows), imgs), kThreads, smem, s>>>(qkv, probs, dA, dI, dqkv, S,
                                                                                               1.f / sqrtf((float)kD));
     BLA_LAUNCH_CHECK();
@@ -453,7 +478,7 @@ void attn_backward(const float* dout, const float* wqkv, const float* wo, const 
 }
 
 void attn_smem_opt_in(int S) {
-    const int smem = (int)(((size_t)2 * S * 17 + (kThreads / 32) * S) * sizeof(float));
+    const int smem = (int)(((size_t)2 * S * kRow + (kThreads / 32) * S) * sizeof(float));
     if (smem > 227 * 1024) die("bla: attention over %d tokens does not fit shared memory, exiting", S);
     static int granted = 0;
     if (smem <= granted) return;
