@@ -224,3 +224,27 @@ def test_unet_single_image_and_host_or_device_inputs(bla):
             b.bla_free(d)
     finally:
         b.bla_unet_destroy(net)
+
+
+def test_unet_sgd_reduces_the_loss_on_a_fixed_batch(bla):
+    """the trainer as a trainer: plain SGD on one fixed batch (intended group-norm semantics, dropout on) drives the MSE down"""
+    b = bla
+    b.bla_set_quirks(0)
+    b.bla_set_gemm_path(b.GEMM_AUTO)
+    net, tensors = make_net(b, SMALL, 4, dropout=0.1)
+    try:
+        flat = unet_ref.synthetic_params(SMALL, tensors, 4, 1)
+        b.bla_unet_set_params(net, ptr(flat))
+        x, temb, noise = inputs(SMALL, 4, 2)
+        losses = []
+        for _ in range(40):
+            loss = np.zeros(1)
+            # gradients are SUMS over pixels and images of 2 (out - noise) (cifar_unet.c:1353-1365, no 1/N): a small step
+            b.bla_unet_train_step(net, ptr(x), ptr(temb), ptr(noise), 4, 3e-6, ptr(loss))
+            losses.append(loss[0] / 4)
+        assert np.isfinite(losses).all()
+        assert losses[-1] < 0.85 * losses[0] and min(losses) > 0, losses
+    finally:
+        b.bla_unet_destroy(net)
+        b.bla_set_quirks(1)
+        b.bla_set_gemm_path(b.GEMM_FP32)
