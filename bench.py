@@ -651,6 +651,23 @@ def run_data_pipeline(b):
         dt = time.perf_counter() - t0
         res[f"epoch_batch_{bs}"] = {"seconds": dt, "samples_per_s": n / dt, "steps": -(-n // bs)}
         b.bla_mlp_destroy(net)
+    # BASELINE.json configs[1]: one full-batch iteration of the 10 one-vs-rest hinge classifiers over the
+    # resident store -- HBM-bound (the sample matrix is streamed twice: scores, then gradients)
+    hg = b.bla_hinge_create(784, 10, n)
+    w0 = (rng.random((10, 784)) / 10 - 0.05).astype(np.float32)
+    b.bla_hinge_set_weights(hg, w0.ctypes.data_as(C.c_void_p))
+    norms = np.zeros(10, np.float32)
+    for _ in range(3):
+        b.bla_hinge_iteration(hg, store, 0.001, None)
+    b.bla_sync()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        b.bla_hinge_iteration(hg, store, 0.001, None)
+    b.bla_hinge_iteration(hg, store, 0.001, norms.ctypes.data_as(C.c_void_p))
+    dt = (time.perf_counter() - t0) / 21
+    res["hinge_iteration"] = {"ms": dt * 1e3, "samples_per_s": n / dt, "gb_per_s_algorithmic": n * 784 * 4 / dt / 1e9,
+                              "note": "algorithmic bytes = one pass over the 60,000 x 784 float samples (SURVEY 8d); this implementation makes two"}
+    b.bla_hinge_destroy(hg)
     idx = np.empty(n, np.int32)
     b.bla_mnist_reset(store)
     t0 = time.perf_counter(); b.bla_mnist_sample_take(store, n, idx.ctypes.data_as(C.c_void_p)); dt = time.perf_counter() - t0

@@ -164,6 +164,11 @@ PROTOTYPES = {
     "bla_mnist_sample_take": (None, [C.c_void_p, C.c_int, C.c_void_p]),
     "bla_mnist_gather": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "bla_mlp_train_epoch": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "bla_hinge_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int]),
+    "bla_hinge_destroy": (None, [C.c_void_p]),
+    "bla_hinge_set_weights": (None, [C.c_void_p, C.c_void_p]),
+    "bla_hinge_get_weights": (None, [C.c_void_p, C.c_void_p]),
+    "bla_hinge_iteration": (None, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "bla_cifar_open": (C.c_void_p, [C.c_char_p]),
     "bla_cifar_destroy": (None, [C.c_void_p]),
     "bla_cifar_num_examples": (C.c_int, [C.c_void_p]),

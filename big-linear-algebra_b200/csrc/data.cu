@@ -166,6 +166,11 @@ void bla_mnist_destroy(bla_mnist* m) {
 }
 
 int bla_mnist_num_examples(const bla_mnist* m) { return m->n; }
+}  // extern "C"
+// for the other device-resident loops of the library (hinge.cu)
+const float* bla_mnist_x_device(const bla_mnist* m) { return m->x; }
+const float* bla_mnist_y_device(const bla_mnist* m) { return m->y; }
+extern "C" {
 
 // mnist_nn.c:189-190: a new round of SGD
 void bla_mnist_reset(bla_mnist* m) { fenwick_reset(m); }

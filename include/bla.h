@@ -189,6 +189,16 @@ void bla_mnist_gather(bla_mnist* data, const int* indices_host, int count, float
  * average loss} as the reference prints them (:340-341).  The net must have been created with max_batch >= batch_size. */
 void bla_mlp_train_epoch(bla_mlp* net, bla_mnist* data, int batch_size, float lr_mult, double* stats_host);
 
+/* model/mnist_hinge.c:100-172: ten one-vs-rest hinge classifiers, one full-batch iteration over a device-resident store
+ * (two skinny GEMMs over the sample matrix + two small kernels), the reference's partial gradient clear (:126) included. */
+typedef struct bla_hinge bla_hinge;
+bla_hinge* bla_hinge_create(int features, int classes, int max_examples);
+void bla_hinge_destroy(bla_hinge* h);
+void bla_hinge_set_weights(bla_hinge* h, const float* w);   /* [classes][features], host or device */
+void bla_hinge_get_weights(bla_hinge* h, float* w);
+/* norms_host (may be NULL) receives |gradient_p| / N per model (:156). */
+void bla_hinge_iteration(bla_hinge* h, bla_mnist* data, float learn_rate, float* norms_host);
+
 typedef struct bla_cifar bla_cifar;
 /* One CIFAR-10 binary batch file (10,000 records of 1 label + 3072 pixel bytes, lib/cifar10.c:6-11) uploaded as bytes. */
 bla_cifar* bla_cifar_open(const char* filepath);

@@ -164,3 +164,35 @@ def test_sampler_and_gather_edge_cases(bla):
     b.bla_mlp_train_epoch(net, store, 16, 0.02, ptr(stats))     # 37 = 16 + 16 + 5
     assert 0.0 <= stats[0] <= 1.0 and np.isfinite(stats[1])
     b.bla_free(xd); b.bla_free(yd); b.bla_mlp_destroy(net); b.bla_mnist_destroy(store)
+
+
+@pytest.mark.parametrize("path", ["fp32", "auto"])
+def test_device_hinge_iterations_match_the_oracle(bla, path):
+    """BASELINE.json configs[1]: three full-batch iterations of model/mnist_hinge.c:123-166 on the device against the float
+    restatement of the same loop (oracle orc_hinge_iter, pinned to the reference program in test_oracle_pinned.py), partial
+    gradient clear (:126) included."""
+    from helpers import load_oracle, rel_err
+    b = bla
+    b.bla_set_gemm_path(b.GEMM_FP32 if path == "fp32" else b.GEMM_AUTO)
+    o32 = load_oracle(np.float32)
+    n, F = 3000, 784
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 256, (n, F)).astype(np.float32)
+    labels = rng.integers(0, 10, n).astype(np.int32)
+    w0 = (rng.random((10, F)) / 10 - 0.05).astype(np.float32)           # mnist_hinge.c:20: rand()/(10*RAND_MAX) - 0.05
+    store = b.bla_mnist_from_arrays(ptr(x), ptr(labels.astype(np.float32)), n, F)
+    h = b.bla_hinge_create(F, 10, n)
+    b.bla_hinge_set_weights(h, ptr(w0))
+    w_ref, grad_ref = w0.copy(), np.zeros((10, F), np.float32)
+    try:
+        for it in range(3):
+            norms = np.zeros(10, np.float32); norms_ref = np.zeros(10, np.float32)
+            b.bla_hinge_iteration(h, store, 0.001, ptr(norms))
+            o32.orc_hinge_iter(n, F, ptr(w_ref), ptr(grad_ref), ptr(x), ptr(labels), C.c_float(0.001), ptr(norms_ref))
+            assert np.allclose(norms, norms_ref, rtol=1e-4, atol=1e-6), (it, norms, norms_ref)
+        got = np.empty_like(w0)
+        b.bla_hinge_get_weights(h, ptr(got))
+        assert rel_err(got, w_ref) <= 1e-4, rel_err(got, w_ref)
+    finally:
+        b.bla_hinge_destroy(h); b.bla_mnist_destroy(store)
+        b.bla_set_gemm_path(b.GEMM_FP32)
