@@ -856,30 +856,6 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p)
     }
 }
 
-// Weight gradient of a conv (conv == 2, split along the pixels): thread = (filter, real channel) sums the slices of its k*k taps
-// and writes them as ONE contiguous run of dW [F][C][k*k]; neighbouring threads write neighbouring runs, and for every tap they
-// read neighbouring channels of the tap-major partials -- coalesced both ways (the generic reduction scatters 4-byte stores
-// k*k floats apart).
-__global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const TcParams p) {
-    const int C = p.cv_Creal, k2 = p.cv_k * p.cv_k;
-    const size_t total = (size_t)p.m * C, slice = (size_t)p.m * p.n;
-    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-        const int f = (int)(e / C), c = (int)(e - (size_t)f * C);
-        float* dst = p.c + e * k2;
-        for (int tap = 0; tap < k2; ++tap) {
-            const float* src = p.partial + (size_t)f * p.n + (size_t)tap * p.cv_C + c;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            int z = 0;
-            for (; z + 3 < p.splits; z += 4) {
-                s0 += src[(size_t)z * slice]; s1 += src[(size_t)(z + 1) * slice];
-                s2 += src[(size_t)(z + 2) * slice]; s3 += src[(size_t)(z + 3) * slice];
-            }
-            for (; z < p.splits; ++z) s0 += src[(size_t)z * slice];
-            dst[tap] = (s0 + s1) + (s2 + s3);
-        }
-    }
-}
-
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1199,13 +1175,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         size_t blocks = (totalc / 4 + 63) / 64;   // 64 float4 columns per block on the vector path
         size_t cap = (size_t)sms * 8;
         if (blocks > cap) blocks = cap;
-        if (p.cv_final) {
-            size_t wb = ((size_t)g.m * p.cv_Creal + 255) / 256;
-            if (wb > cap) wb = cap;
-            conv_wgrad_reduce_kernel<<<(int)wb, 256, 0, s>>>(p);
-        } else {
-            tc_splitk_reduce_kernel<<<(int)blocks, 256, 0, s>>>(p);
-        }
+        tc_splitk_reduce_kernel<<<(int)blocks, 256, 0, s>>>(p);
         BLA_LAUNCH_CHECK();
         count_launch();
         pool_free(ws);
