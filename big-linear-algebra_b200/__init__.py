@@ -125,6 +125,7 @@ PROTOTYPES = {
     "bla_get_gemm_path": (C.c_int, []),
     "bla_tc_available": (C.c_int, []),
     "bla_tc_launch_count": (C.c_ulonglong, []),
+    "bla_tc_main_columns": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "bla_set_quirks": (None, [C.c_int]),
     "bla_get_quirks": (C.c_int, []),
     "bla_launch_count": (C.c_ulonglong, []),

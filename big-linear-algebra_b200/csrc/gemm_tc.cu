@@ -1083,6 +1083,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         const long long main_tiles = m_units > 0 ? full * slots / m_units : 0;
         if (full >= 1 && rem > 0 && rem * 2 <= slots && main_tiles >= 1 && main_tiles < p.n_tiles) {
             const int n_main = (int)(main_tiles * p.bn);
+            if (g.plan_main_columns) { *g.plan_main_columns = n_main; return true; }
             GemmArgs lo = g, hi = g;
             lo.no_tail_split = hi.no_tail_split = true;
             lo.n = n_main;
@@ -1098,6 +1099,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
             }
         }
     }
+    if (g.plan_main_columns) { *g.plan_main_columns = g.n; return true; }
     int splits = 1;
     if (conv_splits > 0) {
         splits = conv_splits;
@@ -1311,3 +1313,18 @@ extern "C" int bla_tc_available(void) {
     return bla::encode_fn() != nullptr && !bla::g_tc_broken;
 }
 extern "C" unsigned long long bla_tc_launch_count(void) { return bla::g_tc_launches; }
+// include/bla.h: how many of the n columns of a row-major m x n x k product the FIRST tensor-kernel launch computes (the rest, if
+// any, is the split-K tail launch; n when the product is not split or not eligible)
+extern "C" int bla_tc_main_columns(int m, int n, int k) {
+    using namespace bla;
+    if (!bla_tc_available() || m <= 0 || n <= 0 || k <= 0) return n;
+    int out = n;
+    GemmArgs g{};
+    g.m = m; g.n = n; g.k = k;
+    g.a = reinterpret_cast<const float*>(uintptr_t(256)); g.lda = k;      // aligned dummies: the query never dereferences them
+    g.b = reinterpret_cast<const float*>(uintptr_t(256)); g.ldb = n;
+    g.c = reinterpret_cast<float*>(uintptr_t(256)); g.ldc = n;
+    g.plan_main_columns = &out;
+    if (!gemm_3xtf32(g, rt().stream)) return n;
+    return out;
+}

@@ -59,6 +59,7 @@ struct GemmArgs {
     bla_epilogue epi;     // zero-initialised = plain store
     const ConvTc* conv;   // nullptr for a plain GEMM; else m = F, n = imgs*Ho*Wo, k = k*k*C, a = weights [F][(ki,kj,c)]
     bool no_tail_split;   // internal: this call already is one half of a main / tail column split (gemm_tc.cu)
+    int* plan_main_columns;   // query only: receives the column count of the first launch (n when there is no split); nothing runs
 };
 // Dispatch on rt().gemm_path and the shape.
 void gemm(const GemmArgs& g, cudaStream_t s);

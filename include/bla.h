@@ -51,6 +51,9 @@ int bla_get_gemm_path(void);
  * A GEMM whose operands are not 16-byte aligned (base or row pitch) runs on the FP32 path instead. */
 int bla_tc_available(void);
 unsigned long long bla_tc_launch_count(void);
+/* Columns of a row-major m x n x k product that the FIRST tensor-kernel launch computes: against wave quantisation a product whose
+ * last wave would be under half full is issued as a main launch + a split-K tail launch (n when it is not split). */
+int bla_tc_main_columns(int m, int n, int k);
 /* 1 (default, $BLA_QUIRKS): reproduce reference defects D2 (matrix_col_sum stride) and D5 (group norm
  * divides by the variance); 0: the mathematically intended results. */
 void bla_set_quirks(int on);
