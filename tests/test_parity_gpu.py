@@ -542,6 +542,46 @@ def _mlp_step_check(b, B, tol):
     assert np.array_equal(probs.argmax(axis=0), want.argmax(axis=0))
 
 
+@pytest.mark.parametrize("path", ["fp32", "auto"])
+def test_mlp_full_size_step_is_the_sum_of_its_column_shards(bla, path):
+    """BASELINE.json configs[2] at its full size (60,000 columns), through the property data parallelism rests on: the
+    update of one full-batch step equals the sum of the updates computed from its column shards, each given its place in the
+    global batch (global_batch, col_offset: the D2 window sums of the bias gradients are global-index based) -- and the
+    loss / accuracy statistics add up.  The oracle covers the same step at sizes it finishes in seconds."""
+    b = bla
+    b.bla_set_gemm_path(b.GEMM_FP32 if path == "fp32" else b.GEMM_AUTO)
+    B, lr = 60000, 0.02
+    rng = np.random.default_rng(60)
+    dims = (C.c_int * 4)(784, 256, 128, 10)
+    shapes = ((256, 784), (256,), (128, 256), (128,), (10, 128), (10,))
+    p0 = [f32(rng.uniform(-0.08, 0.08, s)) for s in shapes]
+    X = rng.integers(0, 256, (784, B)).astype(np.float32)
+    labels = rng.integers(0, 10, B)
+    Y = np.zeros((10, B), np.float32); Y[labels, np.arange(B)] = 1
+
+    def step(c0, cnt):
+        net = b.bla_mlp_create(dims, cnt)
+        b.bla_mlp_set_params(net, *[ptr(p) for p in p0])
+        stats = np.zeros(2)
+        b.bla_mlp_train_step(net, ptr(np.ascontiguousarray(X[:, c0:c0 + cnt])), ptr(np.ascontiguousarray(Y[:, c0:c0 + cnt])), cnt, B, c0, lr,
+                             ptr(stats))
+        got = [np.empty_like(p) for p in p0]
+        b.bla_mlp_get_params(net, *[ptr(g) for g in got])
+        b.bla_mlp_destroy(net)
+        return [g.astype(np.float64) - p.astype(np.float64) for g, p in zip(got, p0)], stats
+
+    try:
+        full, fs = step(0, B)
+        parts = [step(c0, cnt) for c0, cnt in ((0, 22500), (22500, 7500), (30000, 30000))]     # ragged shards, as dp.shard_columns can make
+        assert int(fs[1]) == sum(int(s[1]) for _, s in parts)
+        assert abs(fs[0] - sum(s[0] for _, s in parts)) <= 1e-6 * abs(fs[0])
+        for i, d in enumerate(full):
+            tot = sum(pp[0][i] for pp in parts)
+            assert rel_err(tot, d) <= (2e-5 if path == "fp32" else 1e-4), (i, rel_err(tot, d))
+    finally:
+        b.bla_set_gemm_path(b.GEMM_FP32)
+
+
 # ------------------------------------------------------------------------------------------------
 # batched, device-resident implicit-GEMM conv2d (include/bla.h) vs the f64 oracle, image by image
 # ------------------------------------------------------------------------------------------------
