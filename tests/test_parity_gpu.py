@@ -757,3 +757,40 @@ def test_unet_resnet_block_vs_reference(bla, Cin, F, HW):
     for name in ("gn1", "conv1", "time", "gn2"):
         assert rel_err(gi[name], wi[name]) <= 2e-5, (name, rel_err(gi[name], wi[name]))
     assert rel_err(got, want) <= 5e-5, rel_err(got, want)
+
+
+@pytest.mark.parametrize("Cin,H,F,k,st", [(128, 32, 128, 3, 1), (128, 32, 256, 3, 2), (256, 16, 256, 1, 1)])
+@pytest.mark.parametrize("path", ["fp32", "3xtf32"])
+def test_conv_bench_size_adjoint_and_additivity_properties(bla, Cin, H, F, k, st, path):
+    """The bench's conv shapes (64 images) are too big for the oracle, so they are tied together by the identities
+    that define the three kernels: <conv(x, w), dy> = <x, dgrad(dy, w)> = <w, wgrad(x, dy)> (adjointness), the forward result of
+    an image does not depend on its batch, and the weight gradient of a batch is the sum over its halves."""
+    b = bla
+    b.bla_set_gemm_path(b.GEMM_FP32 if path == "fp32" else b.GEMM_3XTF32)
+    imgs, Ho = 64, -(-H // st)
+    rng = np.random.default_rng(Cin + F + k + st)
+    x = f32(rng.normal(size=(imgs, Cin, H, H))); w = f32(rng.normal(0, 0.05, (F, Cin, k, k))); dy = f32(rng.normal(size=(imgs, F, Ho, Ho)))
+    xd, wd, dyd = _dev(b, x), _dev(b, w), _dev(b, dy)
+    yd = b.bla_malloc_device(dy.nbytes); dxd = b.bla_malloc_device(x.nbytes); dwd = b.bla_malloc_device(w.nbytes)
+    try:
+        b.bla_conv2d_forward(xd, wd, yd, imgs, Cin, H, H, F, k, st)
+        b.bla_conv2d_dgrad(dyd, wd, dxd, imgs, Cin, H, H, F, k, st)
+        b.bla_conv2d_wgrad(xd, dyd, dwd, imgs, Cin, H, H, F, k, st)
+        y, dx, dw = _host(b, yd, dy.shape).astype(np.float64), _host(b, dxd, x.shape).astype(np.float64), _host(b, dwd, w.shape).astype(np.float64)
+        a1 = float((y * dy).sum()); a2 = float((x.astype(np.float64) * dx).sum()); a3 = float((w.astype(np.float64) * dw).sum())
+        scale = float(np.sqrt((y * y).sum() * (dy.astype(np.float64) ** 2).sum()))
+        tol = 1e-5 if path == "fp32" else 5e-5
+        assert abs(a1 - a2) <= tol * scale and abs(a1 - a3) <= tol * scale, (a1, a2, a3, scale)
+        # the second half of the batch on its own: same forward rows, and the weight gradient splits
+        half = imgs // 2
+        off_x, off_y = half * Cin * H * H * 4, half * F * Ho * Ho * 4
+        b.bla_conv2d_forward(xd + off_x, wd, yd, half, Cin, H, H, F, k, st)
+        assert rel_err(_host(b, yd, (half, F, Ho, Ho)), y[half:]) <= tol
+        b.bla_conv2d_wgrad(xd, dyd, dwd, half, Cin, H, H, F, k, st)
+        dw1 = _host(b, dwd, w.shape).astype(np.float64)
+        b.bla_conv2d_wgrad(xd + off_x, dyd + off_y, dwd, half, Cin, H, H, F, k, st)
+        assert rel_err(dw1 + _host(b, dwd, w.shape), dw) <= tol
+    finally:
+        for d in (xd, wd, dyd, yd, dxd, dwd):
+            b.bla_free(d)
+        b.bla_set_gemm_path(b.GEMM_FP32)
