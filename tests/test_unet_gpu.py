@@ -248,3 +248,35 @@ def test_unet_sgd_reduces_the_loss_on_a_fixed_batch(bla):
         b.bla_unet_destroy(net)
         b.bla_set_quirks(1)
         b.bla_set_gemm_path(b.GEMM_FP32)
+
+
+def test_unet_reference_size_gradient_is_additive_over_images(bla):
+    """The reference-size model on 8 images, tensor path: the gradient of the batch is the sum of the gradients of its halves
+    and the losses add (what the data-parallel all-reduce relies on); no CPU checker is needed at this size."""
+    b = bla
+    b.bla_set_quirks(0)
+    b.bla_set_gemm_path(b.GEMM_AUTO)
+    net, tensors = make_net(b, FULL, 8)
+    try:
+        flat = unet_ref.synthetic_params(FULL, tensors, 8, 5)
+        b.bla_unet_set_params(net, ptr(flat))
+        x, temb, noise = inputs(FULL, 8, 4)
+        n = flat.size
+
+        def grads(lo, hi):
+            loss = np.zeros(1)
+            b.bla_unet_train_step(net, ptr(np.ascontiguousarray(x[lo:hi])), ptr(np.ascontiguousarray(temb[lo:hi])),
+                                  ptr(np.ascontiguousarray(noise[lo:hi])), hi - lo, 0.0, ptr(loss))
+            g = np.empty(n, np.float32)
+            b.bla_unet_get_grads(net, ptr(g))
+            return g.astype(np.float64), loss[0]
+        g_all, l_all = grads(0, 8)
+        g_a, l_a = grads(0, 4)
+        g_b, l_b = grads(4, 8)
+        assert abs(l_all - (l_a + l_b)) <= 1e-5 * abs(l_all)
+        worst = max(rel_err(g_a[o:o + c] + g_b[o:o + c], g_all[o:o + c]) for _, o, c in tensors)
+        assert worst <= 2e-3, worst          # the 3xTF32 budget through ~140 chained GEMMs, as in test_unet_reference_size_vs_autograd
+    finally:
+        b.bla_unet_destroy(net)
+        b.bla_set_quirks(1)
+        b.bla_set_gemm_path(b.GEMM_FP32)
