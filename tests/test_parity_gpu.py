@@ -794,3 +794,33 @@ def test_conv_bench_size_adjoint_and_additivity_properties(bla, Cin, H, F, k, st
         for d in (xd, wd, dyd, yd, dxd, dwd):
             b.bla_free(d)
         b.bla_set_gemm_path(b.GEMM_FP32)
+
+
+def test_elementwise_at_bench_size_device_resident(bla):
+    """The bench's 8192 x 8192 (256 MiB) device-resident operands: the elementwise kernels are single IEEE fp32 operations, so the
+    results must be bit-identical to numpy's float32; the D2-quirk window sum and the Frobenius norm against float64 sums."""
+    b = bla
+    R = Cn = 8192
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((R, Cn), dtype=np.float32); y = rng.standard_normal((R, Cn), dtype=np.float32)
+    bias = rng.standard_normal((R, 1), dtype=np.float32)
+    X, Yd, Bd = b.device_matrix_from(x), b.device_matrix_from(y), b.device_matrix_from(bias)
+    try:
+        h0 = b.bla_h2d_bytes()
+        b.matrix_scale(X, C.c_float(1.5)); want = x * np.float32(1.5)
+        b.matrix_add(X, Yd); want += y
+        b.matrix_multiply_elementwise(X, Yd); want *= y
+        b.matrix_add_tile_columns(X, Bd); want += bias
+        b.relu(C.cast(X.contents.data, C.c_void_p), R * Cn); want = np.maximum(want, np.float32(0))
+        assert b.bla_h2d_bytes() == h0                         # device-resident: nothing staged
+        assert np.array_equal(b.to_numpy(X), want)
+        cs = b.matrix_col_sum(X.contents)                      # rows == cols: the quirk window of row i is row i itself
+        assert rel_err(b.to_numpy(cs), want.astype(np.float64).sum(axis=1, keepdims=True)) <= FP32_TOL
+        b.free_matrix(cs)
+        fro = float(np.sqrt((want.astype(np.float64) ** 2).sum()))
+        assert abs(b.frobenius_norm(X.contents) - fro) <= FP32_TOL * fro
+        b.matrix_transpose(X)
+        assert np.array_equal(b.to_numpy(X), want.T)
+    finally:
+        for m_ in (X, Yd, Bd):
+            b.free_matrix(m_)
