@@ -824,3 +824,31 @@ def test_elementwise_at_bench_size_device_resident(bla):
     finally:
         for m_ in (X, Yd, Bd):
             b.free_matrix(m_)
+
+
+def test_group_norm_at_bench_size_vs_float64(bla):
+    """256 images x 128 channels x 32 x 32 (the bench's group-norm shape, slabs of 32768 elements: the persistent TMA / cluster
+    kernels) against lib/norm.c:5-93 restated with float64 numpy reductions -- divide-by-variance quirk on (D5)."""
+    b = bla
+    b.bla_set_quirks(1)
+    imgs, Cn, HW, gs = 256, 128, 1024, 32
+    G = Cn // gs
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((imgs, G, gs * HW), dtype=np.float32) * np.float32(1.5) + np.float32(0.3)
+    dy = rng.standard_normal((imgs, G, gs * HW), dtype=np.float32)
+    xd, dyd = _dev(b, x), _dev(b, dy)
+    yd = b.bla_malloc_device(x.nbytes); dxd = b.bla_malloc_device(x.nbytes)
+    vd = b.bla_malloc_device(imgs * G * 4); md = b.bla_malloc_device(imgs * G * 4)
+    try:
+        b.bla_group_norm(xd, yd, vd, md, imgs, Cn, HW, gs)
+        b.bla_group_norm_ddx(dyd, dxd, xd, md, vd, imgs, Cn, HW, gs)
+        x64, d64 = x.astype(np.float64), dy.astype(np.float64)
+        mu = x64.mean(axis=2, keepdims=True); var = ((x64 - mu) ** 2).mean(axis=2, keepdims=True)
+        wn = (x64 - mu) / var                                                   # norm.c:44 with epsilon == 0
+        assert rel_err(_host(b, yd, x.shape), wn) <= FP32_TOL
+        assert rel_err(_host(b, md, (imgs, G, 1)), mu) <= FP32_TOL and rel_err(_host(b, vd, (imgs, G, 1)), var) <= FP32_TOL
+        want = (d64 - d64.mean(axis=2, keepdims=True) - wn * (wn * d64).mean(axis=2, keepdims=True)) / var   # norm.c:62-90
+        assert rel_err(_host(b, dxd, x.shape), want) <= FP32_TOL
+    finally:
+        for d in (xd, dyd, yd, dxd, vd, md):
+            b.bla_free(d)
