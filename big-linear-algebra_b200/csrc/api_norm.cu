@@ -51,6 +51,7 @@ struct GnParams {
     int relu;
     float drop_rate;
     unsigned long long drop_seed;
+    const float* addend;   // backward only: dx += addend (same layout as dx): the residual branch's gradient
 };
 
 // forward epilogue on element `idx` of the whole [images][C][HW] tensor
@@ -69,6 +70,11 @@ __device__ __forceinline__ float gn_gate(float d, float xv, float mu, size_t idx
     if (p.relu && !(xv > mu)) d = 0.f;                                                      // multi_channel_relu_ddx, cifar_unet.c:241
     if (p.drop_rate > 0.f && uniform_at(p.drop_seed, idx, 0.f, 1.f) < p.drop_rate) d = 0.f;   // _dropout_mask, cifar_unet.c:1170
     return d;
+}
+// backward epilogue: + the gradient that reaches the same tensor through the residual connection (cifar_unet.c:1218-1220)
+__device__ __forceinline__ float4 gn_add4(float4 o, size_t idx, const GnParams& p) {
+    if (p.addend) { const float4 a = __ldg(reinterpret_cast<const float4*>(p.addend + idx)); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+    return o;
 }
 __device__ __forceinline__ float4 gn_gate4(float4 d, float4 xv, float mu, size_t idx, const GnParams& p) {
     if (p.relu | (p.drop_rate > 0.f)) {
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) group_norm_bwd_kernel(const float* _
     for (size_t i = threadIdx.x; i < n; i += kThreads) {
         float w = IN_SMEM ? slab[i] : (x[off + i] - mu) / sd;
         float d = IN_SMEM ? slab[n + i] : gn_gate(dy[off + i], x[off + i], mu, off + i, p);
-        dx[off + i] = (d - mean_g - w * mean_gw) / sd;
+        dx[off + i] = (d - mean_g - w * mean_gw) / sd + (p.addend ? p.addend[off + i] : 0.f);
     }
 }
 
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_vec(const floa
         float4 o;
         o.x = (d.x - mean_g - (a.x - mu) / sd * mean_gw) / sd; o.y = (d.y - mean_g - (a.y - mu) / sd * mean_gw) / sd;
         o.z = (d.z - mean_g - (a.z - mu) / sd * mean_gw) / sd; o.w = (d.w - mean_g - (a.w - mu) / sd * mean_gw) / sd;
-        ds[i] = o;
+        ds[i] = gn_add4(o, off + 4 * (size_t)i, p);
     }
 }
 
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(kClThreads, 2) group_norm_bwd_cluster(const fl
             float4 o;
             o.x = (d[u].x - mean_g - w[u].x * mean_gw) / sd; o.y = (d[u].y - mean_g - w[u].y * mean_gw) / sd;
             o.z = (d[u].z - mean_g - w[u].z * mean_gw) / sd; o.w = (d[u].w - mean_g - w[u].w * mean_gw) / sd;
-            ds[i] = o;
+            ds[i] = gn_add4(o, off + 4 * (size_t)i, p);
         }
     }
     cluster.sync();
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(kSmallThreads) group_norm_bwd_small(const floa
             float4 o;
             o.x = (d[u].x - mean_g - w[u].x * mean_gw) / sd; o.y = (d[u].y - mean_g - w[u].y * mean_gw) / sd;
             o.z = (d[u].z - mean_g - w[u].z * mean_gw) / sd; o.w = (d[u].w - mean_g - w[u].w * mean_gw) / sd;
-            ds[i] = o;
+            ds[i] = gn_add4(o, off + 4 * (size_t)i, p);
         }
     }
 }
@@ -712,7 +718,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
                 float4 o;
                 o.x = (d[u].x - mean_g - w[u].x * mean_gw) / sd; o.y = (d[u].y - mean_g - w[u].y * mean_gw) / sd;
                 o.z = (d[u].z - mean_g - w[u].z * mean_gw) / sd; o.w = (d[u].w - mean_g - w[u].w * mean_gw) / sd;
-                ds[i] = o;
+                ds[i] = gn_add4(o, off + 4 * (size_t)(beg + i), p);
             }
         }
     }
@@ -741,7 +747,7 @@ void launch_cluster(Kernel kernel, dim3 grid, cudaStream_t s, Args... args) {
 
 void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int images, int C, int HW, int group_size, int quirk,
                       cudaStream_t s, const GnFuse* fuse) {
-    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, quirk, 0, 0.f, 0ull};
+    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, quirk, 0, 0.f, 0ull, nullptr};
     if (fuse) { p.relu = fuse->relu; p.drop_rate = fuse->drop_rate; p.drop_seed = fuse->drop_seed; }
     if (images <= 0 || C <= 0 || HW <= 0) return;
     const size_t slab = (size_t)min(group_size, C) * HW;
@@ -782,12 +788,12 @@ void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int i
 
 void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* means, const float* stdevs, int images, int C, int HW,
                       int group_size, cudaStream_t s, const GnFuse* fuse) {
-    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, 1, 0, 0.f, 0ull};
-    if (fuse) { p.relu = fuse->relu; p.drop_rate = fuse->drop_rate; p.drop_seed = fuse->drop_seed; }
+    GnParams p{C, HW, group_size, (C + group_size - 1) / group_size, 1, 0, 0.f, 0ull, nullptr};
+    if (fuse) { p.relu = fuse->relu; p.drop_rate = fuse->drop_rate; p.drop_seed = fuse->drop_seed; p.addend = fuse->addend; }
     if (images <= 0 || C <= 0 || HW <= 0) return;
     const size_t slab = (size_t)min(group_size, C) * HW;
     dim3 grid(p.G, images);
-    const bool vec_ok = al16(dy) && al16(dx) && al16(x) && (HW % 4 == 0);
+    const bool vec_ok = al16(dy) && al16(dx) && al16(x) && al16(p.addend) && (HW % 4 == 0);
     const bool tail_ok = (C % group_size == 0) || (((size_t)(C % group_size) * HW) % 4 == 0);
     if (vec_ok && tail_ok && slab <= (size_t)kSmallThreads * 8 * 4 && (long long)p.G * images >= 2LL * rt().num_sms) {
         if (slab <= (size_t)kSmallThreads * 2 * 4) group_norm_bwd_small<2><<<grid, kSmallThreads, 0, s>>>(dy, dx, x, means, stdevs, p);

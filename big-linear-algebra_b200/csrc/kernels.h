@@ -110,7 +110,7 @@ void conv2d_dgrad(const float* dy, const float* w, float* dx, int imgs, int C, i
 // Neighbours of a group norm fused into its kernels (the U-Net's group_norm -> multi_channel_relu -> _dropout chain,
 // cifar_unet.c:1046-1061): forward writes dropout(relu(norm(x))); backward gates the incoming gradient with the same masks
 // (ReLU: x > mean; dropout: element i of the tensor is dropped iff uniform_at(drop_seed, i) < drop_rate).
-struct GnFuse { int relu; float drop_rate; unsigned long long drop_seed; };
+struct GnFuse { int relu; float drop_rate; unsigned long long drop_seed; const float* addend = nullptr; };   // addend: backward only, dx += addend
 void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int images, int C, int HW, int group_size, int quirk,
                       cudaStream_t s, const GnFuse* fuse = nullptr);
 void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* means, const float* stdevs, int images, int C, int HW,

@@ -709,14 +709,15 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         if (!want_din) break;
         const size_t ein = (size_t)imgs * nd.cin * hw;
         conv2d_dgrad(t2, P + nd.w1, t1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, n->permuted ? nd.f1 : nullptr);
-        Sink k = open_sink(n, nd.in0, n->s3, imgs);
-        k_group_norm_bwd(t1, k.dst, a->out, nd.mu1, nd.var1, imgs, nd.cin, hw, c.group_size, s, &relu_only);
+        // the residual branch's gradient (through the 1x1 conv when the widths differ; t2 is free again) rides in the epilogue
+        // of the first group norm's backward kernel instead of a separate add (cifar_unet.c:1206-1220)
+        GnFuse relu_add{1, 0.f, 0ull, nd.gout};
         if (nd.res) {
-            conv2d_dgrad(nd.gout, P + nd.wr, t1, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, n->permuted ? nd.fr : nullptr);
-            k_add(k.dst, t1, ein, s);
-        } else {
-            k_add(k.dst, nd.gout, ein, s);
+            conv2d_dgrad(nd.gout, P + nd.wr, t2, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, n->permuted ? nd.fr : nullptr);
+            relu_add.addend = t2;
         }
+        Sink k = open_sink(n, nd.in0, n->s3, imgs);
+        k_group_norm_bwd(t1, k.dst, a->out, nd.mu1, nd.var1, imgs, nd.cin, hw, c.group_size, s, &relu_add);
         close_sink(k, s);
         break;
     }
