@@ -484,10 +484,9 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
     if (dp) {                             // the rest of the flat buffer + {loss, correct}
         BLA_CUDA(cudaEventRecord(m->ev_rest, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
-        comm_group_start();
         comm_allreduce_f32_on(m->grads + seg1, m->nparams - seg1, cs);
-        comm_allreduce_f64_on(m->stats, 2 * kStatSlots, cs);
-        comm_group_end();
+        // {loss, correct} are all-reduced where they are READ (bla_mlp_read_stats), not here: they accumulate over steps, and
+        // reducing the running totals every step would count the earlier steps once per rank again
         BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
         BLA_CUDA(cudaStreamWaitEvent(s, m->ev_comm, 0));
     }
@@ -603,6 +602,14 @@ void bla_mlp_init_params(bla_mlp* m, unsigned long long seed) {
 
 void bla_mlp_read_stats(bla_mlp* m, double* stats_host) {
     double slots[2 * kStatSlots];
+    if (comm_active()) {   // data parallel: a collective -- every rank reads its statistics at the same point
+        cudaStream_t cs = comm_stream();
+        BLA_CUDA(cudaEventRecord(m->ev_rest, rt().stream));
+        BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
+        comm_allreduce_f64_on(m->stats, 2 * kStatSlots, cs);
+        BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
+        BLA_CUDA(cudaStreamWaitEvent(rt().stream, m->ev_comm, 0));
+    }
     BLA_CUDA(cudaMemcpyAsync(slots, m->stats, sizeof(slots), cudaMemcpyDeviceToHost, rt().stream));
     rt().d2h_bytes += sizeof(slots);
     BLA_CUDA(cudaMemsetAsync(m->stats, 0, sizeof(slots), rt().stream));

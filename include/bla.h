@@ -168,7 +168,8 @@ void bla_mlp_train_step_u8(bla_mlp* net, const unsigned char* x_u8, const float*
                            int col_offset, float lr_mult, double* stats_host);
 /* Forward only (model/mnist_nn.c:446-463, `run`): probs [classes x batch] out. */
 void bla_mlp_forward(bla_mlp* net, const float* x, int batch, float* probs);
-/* {loss_sum, num_correct} accumulated on the device since the last call (then cleared). */
+/* {loss_sum, num_correct} accumulated on the device since the last call (then cleared).  With an active communicator this is a
+ * collective (the totals of all ranks are summed): every rank must call it -- or pass stats_host to the step -- at the same point. */
 void bla_mlp_read_stats(bla_mlp* net, double* stats_host);
 
 /* ---- data pipeline: lib/mnist_csv2.c and lib/cifar10.c with the dataset resident in HBM ------------------- */

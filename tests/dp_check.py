@@ -46,6 +46,23 @@ def main():
             o64.orc_mlp_step(dims, B, *[ptr(p) for p in p64], ptr(X.astype(np.float64)), ptr(Y.astype(np.float64)), 0.02, 1,
                              C.byref(loss), C.byref(correct), None, 1)
             ok &= abs(stats[0] - loss.value) <= 1e-4 * abs(loss.value) and int(stats[1]) == correct.value
+    # statistics accumulated over steps that do not read them: one collective read returns the global totals, counted once
+    tot_loss = 0.0; tot_correct = 0
+    for s in range(2):
+        X = rng.integers(0, 256, (784, B)).astype(np.float32)
+        labels = rng.integers(0, 10, B)
+        Y = np.zeros((10, B), np.float32); Y[labels, np.arange(B)] = 1
+        b.bla_mlp_train_step(net, ptr(np.ascontiguousarray(X[:, off:off + cnt])), ptr(np.ascontiguousarray(Y[:, off:off + cnt])), cnt, B, off, 0.02, None)
+        if rank == 0:
+            loss = C.c_double(); correct = C.c_int()
+            o64.orc_mlp_step(dims, B, *[ptr(p) for p in p64], ptr(X.astype(np.float64)), ptr(Y.astype(np.float64)), 0.02, 1,
+                             C.byref(loss), C.byref(correct), None, 1)
+            tot_loss += loss.value; tot_correct += correct.value
+    stats = np.zeros(2)
+    b.bla_mlp_read_stats(net, ptr(stats))
+    if rank == 0:
+        ok &= abs(stats[0] - tot_loss) <= 1e-4 * abs(tot_loss) and int(stats[1]) == tot_correct
+    steps += 2
     got = [np.empty_like(p) for p in p32]
     b.bla_mlp_get_params(net, *[ptr(g) for g in got])
     # every rank must hold identical parameters (same all-reduced gradient, same update)
