@@ -365,6 +365,9 @@ def main():
     e2e = timed(step_e2e, e2e_steps, 3)
     e2e_ms = e2e["ms"] / e2e_steps
     e2e_value = Bg / (e2e_ms * 1e-3)
+    b.bla_mlp_set_host_chunking(net, 0)       # the same call with the batch staged in one piece, for the record
+    e2e_one = timed(step_e2e, e2e_steps, 2)["ms"] / e2e_steps
+    b.bla_mlp_set_host_chunking(net, -1)
 
     # the same end-to-end step from BYTE pixels (MNIST's native storage; additive entry point): 4x less PCIe traffic
     hx8 = b.bla_malloc_pinned(DIMS[0] * Bl)
@@ -375,6 +378,9 @@ def main():
 
     e2e8 = timed(step_e2e_u8, e2e_steps, 3)
     e2e8_ms = e2e8["ms"] / e2e_steps
+    b.bla_mlp_set_host_chunking(net, 0)
+    e2e8_one = timed(step_e2e_u8, e2e_steps, 2)["ms"] / e2e_steps
+    b.bla_mlp_set_host_chunking(net, -1)
 
     # ---- roofline of the dominant kernel: layer-1 forward GEMM (256 x 784 x Bl), alone ----
     pk = peaks()
@@ -450,9 +456,12 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"] // e2e_steps,
                         "d2h_bytes_per_step": e2e["d2h"] // e2e_steps, "ms_per_step": e2e_ms,
-                        "api": "bla_mlp_train_step(host float32 X[784xB], Y[10xB], &stats)"},
+                        "launches_per_step": e2e["launches"] // e2e_steps, "ms_per_step_one_piece": e2e_one,
+                        "api": "bla_mlp_train_step(host float32 X[784xB], Y[10xB], &stats), batch staged in column chunks "
+                               "behind the training of the chunk before"},
                 "e2e_u8": {"value": Bg / (e2e8_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e8["h2d"] // e2e_steps,
                            "d2h_bytes_per_step": e2e8["d2h"] // e2e_steps, "ms_per_step": e2e8_ms,
+                           "ms_per_step_one_piece": e2e8_one,
                            "api": "bla_mlp_train_step_u8(host uint8 X[784xB], Y[10xB], &stats)"},
                 "gpu_launches": int(res["launches"]), "clocks": clk,
                 "loss_per_sample_last": float(stats[0] / max(1, Bg * args.steps)) if world == 1 else None,

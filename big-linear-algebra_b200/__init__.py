@@ -211,6 +211,7 @@ PROTOTYPES = {
     "bla_mlp_init_params": (None, [C.c_void_p, C.c_ulonglong]),
     "bla_mlp_train_step": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "bla_mlp_train_step_u8": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "bla_mlp_set_host_chunking": (None, [C.c_void_p, C.c_int]),
     "bla_mlp_forward": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "bla_mlp_read_stats": (None, [C.c_void_p, C.c_void_p]),
     # include/bla.h -- NCCL

@@ -11,6 +11,7 @@
 //   1 all-reduce of the flat gradient buffer (data-parallel only) and 1 fused SGD update.
 // Activations are features x batch (batch = columns), exactly the reference's layout, so a
 // data-parallel shard is a column range and gradients are plain sums over ranks.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -46,6 +47,12 @@ struct bla_mlp {
     cudaEvent_t ev_l1, ev_rest, ev_comm;   // ordering between the compute stream and the collective stream
     cudaStream_t side;                     // bias-gradient window sums run here, next to the wgrad GEMMs
     cudaEvent_t ev_fork, ev_join;
+    // host batches in column chunks: chunk i+1 crosses PCIe on `copy` while chunk i is trained on the compute stream
+    static constexpr int kMaxChunks = 16;
+    int chunk_cols;                        // < 0: automatic (pinned host batches only), 0: off, > 0: forced chunk width
+    float* grads_chunk;                    // gradient of chunks 1.. before it is added to `grads`
+    cudaStream_t copy;
+    cudaEvent_t ev_chunk[kMaxChunks], ev_free;
 };
 
 namespace {
@@ -399,8 +406,9 @@ void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s, b
     gemm(g, s);
 }
 
-void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, float lr_mult, double* stats_host) {
-    if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
+// forward + backward of columns [c0, c0 + B) of a Bg-column batch: gradients into m->grads (all-reduced when `reduce` and a
+// communicator is active), loss / accuracy added to m->stats
+void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, bool reduce) {
     cudaStream_t s = rt().stream;
     const int quirk = rt().quirks;
     const bool skinny = skinny_head(m, B);
@@ -469,7 +477,7 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
     dgrad(1, m->dz2, m->a1, m->dz1);      // :284-289
     wgrad(0, m->dz1, x, x_scale);         // :290-293 (X/255 again folded into alpha)
     join_side();                          // db1 is part of the first segment
-    const bool dp = comm_active();
+    const bool dp = reduce && comm_active();
     cudaStream_t cs = dp ? comm_stream() : nullptr;
     const size_t seg1 = m->off_w[1];      // [W1 | b1] occupy the first seg1 floats of the flat gradient buffer
     if (dp) {
@@ -490,7 +498,85 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
         BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
         BLA_CUDA(cudaStreamWaitEvent(s, m->ev_comm, 0));
     }
+}
+
+void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, float lr_mult, double* stats_host) {
+    if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
+    backprop(m, x, x_scale, y, B, Bg, c0, true);
     // clip_gradient is a no-op (threshold INFINITY, :13,:296-301); scale by -lr and add  :303-315
+    k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, rt().stream);
+    if (stats_host) bla_mlp_read_stats(m, stats_host);
+}
+
+// Chunk width for a HOST batch of B columns, 0 = take it in one piece.  A 60,000-column float batch is 3.5 ms of PCIe
+// against 0.45 ms of training: in ~6,000-column chunks all but the last chunk's math hides behind the transfer (measured
+// 3.96 -> 3.75 ms).  A chunk is a strided 2-D copy, and the copy engine needs rows of >= ~24 KB to keep PCIe full (measured:
+// 6 KB rows reach 19 GB/s of 54), so byte batches are only cut in two (profiles/r01_e2e_chunk_sweep.json).
+int host_chunk_cols(const bla_mlp* m, int B, MemKind kind, size_t elem_bytes) {
+    if (kind == kDevice || kind == kManaged || m->chunk_cols == 0) return 0;
+    int cols = m->chunk_cols;
+    if (cols < 0) {
+        if (kind != kPinned) return 0;   // pageable copies are staged by the driver and block the host anyway
+        if (elem_bytes == 1) {
+            if (B < 32768) return 0;
+            cols = ceil_div(B, 2);
+        } else {
+            if (B < 16384) return 0;
+            cols = 6144;
+        }
+    }
+    cols = (cols + 63) / 64 * 64;
+    while (ceil_div(B, cols) > bla_mlp::kMaxChunks) cols += 64;
+    return ceil_div(B, cols) >= 2 ? cols : 0;
+}
+
+// One step on a host batch (float32 or uint8 pixels), column chunk by column chunk.  A chunk is a column shard of the batch
+// in TIME: it is staged contiguously ([n x cols] at n * first_column of each per-batch buffer), trained with its place in the
+// global batch (col_offset, as a data-parallel rank would be), and its gradient is added to the chunks' before.  The sum over
+// chunks is the full-batch gradient (tests: ...step_is_the_sum_of_its_column_shards, ...host_batch_in_chunks...).
+void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int cols, float x_scale, int B, int Bg, int c0,
+                  float lr_mult, double* stats_host) {
+    if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
+    cudaStream_t s = rt().stream, cp = m->copy;
+    const int n0 = m->n[0], n3 = m->n[3];
+    const int chunks = ceil_div(B, cols);
+    const size_t esz = x_is_u8 ? 1 : sizeof(float);
+    const MemKind yk = classify(y);
+    const bool y_on_host = yk != kDevice && yk != kManaged;
+    // the staging buffers may still be read by the step before this one
+    BLA_CUDA(cudaEventRecord(m->ev_free, s));
+    BLA_CUDA(cudaStreamWaitEvent(cp, m->ev_free, 0));
+    for (int i = 0; i < chunks; ++i) {
+        const int b0 = i * cols, bc = std::min(cols, B - b0);
+        void* dst = x_is_u8 ? (void*)(m->x_u8 + (size_t)n0 * b0) : (void*)(m->x + (size_t)n0 * b0);
+        BLA_CUDA(cudaMemcpy2DAsync(dst, bc * esz, (const char*)x + b0 * esz, B * esz, bc * esz, n0, cudaMemcpyDefault, cp));
+        BLA_CUDA(cudaMemcpy2DAsync(m->y + (size_t)n3 * b0, bc * sizeof(float), y + b0, B * sizeof(float), bc * sizeof(float), n3,
+                                   cudaMemcpyDefault, cp));
+        BLA_CUDA(cudaEventRecord(m->ev_chunk[i], cp));
+        rt().h2d_bytes += (size_t)n0 * bc * esz;
+        if (y_on_host) rt().h2d_bytes += (size_t)n3 * bc * sizeof(float);
+    }
+    for (int i = 0; i < chunks; ++i) {
+        const int b0 = i * cols, bc = std::min(cols, B - b0);
+        BLA_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[i], 0));
+        bla_mlp v = *m;   // the same network looking at chunk i's slice of every per-batch buffer
+        v.x += (size_t)n0 * b0; v.x_u8 += (size_t)n0 * b0; v.y += (size_t)n3 * b0;
+        v.a1 += (size_t)m->n[1] * b0; v.dz1 += (size_t)m->n[1] * b0;
+        v.a2 += (size_t)m->n[2] * b0; v.dz2 += (size_t)m->n[2] * b0;
+        v.z3 += (size_t)n3 * b0;
+        if (i > 0) v.grads = m->grads_chunk;
+        if (x_is_u8) k_u8_to_float(v.x, v.x_u8, (size_t)n0 * bc, 1.0f, s);
+        backprop(&v, v.x, x_scale, v.y, bc, Bg, c0 + b0, false);
+        if (i > 0) k_axpy(m->grads, m->grads_chunk, 1.0f, m->nparams, s);
+    }
+    if (comm_active()) {
+        cudaStream_t cs = comm_stream();
+        BLA_CUDA(cudaEventRecord(m->ev_rest, s));
+        BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
+        comm_allreduce_f32_on(m->grads, m->nparams, cs);
+        BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
+        BLA_CUDA(cudaStreamWaitEvent(s, m->ev_comm, 0));
+    }
     k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, s);
     if (stats_host) bla_mlp_read_stats(m, stats_host);
 }
@@ -533,6 +619,12 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_l1, cudaEventDisableTiming));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_rest, cudaEventDisableTiming));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_comm, cudaEventDisableTiming));
+    m->chunk_cols = -1;
+    if (const char* e = getenv("BLA_MLP_CHUNK_COLS")) m->chunk_cols = atoi(e);
+    m->grads_chunk = (float*)pool_alloc(kDevice, off * sizeof(float));
+    BLA_CUDA(cudaStreamCreateWithFlags(&m->copy, cudaStreamNonBlocking));
+    BLA_CUDA(cudaEventCreateWithFlags(&m->ev_free, cudaEventDisableTiming));
+    for (cudaEvent_t& e : m->ev_chunk) BLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     m->head_ctas = rt().num_sms * 4;
     m->head_partial = (float*)pool_alloc(kDevice, (size_t)(m->head_ctas + 1) * kMaxClasses * 256 * sizeof(float));
     return m;
@@ -541,8 +633,11 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
 void bla_mlp_destroy(bla_mlp* m) {
     if (!m) return;
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
-    void* bufs[] = {m->params, m->grads, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
+    BLA_CUDA(cudaStreamSynchronize(m->copy));
+    void* bufs[] = {m->params, m->grads, m->grads_chunk, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
     for (void* b : bufs) pool_free(b);
+    cudaStreamDestroy(m->copy); cudaEventDestroy(m->ev_free);
+    for (cudaEvent_t e : m->ev_chunk) cudaEventDestroy(e);
     cudaStreamDestroy(m->side); cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join);
     cudaEventDestroy(m->ev_l1); cudaEventDestroy(m->ev_rest); cudaEventDestroy(m->ev_comm);
     free(m);
@@ -624,10 +719,16 @@ void bla_mlp_read_stats(bla_mlp* m, double* stats_host) {
 void bla_mlp_train_step(bla_mlp* m, const float* x, const float* y, int batch, int global_batch, int col_offset, float lr_mult,
                         double* stats_host) {
     cudaStream_t s = rt().stream;
+    if (const int cols = host_chunk_cols(m, batch, classify(x), sizeof(float))) {
+        step_chunked(m, x, false, y, cols, 1 / 255.0F, batch, global_batch, col_offset, lr_mult, stats_host);
+        return;
+    }
     const float* dx = resident(x, m->x, (size_t)m->n[0] * batch, s);
     const float* dy = resident(y, m->y, (size_t)m->n[3] * batch, s);
     step(m, dx, 1 / 255.0F, dy, batch, global_batch, col_offset, lr_mult, stats_host);
 }
+
+void bla_mlp_set_host_chunking(bla_mlp* m, int chunk_cols) { m->chunk_cols = chunk_cols; }
 
 void bla_mlp_train_step_u8(bla_mlp* m, const unsigned char* x_u8, const float* y, int batch, int global_batch, int col_offset,
                            float lr_mult, double* stats_host) {
@@ -635,6 +736,10 @@ void bla_mlp_train_step_u8(bla_mlp* m, const unsigned char* x_u8, const float* y
     const size_t n = (size_t)m->n[0] * batch;
     const unsigned char* src = x_u8;
     MemKind k = classify(x_u8);
+    if (const int cols = host_chunk_cols(m, batch, k, 1)) {
+        step_chunked(m, x_u8, true, y, cols, 1 / 255.0F, batch, global_batch, col_offset, lr_mult, stats_host);
+        return;
+    }
     if (k != kDevice && k != kManaged) {
         BLA_CUDA(cudaMemcpyAsync(m->x_u8, x_u8, n, cudaMemcpyHostToDevice, s));
         rt().h2d_bytes += n;

@@ -166,6 +166,12 @@ void bla_mlp_train_step(bla_mlp* net, const float* x, const float* y, int batch,
 /* Same step from byte pixels (MNIST's native storage): x_u8 [inputs x batch]. */
 void bla_mlp_train_step_u8(bla_mlp* net, const unsigned char* x_u8, const float* y, int batch, int global_batch,
                            int col_offset, float lr_mult, double* stats_host);
+/* Host batches (either step above) are taken in column chunks so that chunk i+1 crosses PCIe while chunk i is trained; the
+ * chunks' gradients are summed before the one update, i.e. the same step with a different summation order.  chunk_cols < 0
+ * (default, or env BLA_MLP_CHUNK_COLS): automatic -- pinned host batches of >= 16384 columns in ~6144-column chunks (byte
+ * batches of >= 32768 columns in two halves: the strided copies need long rows); 0: off; > 0: this chunk width
+ * (rounded up to 64 columns, at most 16 chunks) for any host batch. */
+void bla_mlp_set_host_chunking(bla_mlp* net, int chunk_cols);
 /* Forward only (model/mnist_nn.c:446-463, `run`): probs [classes x batch] out. */
 void bla_mlp_forward(bla_mlp* net, const float* x, int batch, float* probs);
 /* {loss_sum, num_correct} accumulated on the device since the last call (then cleared).  With an active communicator this is a

@@ -582,6 +582,66 @@ def test_mlp_full_size_step_is_the_sum_of_its_column_shards(bla, path):
         b.bla_set_gemm_path(b.GEMM_FP32)
 
 
+@pytest.mark.parametrize("path", ["fp32", "auto"])
+def test_mlp_host_batch_in_chunks_equals_one_piece(bla, path):
+    """Host batches cross PCIe in column chunks while the chunk before is trained (bla_mlp_set_host_chunking): the step must be the
+    one-piece step up to summation order -- float and byte pixels, ragged last chunk, forced chunks on pageable memory and the
+    automatic rule on a pinned batch, two steps in a row (the staging buffers are reused while the step before may still read them)."""
+    b = bla
+    b.bla_set_gemm_path(b.GEMM_FP32 if path == "fp32" else b.GEMM_AUTO)
+    tol = 2e-5 if path == "fp32" else 1e-4
+    dims = (C.c_int * 4)(784, 256, 128, 10)
+    shapes = ((256, 784), (256,), (128, 256), (128,), (10, 128), (10,))
+    rng = np.random.default_rng(77)
+    p0 = [f32(rng.uniform(-0.08, 0.08, s)) for s in shapes]
+
+    def run(B, xptr, yptr, chunk, u8):
+        net = b.bla_mlp_create(dims, B)
+        b.bla_mlp_set_params(net, *[ptr(p) for p in p0])
+        b.bla_mlp_set_host_chunking(net, chunk)
+        stats = np.zeros(2)
+        fn = b.bla_mlp_train_step_u8 if u8 else b.bla_mlp_train_step
+        fn(net, xptr, yptr, B, B, 0, 0.002, None)
+        fn(net, xptr, yptr, B, B, 0, 0.002, ptr(stats))      # totals of both steps
+        got = [np.empty_like(p) for p in p0]
+        b.bla_mlp_get_params(net, *[ptr(g) for g in got])
+        b.bla_mlp_destroy(net)
+        return [g.astype(np.float64) - p.astype(np.float64) for g, p in zip(got, p0)], stats
+
+    def compare(one, many):
+        assert abs(int(one[1][1]) - int(many[1][1])) <= 2          # a near-tie may flip under another summation order
+        assert abs(one[1][0] - many[1][0]) <= 1e-4 * abs(one[1][0])
+        for i, (d1, d2) in enumerate(zip(one[0], many[0])):
+            assert rel_err(d2, d1) <= tol, (i, rel_err(d2, d1))
+
+    try:
+        B = 3000
+        X8 = rng.integers(0, 256, (784, B)).astype(np.uint8)
+        X = X8.astype(np.float32)
+        labels = rng.integers(0, 10, B)
+        Y = np.zeros((10, B), np.float32); Y[labels, np.arange(B)] = 1
+        one = run(B, ptr(X), ptr(Y), 0, False)
+        compare(one, run(B, ptr(X), ptr(Y), 1024, False))      # 1024 + 1024 + 952
+        compare(one, run(B, ptr(X), ptr(Y), 200, False))       # 256-column chunks, 12 of them
+        compare(one, run(B, ptr(X8), ptr(Y), 0, True))
+        compare(one, run(B, ptr(X8), ptr(Y), 1024, True))
+        # automatic rule: pinned, >= 16384 columns
+        B = 20000
+        hx = b.bla_malloc_pinned(784 * B * 4); hy = b.bla_malloc_pinned(10 * B * 4)
+        hx_np = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_float)), shape=(784, B))
+        hy_np = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(10, B))
+        hx_np[:] = rng.integers(0, 256, (784, B)).astype(np.float32)
+        labels = rng.integers(0, 10, B)
+        hy_np[:] = 0; hy_np[labels, np.arange(B)] = 1
+        h0 = b.bla_h2d_bytes()
+        many = run(B, hx, hy, -1, False)
+        assert b.bla_h2d_bytes() - h0 >= 2 * (784 + 10) * B * 4
+        compare(run(B, hx, hy, 0, False), many)
+        b.bla_free(hx); b.bla_free(hy)
+    finally:
+        b.bla_set_gemm_path(b.GEMM_FP32)
+
+
 # ------------------------------------------------------------------------------------------------
 # batched, device-resident implicit-GEMM conv2d (include/bla.h) vs the f64 oracle, image by image
 # ------------------------------------------------------------------------------------------------
