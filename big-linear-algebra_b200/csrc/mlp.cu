@@ -51,8 +51,9 @@ struct bla_mlp {
     static constexpr int kMaxChunks = 16;
     int chunk_cols;                        // < 0: automatic (pinned host batches only), 0: off, > 0: forced chunk width
     float* grads_chunk;                    // gradient of chunks 1.. before it is added to `grads`
+    float* y_whole;                        // the labels cross in ONE copy ahead of the chunks and are cut up on the device
     cudaStream_t copy;
-    cudaEvent_t ev_chunk[kMaxChunks], ev_free;
+    cudaEvent_t ev_chunk[kMaxChunks], ev_free, ev_y;
 };
 
 namespace {
@@ -546,18 +547,26 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
     // the staging buffers may still be read by the step before this one
     BLA_CUDA(cudaEventRecord(m->ev_free, s));
     BLA_CUDA(cudaStreamWaitEvent(cp, m->ev_free, 0));
+    // labels first, in one piece: a second small strided copy per chunk costs the PCIe queue ~15 us each time
+    const float* y_src = y;
+    if (y_on_host) {
+        BLA_CUDA(cudaMemcpyAsync(m->y_whole, y, (size_t)n3 * B * sizeof(float), cudaMemcpyHostToDevice, cp));
+        BLA_CUDA(cudaEventRecord(m->ev_y, cp));
+        BLA_CUDA(cudaStreamWaitEvent(s, m->ev_y, 0));
+        rt().h2d_bytes += (size_t)n3 * B * sizeof(float);
+        y_src = m->y_whole;
+    }
     for (int i = 0; i < chunks; ++i) {
         const int b0 = i * cols, bc = std::min(cols, B - b0);
         void* dst = x_is_u8 ? (void*)(m->x_u8 + (size_t)n0 * b0) : (void*)(m->x + (size_t)n0 * b0);
         BLA_CUDA(cudaMemcpy2DAsync(dst, bc * esz, (const char*)x + b0 * esz, B * esz, bc * esz, n0, cudaMemcpyDefault, cp));
-        BLA_CUDA(cudaMemcpy2DAsync(m->y + (size_t)n3 * b0, bc * sizeof(float), y + b0, B * sizeof(float), bc * sizeof(float), n3,
-                                   cudaMemcpyDefault, cp));
         BLA_CUDA(cudaEventRecord(m->ev_chunk[i], cp));
         rt().h2d_bytes += (size_t)n0 * bc * esz;
-        if (y_on_host) rt().h2d_bytes += (size_t)n3 * bc * sizeof(float);
     }
     for (int i = 0; i < chunks; ++i) {
         const int b0 = i * cols, bc = std::min(cols, B - b0);
+        BLA_CUDA(cudaMemcpy2DAsync(m->y + (size_t)n3 * b0, bc * sizeof(float), y_src + b0, B * sizeof(float), bc * sizeof(float), n3,
+                                   cudaMemcpyDefault, s));
         BLA_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[i], 0));
         bla_mlp v = *m;   // the same network looking at chunk i's slice of every per-batch buffer
         v.x += (size_t)n0 * b0; v.x_u8 += (size_t)n0 * b0; v.y += (size_t)n3 * b0;
@@ -622,6 +631,8 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     m->chunk_cols = -1;
     if (const char* e = getenv("BLA_MLP_CHUNK_COLS")) m->chunk_cols = atoi(e);
     m->grads_chunk = (float*)pool_alloc(kDevice, off * sizeof(float));
+    m->y_whole = (float*)pool_alloc(kDevice, dims[3] * B * sizeof(float));
+    BLA_CUDA(cudaEventCreateWithFlags(&m->ev_y, cudaEventDisableTiming));
     BLA_CUDA(cudaStreamCreateWithFlags(&m->copy, cudaStreamNonBlocking));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_free, cudaEventDisableTiming));
     for (cudaEvent_t& e : m->ev_chunk) BLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -634,9 +645,9 @@ void bla_mlp_destroy(bla_mlp* m) {
     if (!m) return;
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
     BLA_CUDA(cudaStreamSynchronize(m->copy));
-    void* bufs[] = {m->params, m->grads, m->grads_chunk, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
+    void* bufs[] = {m->params, m->grads, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
     for (void* b : bufs) pool_free(b);
-    cudaStreamDestroy(m->copy); cudaEventDestroy(m->ev_free);
+    cudaStreamDestroy(m->copy); cudaEventDestroy(m->ev_free); cudaEventDestroy(m->ev_y);
     for (cudaEvent_t e : m->ev_chunk) cudaEventDestroy(e);
     cudaStreamDestroy(m->side); cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join);
     cudaEventDestroy(m->ev_l1); cudaEventDestroy(m->ev_rest); cudaEventDestroy(m->ev_comm);
