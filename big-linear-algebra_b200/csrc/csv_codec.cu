@@ -12,15 +12,22 @@
 // is not empty, '\r' is skipped, characters after the last terminator are dropped, *num_values is the number of commas.
 // Device-resident tensors are staged through pinned memory (bla_csv_save_device / bla_csv_load_device).
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <unistd.h>
 
 #include "../../include/bla.h"
 #include "../../include/lib/csv.h"
@@ -48,12 +55,23 @@ void parallel_for(int n, Fn fn) {
 }
 
 // ---- "%f," ----------------------------------------------------------------------------------------------------------
+// "00".."99"
+struct DigitPairs {
+    char d[200];
+    constexpr DigitPairs() : d() {
+        for (int i = 0; i < 100; ++i) { d[2 * i] = (char)('0' + i / 10); d[2 * i + 1] = (char)('0' + i % 10); }
+    }
+};
+constexpr DigitPairs kPairs{};
+
 inline char* put_u64(char* p, uint64_t v) {
+    if (v < 10) { *p++ = (char)('0' + v); return p; }   // weights: almost always "0"
     char tmp[20];
-    int n = 0;
-    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) *p++ = tmp[--n];
-    return p;
+    int n = 20;
+    while (v >= 100) { n -= 2; memcpy(tmp + n, kPairs.d + 2 * (v % 100), 2); v /= 100; }
+    if (v >= 10) { n -= 2; memcpy(tmp + n, kPairs.d + 2 * v, 2); } else tmp[--n] = (char)('0' + v);
+    memcpy(p, tmp + n, 20 - n);
+    return p + (20 - n);
 }
 
 // appends printf("%f,", (double)x) to p (at most 48 bytes for |x| < 2^63; larger magnitudes, inf and nan go through snprintf)
@@ -87,21 +105,33 @@ inline char* format_value(char* p, float x) {
     p = put_u64(p, N / 1000000ull);
     uint32_t frac = (uint32_t)(N % 1000000ull);
     *p++ = '.';
-    for (int d = 5; d >= 0; --d) { p[d] = (char)('0' + frac % 10); frac /= 10; }
-    p += 6;
-    *p++ = ',';
-    return p;
+    memcpy(p + 4, kPairs.d + 2 * (frac % 100), 2); frac /= 100;
+    memcpy(p + 2, kPairs.d + 2 * (frac % 100), 2); frac /= 100;
+    memcpy(p, kPairs.d + 2 * frac, 2);
+    p[6] = ',';
+    return p + 7;
 }
 
-void format_rows(const float* data, int cols, size_t row0, size_t row1, std::vector<char>& out) {
-    out.resize((row1 - row0) * ((size_t)cols * 50 + 1) + 64);
-    char* p = out.data();
+// text of rows [row0, row1); the buffer is sized for the worst case but never initialised, so only the pages the text
+// reaches are ever touched
+struct TextPart {
+    std::unique_ptr<char[]> buf;
+    size_t size = 0;
+};
+
+void format_rows(const float* data, int cols, size_t row0, size_t row1, TextPart& out) {
+    out.buf.reset(new char[(row1 - row0) * ((size_t)cols * 50 + 1) + 64]);
+    char* p = out.buf.get();
     for (size_t r = row0; r < row1; ++r) {
         const float* v = data + r * cols;
         for (int c = 0; c < cols; ++c) p = format_value(p, v[c]);
         *p++ = '\n';
     }
-    out.resize((size_t)(p - out.data()));
+    out.size = (size_t)(p - out.buf.get());
+}
+
+int format_workers(size_t rows, int cols) {
+    return std::max(1, std::min(worker_count(rows * (size_t)cols * 10), (int)std::max<size_t>(rows, 1)));
 }
 
 // ---- atof ------------------------------------------------------------------------------------------------------------
@@ -198,16 +228,43 @@ std::vector<char> slurp(FILE* f) {
     return buf;
 }
 
+// The rows are cut into more parts than workers; the workers format parts in order while this thread writes every part as soon
+// as it is ready and frees it, so formatting hides behind the file system (which takes ~3x longer) and at most a few parts
+// are in memory at once.  Plain write(): also right for a pipe or /dev/stdout.
 void write_text(const char* filepath, const float* data, int cols, size_t rows) {
-    FILE* f = fopen(filepath, "w");
-    if (!f) bla::die("bla: cannot open CSV file %s for writing, exiting", filepath);
-    const int T = std::max(1, std::min(worker_count(rows * (size_t)cols * 10), (int)std::max<size_t>(rows, 1)));
-    std::vector<std::vector<char>> parts(T);
-    parallel_for(T, [&](int i) { format_rows(data, cols, rows * i / T, rows * (i + 1) / T, parts[i]); });
-    for (auto& p : parts)
-        if (!p.empty() && fwrite(p.data(), 1, p.size(), f) != p.size()) bla::die("bla: short write to %s, exiting", filepath);
-    fflush(f);
-    fclose(f);
+    const int fd = open(filepath, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) bla::die("bla: cannot open CSV file %s for writing, exiting", filepath);
+    const int T = format_workers(rows, cols);
+    const int P = T == 1 ? 1 : (int)std::min<size_t>(rows, (size_t)T * 4);
+    std::vector<TextPart> parts(P);
+    std::vector<char> ready(P, 0);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<int> next{0};
+    auto work = [&] {
+        for (int k; (k = next.fetch_add(1)) < P;) {
+            format_rows(data, cols, rows * k / P, rows * (k + 1) / P, parts[k]);
+            { std::lock_guard<std::mutex> g(mu); ready[k] = 1; }
+            cv.notify_one();
+        }
+    };
+    std::vector<std::thread> th;
+    if (T == 1) work();
+    else for (int i = 0; i < T; ++i) th.emplace_back(work);
+    bool ok = true;
+    for (int k = 0; k < P; ++k) {
+        { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return ready[k] != 0; }); }
+        const char* q = parts[k].buf.get();
+        size_t left = ok ? parts[k].size : 0;
+        while (left) {
+            const ssize_t w = write(fd, q, left);
+            if (w <= 0) { ok = false; break; }
+            q += w; left -= (size_t)w;
+        }
+        parts[k].buf.reset();
+    }
+    for (auto& t : th) t.join();
+    if (close(fd) != 0 || !ok) bla::die("bla: short write to %s, exiting", filepath);
 }
 
 }  // namespace
@@ -255,16 +312,13 @@ size_t bla_csv_parse(const char* text, size_t len, float** values_out) {
 }
 
 size_t bla_csv_format(const float* data, int cols, size_t rows, char* out, size_t cap) {
-    const int T = std::max(1, std::min(worker_count(rows * (size_t)cols * 10), (int)std::max<size_t>(rows, 1)));
-    std::vector<std::vector<char>> parts(T);
+    const int T = format_workers(rows, cols);
+    std::vector<TextPart> parts(T);
     parallel_for(T, [&](int i) { format_rows(data, cols, rows * i / T, rows * (i + 1) / T, parts[i]); });
-    size_t total = 0;
-    for (auto& p : parts) total += p.size();
-    if (out && total <= cap) {
-        char* q = out;
-        for (auto& p : parts) { memcpy(q, p.data(), p.size()); q += p.size(); }
-    }
-    return total;
+    std::vector<size_t> at(T + 1, 0);
+    for (int i = 0; i < T; ++i) at[i + 1] = at[i] + parts[i].size;
+    if (out && at[T] <= cap) parallel_for(T, [&](int i) { memcpy(out + at[i], parts[i].buf.get(), parts[i].size); });
+    return at[T];
 }
 
 // a [rows x cols] tensor in any memory (device, managed, host) -> the reference's CSV
