@@ -27,6 +27,7 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "../../include/bla.h"
@@ -135,8 +136,36 @@ int format_workers(size_t rows, int cols) {
 }
 
 // ---- atof ------------------------------------------------------------------------------------------------------------
+// What "%f" writes -- [-]digits[.digits], at most 15 digits in all -- read in one walk.  The digits are an integer below 2^53
+// and the power of ten is exact, so one IEEE division gives the correctly rounded double strtod would return.  Returns the
+// first character not consumed; *ok is false when the text walked is not of that form (the caller then takes the general path).
+inline const char* walk_fixed(const char* q, const char* e, double* v, bool* ok) {
+    static const double kPow10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+    const bool neg = q < e && *q == '-';
+    q += neg;
+    uint64_t m = 0;
+    const char* first = q;
+    for (; q < e && (unsigned)(*q - '0') < 10u; ++q) m = m * 10 + (unsigned)(*q - '0');
+    int digits = (int)(q - first), frac = 0;
+    if (q < e && *q == '.') {
+        const char* dot = ++q;
+        for (; q < e && (unsigned)(*q - '0') < 10u; ++q) m = m * 10 + (unsigned)(*q - '0');
+        frac = (int)(q - dot);
+        digits += frac;
+    }
+    *ok = digits > 0 && digits <= 15;
+    const double x = (double)m / kPow10[frac & 15];
+    *v = neg ? -x : x;
+    return q;
+}
+
 inline float parse_token(const char* b, const char* e) {
     // the reference: atof on the field (leading blanks skipped, trailing junk ignored, "" -> 0)
+    {
+        double v;
+        bool ok;
+        if (walk_fixed(b, e, &v, &ok) == e && ok) return (float)v;
+    }
     const char* q = b;
     bool plain = true;
     if (q < e && *q == '+') { ++q; plain = !(q < e && (*q == '+' || *q == '-')); }   // strtod("+-1") is 0, not -1
@@ -154,32 +183,37 @@ inline float parse_token(const char* b, const char* e) {
 
 struct Scan { size_t values = 0, commas = 0; };
 
-// Walks [b, e) with the reference's state machine.  `pending` = the field open at b is non-empty (chunk boundaries are placed
-// right after a terminator, so it is false there).  With out != nullptr the values are stored.
+// Walks [b, e) with the reference's state machine, field by field, storing the values in out (room for e - b of them: a
+// value needs at least its terminator).  Chunk boundaries are placed right after a terminator, so b starts a field.  A field
+// written by "%f" is read and delimited in the same walk; anything else (empty, exponent, blanks, '\r', text) is delimited
+// first and goes through parse_token.
 Scan scan(const char* b, const char* e, float* out) {
     Scan s;
-    const char* tok = b;        // start of the current field
-    bool has_cr = false;
-    for (const char* p = b; p < e; ++p) {
-        const char c = *p;
-        if (c == ',' || c == '\n') {
-            bool nonempty = p > tok;
-            if (has_cr) {       // rare: strip the '\r's into a scratch copy
-                char tmp[1100];
-                size_t n = 0;
-                for (const char* q = tok; q < p && n < sizeof(tmp) - 1; ++q) if (*q != '\r') tmp[n++] = *q;
-                nonempty = n > 0;
-                if (c == ',' || nonempty) { if (out) out[s.values] = parse_token(tmp, tmp + n); ++s.values; }
-            } else if (c == ',' || nonempty) {
-                if (out) out[s.values] = parse_token(tok, p);
-                ++s.values;
-            }
-            if (c == ',') ++s.commas;
-            tok = p + 1;
-            has_cr = false;
-        } else if (c == '\r') {
-            has_cr = true;
+    const char* tok = b;
+    while (tok < e) {
+        double v;
+        bool ok;
+        const char* q = walk_fixed(tok, e, &v, &ok);
+        if (ok && q < e && (*q == ',' || *q == '\n')) {
+            out[s.values++] = (float)v;
+            s.commas += *q == ',';
+            tok = q + 1;
+            continue;
         }
+        const char* p = q;
+        while (p < e && *p != ',' && *p != '\n') ++p;
+        if (p == e) break;                        // no terminator: the reference drops what follows the last one
+        const char c = *p;
+        if (memchr(tok, '\r', (size_t)(p - tok))) {   // rare: strip the '\r's into a scratch copy
+            char tmp[1100];
+            size_t n = 0;
+            for (const char* r = tok; r < p && n < sizeof(tmp) - 1; ++r) if (*r != '\r') tmp[n++] = *r;
+            if (c == ',' || n > 0) out[s.values++] = parse_token(tmp, tmp + n);
+        } else if (c == ',' || p > tok) {
+            out[s.values++] = parse_token(tok, p);
+        }
+        s.commas += c == ',';
+        tok = p + 1;
     }
     return s;
 }
@@ -194,38 +228,74 @@ float* parse_buffer(const char* text, size_t len, int* num_values, size_t* count
         cut[i] = std::min(len, p + 1);
     }
     for (int i = 1; i <= T; ++i) cut[i] = std::max(cut[i], cut[i - 1]);
+    // one pass: every worker parses its chunk into a buffer of its own sized for the worst case (never initialised, so only the
+    // pages the values reach are touched); the values are then gathered into one array
     std::vector<Scan> counts(T);
-    parallel_for(T, [&](int i) { counts[i] = scan(text + cut[i], text + cut[i + 1], nullptr); });
+    std::vector<float*> local(T, nullptr);
+    std::vector<char> oom(T, 0);
+    parallel_for(T, [&](int i) {
+        const size_t bytes = cut[i + 1] - cut[i];
+        local[i] = (float*)malloc((bytes + 1) * sizeof(float));
+        if (!local[i]) { oom[i] = 1; return; }
+        counts[i] = scan(text + cut[i], text + cut[i + 1], local[i]);
+    });
     size_t total = 0, commas = 0;
     std::vector<size_t> first(T);
     for (int i = 0; i < T; ++i) { first[i] = total; total += counts[i].values; commas += counts[i].commas; }
     // the reference sizes its buffer by the comma count (lib/csv.c:29-35) and overflows it when rows lack the trailing comma
     // (SURVEY D8); here the buffer always holds every value
-    float* out = (float*)malloc(std::max<size_t>(std::max(total, commas), 1) * sizeof(float));
-    if (!out) bla::die("bla: out of memory parsing a CSV of %zu bytes, exiting", len);
-    parallel_for(T, [&](int i) { scan(text + cut[i], text + cut[i + 1], out + first[i]); });
+    float* out = T == 1 && local[0] ? local[0] : (float*)malloc(std::max<size_t>(std::max(total, commas), 1) * sizeof(float));
+    if (!out || std::find(oom.begin(), oom.end(), 1) != oom.end()) bla::die("bla: out of memory parsing a CSV of %zu bytes, exiting", len);
+    if (out != local[0]) {
+        parallel_for(T, [&](int i) { memcpy(out + first[i], local[i], counts[i].values * sizeof(float)); free(local[i]); });
+    }
     if (num_values) *num_values = (int)commas;
     if (count_out) *count_out = total;
     return out;
 }
 
-std::vector<char> slurp(FILE* f) {
-    std::vector<char> buf;
+// The whole file as one buffer (malloc'd, uninitialised until read).  A regular file is read by all workers at once, each its
+// slice with pread (page-cache copies scale with the cores); anything else (a pipe) is read to its end through the FILE.
+struct Text {
+    char* data = nullptr;
+    size_t size = 0;
+    ~Text() { free(data); }
+};
+
+void slurp(FILE* f, Text& t) {
     rewind(f);
-    if (fseek(f, 0, SEEK_END) == 0) {
-        long n = ftell(f);
-        rewind(f);
-        if (n > 0) {
-            buf.resize((size_t)n);
-            size_t got = fread(buf.data(), 1, buf.size(), f);
-            buf.resize(got);
-            return buf;
+    struct stat st;
+    const int fd = fileno(f);
+    if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+        const size_t n = (size_t)st.st_size;
+        t.data = (char*)malloc(n);
+        if (!t.data) bla::die("bla: out of memory reading a CSV of %zu bytes, exiting", n);
+        const int T = worker_count(n);
+        std::vector<size_t> got(T, 0);
+        parallel_for(T, [&](int i) {
+            size_t at = n / T * i;
+            const size_t end = i + 1 == T ? n : n / T * (i + 1);
+            while (at < end) {
+                const ssize_t r = pread(fd, t.data + at, end - at, (off_t)at);
+                if (r <= 0) break;
+                at += (size_t)r;
+                got[i] += (size_t)r;
+            }
+        });
+        // a file cut short under the reader: keep the leading part that did arrive
+        for (int i = 0; i < T; ++i) {
+            t.size += got[i];
+            if (got[i] != (i + 1 == T ? n : n / T * (i + 1)) - n / T * i) break;
         }
+        return;
     }
-    char tmp[1 << 16];
-    size_t got;
-    while ((got = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
-    return buf;
+    size_t cap = 1 << 16, got;
+    t.data = (char*)malloc(cap);
+    while (t.data && (got = fread(t.data + t.size, 1, cap - t.size, f)) > 0) {
+        t.size += got;
+        if (t.size == cap) t.data = (char*)realloc(t.data, cap *= 2);
+    }
+    if (!t.data) bla::die("bla: out of memory reading a CSV, exiting");
 }
 
 // The rows are cut into more parts than workers; the workers format parts in order while this thread writes every part as soon
@@ -280,9 +350,10 @@ float* read_csv_contents(const char* filepath) {
 
 // lib/csv.c:28-54.  Side-effect (as the reference): closes f.  The result is malloc'd: callers free() it or hand it to make_matrix.
 float* read_csv_contents_file(FILE* f, int* num_values) {
-    std::vector<char> buf = slurp(f);
+    Text text;
+    slurp(f, text);
     fclose(f);
-    return parse_buffer(buf.data(), buf.size(), num_values, nullptr);
+    return parse_buffer(text.data, text.size, num_values, nullptr);
 }
 
 // lib/csv.c:56-67
@@ -343,10 +414,11 @@ void bla_csv_load(const char* filepath, float* dst, size_t count) {
     using namespace bla;
     FILE* f = fopen(filepath, "r");
     if (!f) die("bla: cannot open CSV file %s, exiting", filepath);
-    std::vector<char> buf = slurp(f);
+    Text text;
+    slurp(f, text);
     fclose(f);
     size_t n = 0;
-    float* v = parse_buffer(buf.data(), buf.size(), nullptr, &n);
+    float* v = parse_buffer(text.data, text.size, nullptr, &n);
     if (n < count) die("bla: CSV file %s holds %zu values, %zu expected, exiting", filepath, n, count);
     if (classify(dst) == kDevice) {
         float* pin = (float*)pool_alloc(kPinned, count * sizeof(float));
