@@ -123,3 +123,27 @@ def test_large_text_parallel_parse_and_round_trip(b):
     want = np.array([np.float32(float("%f" % float(x))) for x in v.ravel()], np.float32)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.abs(got.astype(np.float64) - v.ravel()).max() <= 5e-7 + 2.0 ** -20          # six decimals + one float32 ulp at |x| < 16
+
+
+def test_fixed_notation_fields_match_strtod(b):
+    """The reader's one-walk path for [-]digits[.digits] (<= 15 digits: an exact integer over an exact power of ten, one IEEE
+    division) and its hand-over to the general path (16+ digits, a lone sign or dot, signs the walk does not take) give the
+    float atof-then-cast gives -- Python's float() is the same correctly rounded strtod."""
+    rng = np.random.default_rng(15)
+    toks = []
+    for _ in range(40000):
+        nd = int(rng.integers(1, 19))                                   # 1..18 digits: both sides of the 15-digit limit
+        digits = "".join(rng.choice(list("0123456789"), nd))
+        cut = int(rng.integers(0, nd + 1))
+        t = digits[:cut] + ("." if cut < nd or rng.random() < 0.2 else "") + digits[cut:]
+        toks.append(("-" if rng.random() < 0.4 else "") + t)
+    toks += ["0", "-0", "-0.0", "0.000000", "-0.000000", "5.", "-.5", ".5", "999999999999999", "9999999999999999", "0.999999999999999",
+             "123456789012345.", "1234567.12345678", "4.9999997e-7", "16777217", "0.1", "-0.3", "7.0000005", "33554434.000000"]
+    text = (",".join(toks) + ",\n").encode()
+    out = C.POINTER(C.c_float)()
+    n = b.bla_csv_parse(text, len(text), C.byref(out))
+    assert n == len(toks)
+    got = np.ctypeslib.as_array(out, shape=(n,)).copy()
+    want = np.array([np.float32(float(t)) for t in toks], np.float32)
+    bad = np.nonzero(got.view(np.uint32) != want.view(np.uint32))[0]
+    assert bad.size == 0, [(toks[i], got[i], want[i]) for i in bad[:5]]
