@@ -22,6 +22,7 @@
 #include "../../include/lib/csv.h"
 #include "kernels.h"
 #include "runtime.h"
+#include "take_sampler.h"
 
 namespace bla {
 bool comm_active();   // comm.cu
@@ -32,7 +33,7 @@ struct bla_mnist {
     int n = 0, features = 0;
     float* x = nullptr;                  // device [n][features]
     float* y = nullptr;                  // device [n] labels
-    std::vector<int> tree;               // Fenwick tree over "example i has not been sampled"
+    TakeSampler sampler;                 // get_random_data_take's index rule on a Fenwick tree (take_sampler.h)
     std::vector<char> sampled;           // mnist_csv2.h:11
     int num_sampled = 0;
     int* idx_dev = nullptr;              // staging for a batch's indices
@@ -93,27 +94,10 @@ __global__ void __launch_bounds__(kThreads) cifar_gather_kernel(const unsigned c
     }
 }
 
-void fenwick_reset(bla_mnist* m) {
-    const int n = m->n;
-    m->tree.assign(n + 1, 0);
-    for (int i = 1; i <= n; ++i) {
-        m->tree[i] += 1;
-        const int j = i + (i & -i);
-        if (j <= n) m->tree[j] += m->tree[i];
-    }
+void sampler_reset(bla_mnist* m) {
+    m->sampler.reset_all_unsampled(m->n);
     std::fill(m->sampled.begin(), m->sampled.end(), 0);
     m->num_sampled = 0;
-}
-// index (0-based) of the k-th (1-based) unsampled example
-int fenwick_find(const bla_mnist* m, int k) {
-    int pos = 0, step = 1;
-    while (step * 2 <= m->n) step *= 2;
-    for (; step > 0; step >>= 1)
-        if (pos + step <= m->n && m->tree[pos + step] < k) { pos += step; k -= m->tree[pos]; }
-    return pos;   // 0-based index of the element at 1-based position pos + 1
-}
-void fenwick_clear(bla_mnist* m, int i) {
-    for (int j = i + 1; j <= m->n; j += j & -j) m->tree[j] -= 1;
 }
 
 template <class T>
@@ -137,7 +121,7 @@ bla_mnist* mnist_new(const float* x_sample_major, const float* y, int n, int fea
     BLA_CUDA(cudaStreamSynchronize(s));
     rt().h2d_bytes += (size_t)n * (features + 1) * sizeof(float);
     m->sampled.assign(n, 0);
-    fenwick_reset(m);
+    sampler_reset(m);
     return m;
 }
 
@@ -182,25 +166,11 @@ const float* bla_mnist_y_device(const bla_mnist* m) { return m->y; }
 extern "C" {
 
 // mnist_nn.c:189-190: a new round of SGD
-void bla_mnist_reset(bla_mnist* m) { fenwick_reset(m); }
+void bla_mnist_reset(bla_mnist* m) { sampler_reset(m); }
 
 // get_random_data_take (mnist_csv2.c:41-62) `count` times: same libc rand() stream, same index rule
 void bla_mnist_sample_take(bla_mnist* m, int count, int* indices_out) {
-    for (int k = 0; k < count; ++k) {
-        if (m->num_sampled == m->n) fenwick_reset(m);                                   // :43-46
-        int n = (int)floor((float)(m->n - m->num_sampled) * (float)rand() / (float)RAND_MAX);   // :49
-        // :52-57: the scan stops one past the n-th unsampled element (at 0 when n == 0) and takes whatever sits there
-        int i = 0;
-        if (n > 0) {
-            const int remaining = m->n - m->num_sampled;
-            if (n > remaining) n = remaining;            // rand() == RAND_MAX on the last draws: the reference runs off the end
-            i = fenwick_find(m, n) + 1;
-        }
-        if (i >= m->n) i = m->n - 1;                     // (the reference reads out of bounds there)
-        if (!m->sampled[i]) { m->sampled[i] = 1; fenwick_clear(m, i); }
-        m->num_sampled++;                                // :59 counts the draw even when the example had been taken already
-        indices_out[k] = i;
-    }
+    for (int k = 0; k < count; ++k) indices_out[k] = m->sampler.take(m->sampled.data(), &m->num_sampled);
 }
 
 // the batch matrices of mnist_nn.c:199-217 on the device: x_out [features x count] raw pixel values, y_out [classes x count]

@@ -55,7 +55,9 @@ build_lib() {          # $1 = variant, $2 = with layer.c? (0/1)
 
 mk_tree f64 double 0;          build_lib f64 0
 # the reference's data readers / samplers (lib/mnist_csv2.c, lib/cifar10.c) for the data-pipeline parity tests
-$CC $CFLAGS -shared -Wl,-Bsymbolic -o "$OUT/libref_data.so" "$GEN/f64/lib/mnist_csv2.c" "$GEN/f64/lib/cifar10.c" "$GEN/f64/lib/csv.c" -lm
+$CC $CFLAGS -shared -Wl,-Bsymbolic -o "$OUT/libref_data.so" "$GEN/f64/lib/mnist_csv2.c" "$GEN/f64/lib/cifar10.c" "$GEN/f64/lib/bmp.c" "$GEN/f64/lib/csv.c" -lm
+# lib/mnist_csv.c (mnist_hinge's row reader) apart: its MnistCSV / visualize_digit_data clash with mnist_csv2.c's
+$CC $CFLAGS -shared -Wl,-Bsymbolic -o "$OUT/libref_mnist_csv.so" "$GEN/f64/lib/mnist_csv.c" -lm
 mk_tree f64_convfix double 1;  build_lib f64_convfix 0
 mk_tree f32 float 0;           build_lib f32 1
 mk_tree f32_convfix float 1;   build_lib f32_convfix 1
@@ -97,6 +99,18 @@ if [ -f "$BLA_DIR/libbla.so" ]; then
   # libbla.so's parallel codec (csrc/csv_codec.cu), also underneath the reference's own mnist_csv2.c loader
   $CC $HOSTFLAGS -o "$OUT/bin/bla_main_nocsv"          "$t/model/main.c" -I"$t" $LINK
   $CC $HOSTFLAGS -o "$OUT/bin/bla_mnist_nn_b512_nocsv" "$t/model/mnist_nn_b512.c" "$t/lib/mnist_csv2.c" $LINK
+  # ... and with NO reference object or header under lib/ at all: every lib/*.h is this repo's (include/lib), the host I/O
+  # (csv, mnist_csv2, cifar10, bmp) comes from libbla.so, mnist_hinge's row reader from libbla_mnist_csv.so
+  t2="$GEN/bla_only"
+  mkdir -p "$t2/lib" "$t2/model"
+  for h in "$HERE"/../include/lib/*.h; do ln -s "$h" "$t2/lib/$(basename "$h")"; done
+  for f in "$REF"/model/*.c "$REF"/main.c; do ln -s "$f" "$t2/model/$(basename "$f")"; done
+  cp "$t/model/mnist_nn_b512.c" "$t2/model/mnist_nn_b512.c"
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_only_main"           "$t2/model/main.c" -I"$t2" $LINK
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_only_my_first_model" "$t2/model/my_first_model.c" $LINK
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_only_mnist_hinge"    "$t2/model/mnist_hinge.c" -L"$BLA_DIR" -lbla_mnist_csv $LINK
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_only_mnist_nn_b512"  "$t2/model/mnist_nn_b512.c" $LINK
+  $CC $HOSTFLAGS -o "$OUT/bin/bla_only_cifar_unet"     "$t2/model/cifar_unet.c" $LINK
   # the reference's own U-Net build (double, as shipped) for comparison runs
   $CC $CFLAGS -o "$OUT/bin/ref_cifar_unet_f64" "$GEN/f64/model/cifar_unet.c" "$GEN/f64/lib/matrix.c" "$GEN/f64/lib/csv.c" \
       "$GEN/f64/lib/cifar10.c" "$GEN/f64/lib/bmp.c" "$GEN/f64/lib/conv.c" "$GEN/f64/lib/norm.c" "$GEN/f64/lib/util.c" -lm
