@@ -254,3 +254,25 @@ def test_row_reader_of_the_hinge_model(tmp_path):
     for r, ret in zip(rows, rets):
         assert np.array_equal(r, want) and ret == [0] * 7
     assert len(set(pics)) == 1 and pics[0].count(b"\n") == 31 and b"#" in pics[0] and b":" in pics[0]
+
+
+def test_init_commands_of_the_programs_built_without_reference_objects(tmp_path):
+    """`init` of mnist_nn and mnist_hinge only draws parameters with rand() and writes the checkpoint -- no GPU work -- so the
+    programs built from the unchanged model sources with NO reference file under lib/ (oracle/_ref/bin/bla_only_*) run here
+    and must leave byte-identical checkpoints to the reference's own builds."""
+    import subprocess
+    bins = os.path.join(REF_DIR, "bin")
+    pairs = (("ref_mnist_nn_f64_b512", "bla_only_mnist_nn_b512", "mnist_nn"), ("ref_mnist_hinge_f32", "bla_only_mnist_hinge", "mnist_hinge"))
+    if not all(os.path.exists(os.path.join(bins, b)) for p in pairs for b in p[:2]):
+        pytest.skip("oracle/_ref programs not built")
+    for ref_bin, our_bin, sub in pairs:
+        dirs = []
+        for tag, binary in (("r", ref_bin), ("o", our_bin)):
+            d = tmp_path / f"{sub}_{tag}"
+            (d / "data" / sub).mkdir(parents=True)
+            subprocess.run([os.path.join(bins, binary), "init"], cwd=d, check=True, capture_output=True, timeout=120)
+            dirs.append(d / "data" / sub)
+        names = sorted(os.listdir(dirs[0]))
+        assert names and names == sorted(os.listdir(dirs[1]))
+        for f in names:
+            assert (dirs[0] / f).read_bytes() == (dirs[1] / f).read_bytes(), (sub, f)
