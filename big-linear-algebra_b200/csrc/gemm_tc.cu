@@ -36,7 +36,6 @@ namespace bla {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 16;   // BN = widest tile (TMEM stage); the tile width actually used is p.bn
-constexpr int kMaxStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kSplitWarps = 8;   // 4 warps needed ~700 cycles per 24 KB stage, as long as its MMAs: the split was co-critical
 constexpr int kThreads = 32 * (6 + kSplitWarps);   // TMA, MMA, 4 epilogue, kSplitWarps splitters
@@ -147,9 +146,6 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
 // release/acquire pair compiles to MEMBAR.GPU + CCTL.IVALL per k-block and halved the kernel's speed.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void st_shared_cluster_u32(uint32_t cluster_addr, uint32_t v) {
-    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
     asm volatile(

@@ -58,8 +58,6 @@ struct bla_mlp {
 
 namespace {
 
-constexpr int kThreads = 256;
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -79,13 +79,6 @@ __global__ void __launch_bounds__(kThreads) plane_sum_kernel(const float* __rest
     }
 }
 
-// cifar_unet.c:1032-1042 (_dropout): y = u < rate ? 0 : x with u from the library's counter-based generator
-__global__ void __launch_bounds__(kThreads) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, unsigned long long seed,
-                                                           float rate) {
-    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
-        y[i] = uniform_at(seed, i, 0.f, 1.f) < rate ? 0.f : x[i];
-}
-
 // cifar_unet.c:1074-1086 (_nearest_neighbours, scale 2): out[p][i][j] = in[p][i/2][j/2]
 __global__ void __launch_bounds__(kThreads) upsample2_kernel(const float* __restrict__ in, float* __restrict__ out, size_t planes, int h, int w) {
     const size_t total = planes * (size_t)h * w;   // one thread per INPUT element: writes a 2x2 block
@@ -619,7 +612,6 @@ void forward_node(bla_unet* n, Node& nd, int imgs, bool train, cudaStream_t s) {
     switch (nd.kind) {
     case kInput: break;
     case kRes: {   // cifar_unet.c:1044-1072
-        const size_t eout = (size_t)imgs * nd.C * hw;
         const GnFuse relu_only{1, 0.f, 0ull};
         k_group_norm_fwd(a->out, nd.relu1, nd.var1, nd.mu1, imgs, nd.cin, hw, c.group_size, quirk, s, &relu_only);   // + multi_channel_relu
         // conv_1 + _add_time_embedding (the projection of all blocks was computed up front into nd.td)
@@ -692,10 +684,8 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
     switch (nd.kind) {
     case kInput: break;
     case kRes: {   // cifar_unet.c:1181-1226
-        const size_t eout = (size_t)imgs * nd.C * hw;
         const float* conv2_in = nd.relu2;
         float *t1 = n->s1, *t2 = n->s2;
-        const GnFuse relu_only{1, 0.f, 0ull};
         conv2d_wgrad(conv2_in, nd.gout, G + nd.w2, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c2);
         conv2d_dgrad(nd.gout, P + nd.w2, t1, imgs, nd.C, nd.side, nd.side, nd.C, nd.k, 1, s, n->permuted ? nd.f2 : nullptr);
         // _dropout_mask, multi_channel_relu_ddx and group_norm_ddx in one pass (the masks are regenerated, not stored)
@@ -707,7 +697,6 @@ void backward_node(bla_unet* n, Node& nd, int imgs, cudaStream_t s) {
         conv2d_wgrad(nd.relu1, t2, G + nd.w1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, &nd.c1);
         if (nd.res) conv2d_wgrad(a->out, nd.gout, G + nd.wr, imgs, nd.cin, nd.side, nd.side, nd.C, 1, 1, s, &nd.cr);
         if (!want_din) break;
-        const size_t ein = (size_t)imgs * nd.cin * hw;
         conv2d_dgrad(t2, P + nd.w1, t1, imgs, nd.cin, nd.side, nd.side, nd.C, nd.k, 1, s, n->permuted ? nd.f1 : nullptr);
         // the residual branch's gradient (through the 1x1 conv when the widths differ; t2 is free again) rides in the epilogue
         // of the first group norm's backward kernel instead of a separate add (cifar_unet.c:1206-1220)
