@@ -236,23 +236,27 @@ void bla_mlp_train_epoch(bla_mlp* net, bla_mnist* data, int batch_size, float lr
         const unsigned long long before = rt().launches;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
-        BLA_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-        mnist_gather_launch(data, data->idx_dev, batch_size, xb, yb, 10, s, data->cursor);
-        bla_mlp_train_step(net, xb, yb, batch_size, batch_size, 0, lr_mult, nullptr);
-        cursor_advance_kernel<<<1, 1, 0, s>>>(data->cursor, batch_size);
-        BLA_LAUNCH_CHECK();
-        count_launch();
-        BLA_CUDA(cudaStreamEndCapture(s, &graph));
-        const int per_replay = (int)(rt().launches - before);
-        rt().launches = before;                                                         // nothing ran while capturing
-        BLA_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-        for (; j < full; ++j) {
-            BLA_CUDA(cudaGraphLaunch(exec, s));
-            count_launch(per_replay);
+        // a stream that cannot be captured (the caller handed bla_set_stream the legacy default stream): stay eager
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            mnist_gather_launch(data, data->idx_dev, batch_size, xb, yb, 10, s, data->cursor);
+            bla_mlp_train_step(net, xb, yb, batch_size, batch_size, 0, lr_mult, nullptr);
+            cursor_advance_kernel<<<1, 1, 0, s>>>(data->cursor, batch_size);
+            BLA_LAUNCH_CHECK();
+            count_launch();
+            BLA_CUDA(cudaStreamEndCapture(s, &graph));
+            const int per_replay = (int)(rt().launches - before);
+            rt().launches = before;                                                     // nothing ran while capturing
+            BLA_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+            for (; j < full; ++j) {
+                BLA_CUDA(cudaGraphLaunch(exec, s));
+                count_launch(per_replay);
+            }
+            BLA_CUDA(cudaStreamSynchronize(s));
+            BLA_CUDA(cudaGraphExecDestroy(exec));
+            BLA_CUDA(cudaGraphDestroy(graph));
+        } else {
+            cudaGetLastError();
         }
-        BLA_CUDA(cudaStreamSynchronize(s));
-        BLA_CUDA(cudaGraphExecDestroy(exec));
-        BLA_CUDA(cudaGraphDestroy(graph));
     }
     for (; j < num_batches; ++j) eager_step(j);
     bla_mlp_read_stats(net, stats);
