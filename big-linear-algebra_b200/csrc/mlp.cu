@@ -27,6 +27,9 @@ void comm_group_end();
 cudaStream_t comm_stream();
 void comm_allreduce_f32_on(float* buf, size_t n, cudaStream_t s);
 void comm_allreduce_f64_on(double* buf, size_t n, cudaStream_t s);
+float* comm_peer_window(size_t floats);
+void comm_peer_allreduce_f32(float* dst, size_t offset, size_t n, cudaStream_t s);
+bool comm_peer_failed();
 }  // namespace bla
 
 using namespace bla;
@@ -54,6 +57,13 @@ struct bla_mlp {
     float* y_whole;                        // the labels cross in ONE copy ahead of the chunks and are cut up on the device
     cudaStream_t copy;
     cudaEvent_t ev_chunk[kMaxChunks], ev_free, ev_y;
+    // data parallel over NVLink peer windows (comm.cu, opt-in): the gradient is produced straight into this rank's window, one
+    // half per step, and summed over the ranks' windows into `reduced` by one kernel; `grads` then points into the window
+    float* grads_own;                      // the private gradient buffer `grads` starts as
+    float* window;                         // nullptr: NCCL
+    float* reduced;
+    int parity;
+    bool peer_checked;
 };
 
 namespace {
@@ -405,6 +415,26 @@ void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s, b
     gemm(g, s);
 }
 
+// Where this step's gradient goes: with peer windows, the half of the window the peers are not reading any more.  Collective
+// the first time (the windows are exchanged), so every rank must reach its first data-parallel step.
+void select_grads(bla_mlp* m) {
+    if (!comm_active()) return;
+    if (!m->peer_checked) {
+        m->peer_checked = true;
+        m->window = comm_peer_window(2 * m->nparams);
+        if (m->window) m->reduced = (float*)pool_alloc(kDevice, m->nparams * sizeof(float));
+    }
+    if (!m->window) return;
+    m->grads = m->window + (size_t)m->parity * m->nparams;
+    m->parity ^= 1;
+}
+// sum over ranks of grads[off, off + n): in place through NCCL, or from the windows into `reduced`
+void reduce_grads(bla_mlp* m, size_t off, size_t n, cudaStream_t cs) {
+    if (m->window) comm_peer_allreduce_f32(m->reduced + off, (size_t)(m->grads - m->window) + off, n, cs);
+    else comm_allreduce_f32_on(m->grads + off, n, cs);
+}
+const float* summed_grads(const bla_mlp* m) { return m->window && comm_active() ? m->reduced : m->grads; }
+
 // forward + backward of columns [c0, c0 + B) of a Bg-column batch: gradients into m->grads (all-reduced when `reduce` and a
 // communicator is active), loss / accuracy added to m->stats
 void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, bool reduce) {
@@ -482,7 +512,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
     if (dp) {
         BLA_CUDA(cudaEventRecord(m->ev_l1, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_l1, 0));
-        comm_allreduce_f32_on(m->grads, seg1, cs);
+        reduce_grads(m, 0, seg1, cs);
     }
     wgrad(1, m->dz2, m->a1, 0.f);         // :279-282
     if (skinny) head_wgrad();
@@ -491,7 +521,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
     if (dp) {                             // the rest of the flat buffer + {loss, correct}
         BLA_CUDA(cudaEventRecord(m->ev_rest, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
-        comm_allreduce_f32_on(m->grads + seg1, m->nparams - seg1, cs);
+        reduce_grads(m, seg1, m->nparams - seg1, cs);
         // {loss, correct} are all-reduced where they are READ (bla_mlp_read_stats), not here: they accumulate over steps, and
         // reducing the running totals every step would count the earlier steps once per rank again
         BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
@@ -501,9 +531,10 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
 
 void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, float lr_mult, double* stats_host) {
     if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
+    select_grads(m);
     backprop(m, x, x_scale, y, B, Bg, c0, true);
     // clip_gradient is a no-op (threshold INFINITY, :13,:296-301); scale by -lr and add  :303-315
-    k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, rt().stream);
+    k_axpy(m->params, summed_grads(m), -(float)lr_mult, m->nparams, rt().stream);
     if (stats_host) bla_mlp_read_stats(m, stats_host);
 }
 
@@ -539,6 +570,7 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
     cudaStream_t s = rt().stream, cp = m->copy;
     const int n0 = m->n[0], n3 = m->n[3];
     const int chunks = ceil_div(B, cols);
+    select_grads(m);
     const size_t esz = x_is_u8 ? 1 : sizeof(float);
     const MemKind yk = classify(y);
     const bool y_on_host = yk != kDevice && yk != kManaged;
@@ -580,11 +612,11 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
         cudaStream_t cs = comm_stream();
         BLA_CUDA(cudaEventRecord(m->ev_rest, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
-        comm_allreduce_f32_on(m->grads, m->nparams, cs);
+        reduce_grads(m, 0, m->nparams, cs);
         BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
         BLA_CUDA(cudaStreamWaitEvent(s, m->ev_comm, 0));
     }
-    k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, s);
+    k_axpy(m->params, summed_grads(m), -(float)lr_mult, m->nparams, s);
     if (stats_host) bla_mlp_read_stats(m, stats_host);
 }
 
@@ -607,7 +639,7 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     m->nparams = off;
     const size_t B = (size_t)max_batch;
     m->params = (float*)pool_alloc(kDevice, off * sizeof(float));
-    m->grads = (float*)pool_alloc(kDevice, off * sizeof(float));
+    m->grads = m->grads_own = (float*)pool_alloc(kDevice, off * sizeof(float));
     BLA_CUDA(cudaMemsetAsync(m->params, 0, off * sizeof(float), rt().stream));
     BLA_CUDA(cudaMemsetAsync(m->grads, 0, off * sizeof(float), rt().stream));
     m->x = (float*)pool_alloc(kDevice, dims[0] * B * sizeof(float));
@@ -643,7 +675,7 @@ void bla_mlp_destroy(bla_mlp* m) {
     if (!m) return;
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
     BLA_CUDA(cudaStreamSynchronize(m->copy));
-    void* bufs[] = {m->params, m->grads, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
+    void* bufs[] = {m->params, m->grads_own, m->reduced, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
     for (void* b : bufs) pool_free(b);
     cudaStreamDestroy(m->copy); cudaEventDestroy(m->ev_free); cudaEventDestroy(m->ev_y);
     for (cudaEvent_t e : m->ev_chunk) cudaEventDestroy(e);
@@ -706,6 +738,7 @@ void bla_mlp_init_params(bla_mlp* m, unsigned long long seed) {
 
 void bla_mlp_read_stats(bla_mlp* m, double* stats_host) {
     double slots[2 * kStatSlots];
+    if (m->window && comm_peer_failed()) die("bla: a rank never arrived in a peer-window all-reduce, exiting");
     if (comm_active()) {   // data parallel: a collective -- every rank reads its statistics at the same point
         cudaStream_t cs = comm_stream();
         BLA_CUDA(cudaEventRecord(m->ev_rest, rt().stream));
