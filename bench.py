@@ -195,6 +195,8 @@ def workload_config(world, scaling="weak"):
                         if scaling == "weak" else
                         "model/mnist_nn.c train step: MLP 784-256-128-10, global batch 60000 columns split over the GPUs",
             "global_batch": gb, "per_gpu_batch": gb // world, "parallelism": f"dp{world}",
+            "allreduce": None if world == 1 else
+                         "library kernel over NVLink peer windows" if os.environ.get("BLA_PEER_ALLREDUCE", "0") not in ("", "0") else "nccl",
             "flop_per_sample": FLOP_PER_SAMPLE, "lr": LR}
 
 
