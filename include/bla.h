@@ -196,7 +196,9 @@ void bla_mnist_sample_take(bla_mnist* data, int count, int* indices_out);
  * y_out [classes x count] one-hot (may be NULL).  Only the indices cross PCIe. */
 void bla_mnist_gather(bla_mnist* data, const int* indices_host, int count, float* x_out, float* y_out, int classes);
 /* One epoch of model/mnist_nn.c:181-342 (sampler, batch assembly, SGD steps) on the device; stats_host = {average accuracy,
- * average loss} as the reference prints them (:340-341).  The net must have been created with max_batch >= batch_size. */
+ * average loss} as the reference prints them (:340-341).  The net must have been created with max_batch >= batch_size.
+ * Small batches (<= 4096 columns, >= 16 full batches, one GPU) replay one captured CUDA graph of the gather + step per batch,
+ * with the same kernels in the same order as the eager loop (env BLA_MLP_GRAPH=0 keeps the eager loop). */
 void bla_mlp_train_epoch(bla_mlp* net, bla_mnist* data, int batch_size, float lr_mult, double* stats_host);
 
 /* model/mnist_hinge.c:100-172: ten one-vs-rest hinge classifiers, one full-batch iteration over a device-resident store
