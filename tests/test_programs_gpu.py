@@ -21,7 +21,11 @@ def have(*names):
 
 
 def run(binary, cwd, *args, timeout=600):
-    env = dict(os.environ, BLA_PATH="fp32")
+    # MALLOC_PERTURB_=255: glibc fills every malloc'd block with 0x00.  model/mnist_hinge.c:120 mallocs its ten gradient
+    # vectors and :126 clears only 784 BYTES of each, so elements 196..783 start as whatever the heap held --
+    # the reference program itself prints 4e9 gradient norms under MALLOC_PERTURB_=1.  Which garbage a build sees depends
+    # on the allocation history of its CSV reader, so every program of a comparison runs with the same (zero) fill.
+    env = dict(os.environ, BLA_PATH="fp32", MALLOC_PERTURB_="255")
     p = subprocess.run([os.path.join(BIN, binary), *args], cwd=cwd, capture_output=True, text=True, timeout=timeout, env=env)
     assert p.returncode == 0, (binary, args, p.returncode, p.stdout[-2000:], p.stderr[-2000:])
     return p.stdout
