@@ -59,6 +59,7 @@ struct TcParams {
     int bn;                  // tile width: multiple of 16 (B K-major) or 32 (B MN-major), <= 256
     uint32_t stage_tx_bytes; // bytes TMA delivers per stage
     bool a_kmajor, b_kmajor;
+    bool a_box3, b_box3;     // MN-major operand fetched as ONE 3-D box {32 columns, BK rows, atoms} per k-block instead of one 2-D box per atom
     float* c; int ldc;
     float* partial;          // [splits][m][n] when splits > 1
     bla_epilogue epi;
@@ -73,7 +74,8 @@ struct TcParams {
     const float* cv_bias;     // conv == 1: + bias[img][filter]   (the U-Net's time-embedding add, cifar_unet.c:1024-1030)
     const float* cv_add;      // conv == 1: + addend[img][filter][pixel]   (the residual connection, cifar_unet.c:1067-1071)
     int cv_final, cv_Creal;   // conv == 2 with split-K: the reduce kernel writes dW in the reference layout [F][C][k][k] (C = cv_Creal)
-    int debug;               // BLA_TC_DEBUG: 1 = no split (1xTF32: hi.hi only), for bottleneck experiments
+    int debug;               // BLA_TC_DEBUG: 1 = no split (1xTF32: hi.hi only), 4 = never skip a zero lo tile, 5 = no split work but
+                             // three products -- bottleneck experiments
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -146,6 +148,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
 // release/acquire pair compiles to MEMBAR.GPU + CCTL.IVALL per k-block and halved the kernel's speed.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// One 32-bit word into the shared memory of another CTA of the cluster, counted as 4 bytes of transaction on a barrier of THAT CTA:
+// whoever sees the barrier's phase complete sees the word (the async-proxy store and its complete_tx are ordered) -- a cross-CTA
+// message without any cluster-scope fence.
+__device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t value, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(value),
+                 "r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
     asm volatile(
@@ -425,6 +434,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 const int k0 = cur.kb * BK, m0 = cur.m0, n0 = cur.n0;
                 if (p.a_kmajor) {
                     tma_load_2d(sa, &tma_a, k0, m0, bar_full(stage));                              // box {16 k, 128 m}
+                } else if (p.a_box3) {
+                    tma_load_3d(sa, &tma_a, 0, k0, m0 >> 5, bar_full(stage));                      // box {32 m, 16 k, 4 atoms}
                 } else {
 #pragma unroll
                     for (int at = 0; at < BM / 32; ++at)                                            // box {32 m, 16 k} per atom
@@ -433,6 +444,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 if (cl == 1) {
                     if (p.b_kmajor) {
                         tma_load_2d(sb, &tma_b, k0, n0, bar_full(stage));                          // box {16 k, bn n}
+                    } else if (p.b_box3) {
+                        tma_load_3d(sb, &tma_b, 0, k0, n0 >> 5, bar_full(stage));                  // box {32 n, 16 k, bn/32 atoms}
                     } else {
                         for (int at = 0; at < p.bn / 32; ++at)
                             tma_load_2d(sb + at * (BK * 128), &tma_b, n0 + 32 * at, k0, bar_full(stage));
@@ -442,6 +455,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     const int half = p.bn / 2, nh = n0 + (int)rank * half;
                     if (p.b_kmajor) {                                                              // box {16 k, bn/2 n}
                         tma_load_2d(sb, &tma_b, k0, nh, bar_full(stage));
+                    } else if (p.b_box3) {
+                        tma_load_3d(sb, &tma_b, 0, k0, nh >> 5, bar_full(stage));                  // box {32 n, 16 k, bn/64 atoms}
                     } else {
                         for (int at = 0; at < half / 32; ++at)
                             tma_load_2d(sb + at * (BK * 128), &tma_b, nh + 32 * at, k0, bar_full(stage));
@@ -483,13 +498,12 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
                     uint32_t a_lo_nz = 0, b_lo_nz = 0;
 #pragma unroll
-                    if (cl == 1) {   // lo-tile-is-zero shortcut (single-CTA kernel only: the flags are CTA-local)
+                    {   // lo-tile-is-zero shortcut; in a pair the peer's splitters posted their words into this CTA (st.async)
                         uint32_t f = 0;
 #pragma unroll
-                        for (int w = 0; w < kSplitWarps; ++w) f |= lo_flags[stage * 2 * kSplitWarps + w];
+                        for (int w = 0; w < kSplitWarps * cl; ++w) f |= lo_flags[stage * 2 * kSplitWarps + w];
                         a_lo_nz = f & 1u; b_lo_nz = f & 2u;
-                    } else {
-                        a_lo_nz = b_lo_nz = 1u;
+                        if (p.debug == 4 || p.debug == 5) a_lo_nz = b_lo_nz = 1u;   // experiments: always three products
                     }
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
@@ -534,7 +548,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 float4* lo = reinterpret_cast<float4*>(smem_gen + stage * kStageBytes + kRawBytes);
                 const int n_f4 = (int)(kABytes / 16) + (p.bn / cl) * (BK * 4 / 16);   // A tile + the staged part of the B tile
                 uint32_t nz_a = 0, nz_b = 0;
-                if (p.debug != 1)
+                if (p.debug != 1 && p.debug != 5)
 #pragma unroll 4
                 for (int i = t; i < n_f4; i += 32 * kSplitWarps) {
                     const float4 v = raw[i];
@@ -560,8 +574,14 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     if (cl == 1) {
                         lo_flags[slot] = fl;
                         mbar_arrive(bar_split(stage));
-                    } else {   // the arrival goes to the leader CTA, whose MMA lane issues for the pair
-                        mbar_arrive_cluster(mapa_shared(bar_split(stage), 0));
+                    } else if (rank == 0) {   // leader CTA (its MMA lane issues for the pair): the first warp also arms the barrier
+                        lo_flags[slot] = fl;  // for the peer's kSplitWarps flag words
+                        if (warp == 6) mbar_arrive_expect_tx(bar_split(stage), 4u * kSplitWarps);
+                        else mbar_arrive(bar_split(stage));
+                    } else {   // peer CTA: flag word and arrival both go to the leader's barrier
+                        const uint32_t lbar = mapa_shared(bar_split(stage), 0);
+                        st_async_u32(mapa_shared(lo_flags_u32 + 4u * slot, 0), fl, lbar);
+                        mbar_arrive_cluster(lbar);
                     }
                 }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -886,6 +906,29 @@ bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, i
     return r == CUDA_SUCCESS;
 }
 
+// MN-major operand, all atoms of a tile in one box.  The row-major [rows = k][cols = m or n] array is described as a 3-D tensor
+// {32 columns of an atom, k, atom} (strides ld and 32 floats): a box {32, BK, atoms} lands as `atoms` consecutive [BK][32] blocks,
+// exactly what `atoms` 2-D boxes produce -- but as ONE request.  The TMA engine costs ~105 cycles per box plus ~86 B/clk
+// (profiles/probes/tma_feed_probe.cu): eight 2 KB boxes take 1030 cycles, one 16 KB box 300; the short-K GEMMs of the MLP were bound
+// by exactly that.  The map pretends the last atom is whole: the caller checks that the bytes behind a ragged last row exist.
+bool make_map_mn3(CUtensorMap* map, const float* base, int rows, int cols, int ld, int atoms) {
+    cuuint64_t dims[3] = {32u, (cuuint64_t)rows, (cuuint64_t)((cols + 31) / 32)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), 32u * sizeof(float)};
+    cuuint32_t box[3] = {32u, (cuuint32_t)BK, (cuuint32_t)atoms};
+    cuuint32_t elem[3] = {1u, 1u, 1u};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+// may the 3-D form read the [rows][cols] array at `base`?  Columns past `cols` in the last atom are read from the next row (harmless:
+// they only feed output rows / columns that are clipped) -- for the LAST row they must still be inside the allocation.
+bool mn3_readable(const float* base, int rows, int cols, int ld) {
+    const int padded = (cols + 31) / 32 * 32;
+    if (padded <= ld) return true;
+    const size_t need = ((size_t)(rows - 1) * ld + padded) * sizeof(float);
+    return owned_bytes_from(base) >= need;
+}
+
 // fp32 tensor map for the epilogue's 32x32 tile stores (SWIZZLE_128B, clipped at the matrix edge)
 bool make_map_c(CUtensorMap* map, float* base, long long rows, int cols, int ld) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -1059,11 +1102,22 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
 
     CUtensorMap ma, mb;
     bool ok;
+    { static int en = -1; if (en < 0) { const char* e = getenv("BLA_TC_BOX3"); en = e ? atoi(e) : 1; }   // A/B switch
+      p.a_box3 = en && cmode == 0 && !p.a_kmajor && mn3_readable(g.a, g.k, g.m, g.lda);
+      p.b_box3 = en && cmode == 0 && !p.b_kmajor && mn3_readable(g.b, g.k, g.n, g.ldb); }
     if (cmode == 2) ok = make_map_conv_dy(&ma, g.a, *g.conv);
-    else ok = p.a_kmajor ? make_map(&ma, g.a, g.m, g.k, g.lda, BM, false) : make_map(&ma, g.a, g.k, g.m, g.lda, BK, true);
+    else if (p.a_kmajor) ok = make_map(&ma, g.a, g.m, g.k, g.lda, BM, false);
+    else {
+        if (p.a_box3 && !make_map_mn3(&ma, g.a, g.k, g.m, g.lda, BM / 32)) p.a_box3 = false;
+        ok = p.a_box3 || make_map(&ma, g.a, g.k, g.m, g.lda, BK, true);
+    }
     if (cmode == 1) ok = ok && make_map_conv_in(&mb, *g.conv, p.cv_bw, p.cv_bh);
     else if (cmode == 2) ok = ok && make_map_conv_in_mn(&mb, *g.conv);
-    else ok = ok && (p.b_kmajor ? make_map(&mb, g.b, g.n, g.k, g.ldb, p.bn / p.cluster, false) : make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
+    else if (p.b_kmajor) ok = ok && make_map(&mb, g.b, g.n, g.k, g.ldb, p.bn / p.cluster, false);
+    else {
+        if (p.b_box3 && !make_map_mn3(&mb, g.b, g.k, g.n, g.ldb, p.bn / p.cluster / 32)) p.b_box3 = false;
+        ok = ok && (p.b_box3 || make_map(&mb, g.b, g.k, g.n, g.ldb, BK, true));
+    }
     if (!ok) return false;
 
     const int sms = rt().num_sms;

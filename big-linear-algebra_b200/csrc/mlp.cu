@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(kBiasThreads) bias_grad_kernel(const float* __
     }
 }
 
-// ---- the skinny output layer (classes <= 16): three fused kernels instead of three padded GEMMs -------
-// All three stream the [hidden x B] activation matrix once with coalesced rows; the tiny weight
+// ---- the skinny output layer (classes <= 16): fused kernels instead of three padded GEMMs -------
+// They stream the [hidden x B] activation matrix once with coalesced rows; the tiny weight
 // matrix lives in shared memory and is read as broadcasts.
 constexpr int kMaxClasses = 16;
 constexpr int kStatSlots = 32;
@@ -228,65 +228,190 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
     }
 }
 
-// dW3 partials: each CTA owns a contiguous range of sample columns and produces a full [NC x hidden]
-// partial sum (thread k = one hidden unit); a second launch adds the partials in a fixed order.
+// The whole skinny output layer of a TRAINING step in one pass over A2 (model/mnist_nn.c:231-278): a CTA takes 64 sample columns
+// at a time, parks their [hidden x 64] slice of A2 in shared memory and derives everything that needs it from that one copy --
+//   logits = W3 . A2 + b3, softmax, argmax hit, cross-entropy, dZ3 = (p - y) * scale            (:231-268)
+//   dZ2 = (A2 > 0) (.) (W3^T . dZ3)                                                               (:273-278)
+//   dW3 += dZ3 . A2^T   (kept in registers across the CTA's tiles, one partial per CTA)           (:266-270)
+// Three separate kernels read A2 three times (92 MB at 60,000 columns) and took 70 us of a 450 us step for 0.7 % of its flops;
+// this one moves A2 once in, dZ2 once out.  Tile rows are 68 floats apart: float4 stores stay aligned, a column walk (lanes =
+// consecutive hidden units, phase 3) reads 128-bit quads from 8 distinct 4-bank groups = conflict free.
+constexpr int kHeadCols = 64, kHeadPitch = 68;
 template <int NC>
-__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ A2, int hidden, int B,
-                                                         int cols_per_cta, float* partial) {
-    constexpr int STEP = 64;
-    __shared__ float a_s[128][STEP + 1];          // [hidden unit (128 per pass)][column in step]
-    constexpr int NCP = (NC + 3) / 4 * 4;          // rows padded to whole float4: 128-bit broadcast reads in the inner loop
-    __shared__ __align__(16) float d_s[STEP][NCP];  // [column in step][class]
-    const int cbeg = blockIdx.x * cols_per_cta;
-    const int cend = min(B, cbeg + cols_per_cta);
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (int h0 = 0; h0 < hidden; h0 += 128) {     // hidden <= 256: at most two passes
-        const int k = h0 + (threadIdx.x & 127), half = threadIdx.x >> 7;   // thread = (hidden unit, half of the classes' columns)
+__global__ void __launch_bounds__(256, 3) head_train_kernel(const float* __restrict__ W3, const float* __restrict__ b3,
+                                                            const float* __restrict__ A2, const float* __restrict__ Y, int hidden, int B,
+                                                            float scale, float* __restrict__ dz3, float* __restrict__ dz2,
+                                                            float* __restrict__ partial, double* stats) {
+    constexpr int NCP = (NC + 3) / 4 * 4;
+    extern __shared__ __align__(16) float head_smem[];
+    float* a_s = head_smem;                                   // [hidden][kHeadPitch]
+    float* w_s = a_s + (size_t)hidden * kHeadPitch;           // [hidden][NCP]   w_s[k][r] = W3[r][k]
+    float* d_s = w_s + (size_t)hidden * NCP;                  // [kHeadCols][NCP] dZ3 of the tile
+    float* part = d_s + kHeadCols * NCP;                      // [3][kHeadCols][NC + 1] partial logits of k groups 1..3
+    for (int e = threadIdx.x; e < hidden * NCP; e += 256) {
+        const int k = e / NCP, r = e % NCP;
+        w_s[e] = r < NC ? W3[(size_t)r * hidden + k] : 0.f;
+    }
+    const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int kper = ((hidden + 3) / 4 + 3) / 4 * 4, kbeg = min(hidden, grp * kper), kend = min(hidden, kbeg + kper);
+    // phase 3 roles: hidden <= 128: thread = (hidden unit, half of the tile's columns); else thread = hidden unit, all columns
+    const int halves = hidden <= 128 ? 2 : 1;
+    const int wk = halves == 2 ? (threadIdx.x & 127) : threadIdx.x, whalf = halves == 2 ? (threadIdx.x >> 7) : 0;
+    const int wcols = kHeadCols / halves;
+    float wacc[NC];
+#pragma unroll
+    for (int r = 0; r < NC; ++r) wacc[r] = 0.f;
+    double loss = 0.0;
+    int correct = 0;
+    const int tiles = (B + kHeadCols - 1) / kHeadCols;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int c0 = tile * kHeadCols;
+        __syncthreads();                                      // the previous tile's readers are done (and w_s is complete)
+        // ---- load: 16 rows x 64 columns per pass, one float4 per thread, all loads of 8 passes in flight ----
+        {
+            const int lr = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;
+            const bool in = c0 + lc < B;                      // B % 4 == 0: a quad is wholly inside or outside
+            for (int k0 = 0; k0 < hidden; k0 += 128) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = k0 + 16 * u + lr;
+                    v[u] = (in && k < hidden) ? __ldg(reinterpret_cast<const float4*>(A2 + (size_t)k * B + c0 + lc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = k0 + 16 * u + lr;
+                    if (k < hidden) *reinterpret_cast<float4*>(a_s + k * kHeadPitch + lc) = v[u];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 1: logits of column `col` over this thread's quarter of the hidden units ----
+        const int c = c0 + col;
         float acc[NC];
 #pragma unroll
         for (int r = 0; r < NC; ++r) acc[r] = 0.f;
-        for (int c0 = cbeg; c0 < cend; c0 += STEP) {
-            // rows of A2 (hidden units) are read 64 columns = 256 bytes at a time by one warp each
-            for (int row = wrp; row < 128; row += 8) {
+#pragma unroll 4
+        for (int k = kbeg; k < kend; ++k) {
+            const float a = a_s[k * kHeadPitch + col];
+            float wr[NCP];
 #pragma unroll
-                for (int u = 0; u < STEP / 32; ++u) {
-                    const int c = c0 + lane + 32 * u;
-                    a_s[row][lane + 32 * u] = (h0 + row < hidden && c < cend) ? A2[(size_t)(h0 + row) * B + c] : 0.f;
+            for (int q = 0; q < NCP / 4; ++q) {
+                const float4 t = reinterpret_cast<const float4*>(w_s + k * NCP)[q];
+                wr[4 * q] = t.x; wr[4 * q + 1] = t.y; wr[4 * q + 2] = t.z; wr[4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int r = 0; r < NC; ++r) acc[r] = fmaf(wr[r], a, acc[r]);
+        }
+        if (grp > 0) {
+#pragma unroll
+            for (int r = 0; r < NC; ++r) part[((grp - 1) * kHeadCols + col) * (NC + 1) + r] = acc[r];
+        }
+        __syncthreads();
+        if (grp == 0) {
+            float dzr[NCP];
+#pragma unroll
+            for (int r = 0; r < NCP; ++r) dzr[r] = 0.f;
+            if (c < B) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int r = 0; r < NC; ++r) {
+                    acc[r] = ((acc[r] + part[col * (NC + 1) + r]) + part[(kHeadCols + col) * (NC + 1) + r]) + part[(2 * kHeadCols + col) * (NC + 1) + r];
+                    acc[r] += b3[r];
+                    mx = fmaxf(mx, acc[r]);
                 }
+                float tot = 0.f;
+#pragma unroll
+                for (int r = 0; r < NC; ++r) { acc[r] = expf(acc[r] - mx); tot += acc[r]; }
+                int pred = 0;
+                float best = 0.f, l = 0.f, ypred = 0.f;
+#pragma unroll
+                for (int r = 0; r < NC; ++r) {
+                    const size_t at = (size_t)r * B + c;
+                    const float pr = acc[r] / tot;
+                    const float y = Y[at];
+                    if (pr > best) { best = pr; pred = r; ypred = y; }
+                    l += -1.f * (y * logf(pr + 1e-15f));
+                    dzr[r] = (pr + (-1.0f) * y) * scale;
+                    dz3[at] = dzr[r];
+                }
+                (void)pred;
+                if (ypred == 1.f) ++correct;
+                loss += (double)l;
             }
-            for (int e = threadIdx.x; e < STEP * NC; e += 256) {
-                const int cc = e % STEP, r = e / STEP;
-                const int c = c0 + cc;
-                d_s[cc][r] = c < cend ? dz[(size_t)r * B + c] : 0.f;
+#pragma unroll
+            for (int q = 0; q < NCP / 4; ++q)
+                reinterpret_cast<float4*>(d_s + col * NCP)[q] = make_float4(dzr[4 * q], dzr[4 * q + 1], dzr[4 * q + 2], dzr[4 * q + 3]);
+        }
+        __syncthreads();
+        // ---- phase 2: dZ2[k][c] = (A2[k][c] > 0) ? sum_r W3[r][k] * dZ3[r][c] : 0, coalesced along the columns ----
+        if (c < B) {
+            float d[NCP];
+#pragma unroll
+            for (int q = 0; q < NCP / 4; ++q) {
+                const float4 t = reinterpret_cast<const float4*>(d_s + col * NCP)[q];
+                d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
             }
-            __syncthreads();
-            // the two halves of the block split the 64 columns of the step
-#pragma unroll 8
-            for (int cc = half * (STEP / 2); cc < (half + 1) * (STEP / 2); ++cc) {
-                const float a = a_s[threadIdx.x & 127][cc];
-                float dr[NCP];
+#pragma unroll 4
+            for (int k = kbeg; k < kend; ++k) {
+                float v = 0.f;
 #pragma unroll
                 for (int q = 0; q < NCP / 4; ++q) {
-                    const float4 t = reinterpret_cast<const float4*>(&d_s[cc][0])[q];
-                    dr[4 * q] = t.x; dr[4 * q + 1] = t.y; dr[4 * q + 2] = t.z; dr[4 * q + 3] = t.w;
+                    const float4 t = reinterpret_cast<const float4*>(w_s + k * NCP)[q];
+                    v = fmaf(t.x, d[4 * q], v);
+                    if (4 * q + 1 < NC) v = fmaf(t.y, d[4 * q + 1], v);
+                    if (4 * q + 2 < NC) v = fmaf(t.z, d[4 * q + 2], v);
+                    if (4 * q + 3 < NC) v = fmaf(t.w, d[4 * q + 3], v);
                 }
-#pragma unroll
-                for (int r = 0; r < NC; ++r) acc[r] = fmaf(dr[r], a, acc[r]);
+                dz2[(size_t)k * B + c] = a_s[k * kHeadPitch + col] > 0.f ? v : 0.f;
             }
-            __syncthreads();
         }
-        // combine the two halves through shared memory (reuse a_s), then one partial per CTA
-        float* comb = &a_s[0][0];
-        if (half == 1) {
+        // ---- phase 3: dW3[r][k] += sum over the tile's columns of dZ3[r][c] * A2[k][c]  (columns past B hold zeros) ----
+        if (wk < hidden) {
+            const float* arow = a_s + wk * kHeadPitch + whalf * wcols;
+            const float* drow = d_s + (size_t)whalf * wcols * NCP;
+#pragma unroll 2
+            for (int cc = 0; cc < wcols; cc += 4) {
+                const float4 a4 = *reinterpret_cast<const float4*>(arow + cc);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int r = 0; r < NC; ++r) comb[(threadIdx.x & 127) * NC + r] = acc[r];
-        }
-        __syncthreads();
-        if (half == 0 && k < hidden) {
+                for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int r = 0; r < NC; ++r) partial[((size_t)blockIdx.x * NC + r) * hidden + k] = acc[r] + comb[(threadIdx.x & 127) * NC + r];
+                    for (int q = 0; q < NCP / 4; ++q) {
+                        const float4 t = reinterpret_cast<const float4*>(drow + (cc + j) * NCP)[q];
+                        wacc[4 * q] = fmaf(t.x, av[j], wacc[4 * q]);
+                        if (4 * q + 1 < NC) wacc[4 * q + 1] = fmaf(t.y, av[j], wacc[4 * q + 1]);
+                        if (4 * q + 2 < NC) wacc[4 * q + 2] = fmaf(t.z, av[j], wacc[4 * q + 2]);
+                        if (4 * q + 3 < NC) wacc[4 * q + 3] = fmaf(t.w, av[j], wacc[4 * q + 3]);
+                    }
+                }
+            }
         }
-        __syncthreads();
+    }
+    // ---- one [NC x hidden] partial of dW3 per CTA (the halves meet in shared memory), two statistics per CTA ----
+    __syncthreads();
+    float* comb = a_s;
+    if (whalf == 1 && wk < hidden) {
+#pragma unroll
+        for (int r = 0; r < NC; ++r) comb[wk * NC + r] = wacc[r];
+    }
+    __syncthreads();
+    if (whalf == 0 && wk < hidden) {
+#pragma unroll
+        for (int r = 0; r < NC; ++r)
+            partial[((size_t)blockIdx.x * NC + r) * hidden + wk] = halves == 2 ? wacc[r] + comb[wk * NC + r] : wacc[r];
+    }
+    __shared__ double red[2][8];
+    double cv = (double)correct;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { loss += __shfl_xor_sync(0xffffffffu, loss, o); cv += __shfl_xor_sync(0xffffffffu, cv, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = loss; red[1][threadIdx.x >> 5] = cv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tl = 0.0, tc = 0.0;
+        for (int w = 0; w < 8; ++w) { tl += red[0][w]; tc += red[1][w]; }
+        atomicAdd(&stats[2 * (blockIdx.x % kStatSlots) + 0], tl);
+        atomicAdd(&stats[2 * (blockIdx.x % kStatSlots) + 1], tc);
     }
 }
 
@@ -298,45 +423,6 @@ __global__ void __launch_bounds__(256) head_wgrad_reduce_kernel(const float* __r
     for (int p = lane; p < nparts; p += 32) s += partial[(size_t)p * count + e];
     s = warp_sum(s);
     if (lane == 0) out[e] = s;
-}
-
-// dZ2 = (A2 > 0) (.) (W3^T . dZ3)  (model/mnist_nn.c:273-278): a thread owns 4 sample columns (float4) and
-// walks the hidden units; W3 is read from shared memory as broadcasts.
-template <int NC>
-__global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ W3, const float* __restrict__ dz,
-                                                         const float* __restrict__ A2, int hidden, int B, float* out) {
-    extern __shared__ float w_s[];   // [hidden][NC]
-    for (int e = threadIdx.x; e < hidden * NC; e += 256) {
-        const int k = e / NC, r = e % NC;
-        w_s[e] = W3[(size_t)r * hidden + k];
-    }
-    __syncthreads();
-    const int B4 = B >> 2;
-    const int hper = ((hidden + gridDim.y - 1) / gridDim.y + 3) / 4 * 4;   // hidden units of this blockIdx.y, a multiple of 4
-    const int hbeg = blockIdx.y * hper, hend = min(hidden, hbeg + hper);
-    for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < B4; c4 += gridDim.x * 256) {
-        float4 d[NC];
-#pragma unroll
-        for (int r = 0; r < NC; ++r) d[r] = *reinterpret_cast<const float4*>(dz + (size_t)r * B + 4 * c4);
-        for (int k0 = hbeg; k0 < hend; k0 += 4) {
-            float4 g[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) g[u] = *reinterpret_cast<const float4*>(A2 + (size_t)(k0 + u) * B + 4 * c4);   // hidden % 4 == 0
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int r = 0; r < NC; ++r) {
-                    const float w = w_s[(k0 + u) * NC + r];
-                    acc.x = fmaf(w, d[r].x, acc.x); acc.y = fmaf(w, d[r].y, acc.y);
-                    acc.z = fmaf(w, d[r].z, acc.z); acc.w = fmaf(w, d[r].w, acc.w);
-                }
-                acc.x = g[u].x > 0.f ? acc.x : 0.f; acc.y = g[u].y > 0.f ? acc.y : 0.f;
-                acc.z = g[u].z > 0.f ? acc.z : 0.f; acc.w = g[u].w > 0.f ? acc.w : 0.f;
-                *reinterpret_cast<float4*>(out + (size_t)(k0 + u) * B + 4 * c4) = acc;
-            }
-        }
-    }
 }
 
 // He-uniform init of model/mnist_nn.c:97-121: range * u - range/2 with range = 2*sqrtf(6/fan_in)
@@ -393,6 +479,29 @@ void head_forward(bla_mlp* m, const float* y, int B, float* dz, float* probs, cu
     count_launch();
 }
 
+// the training step's output layer: one pass over A2 gives dZ3 (into z3), dZ2, the loss statistics and one dW3 partial per CTA,
+// which a second small launch folds in a fixed order                                              model/mnist_nn.c:231-278
+void head_train(bla_mlp* m, const float* y, int B, cudaStream_t s) {
+    const int n2 = m->n[2], n3 = m->n[3], ncp = (n3 + 3) / 4 * 4;
+    int ctas = ceil_div(B, kHeadCols);
+    const int cap = std::min(m->head_ctas, rt().num_sms * 3);
+    if (ctas > cap) ctas = cap;
+    const size_t smem = ((size_t)n2 * kHeadPitch + (size_t)n2 * ncp + (size_t)kHeadCols * ncp + 3 * (size_t)kHeadCols * (n3 + 1)) * sizeof(float);
+    static bool attr_done[kMaxClasses + 1] = {};
+    BLA_DISPATCH_NC(n3, {
+        if (!attr_done[NC]) {
+            BLA_CUDA(cudaFuncSetAttribute(head_train_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_done[NC] = true;
+        }
+        head_train_kernel<NC><<<ctas, 256, smem, s>>>(W(m, 2), Bv(m, 2), m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2,
+                                                      m->head_partial, m->stats);
+    });
+    BLA_LAUNCH_CHECK();
+    head_wgrad_reduce_kernel<<<ceil_div(n3 * n2, 8), 256, 0, s>>>(m->head_partial, ctas, n3 * n2, dW(m, 2));   // :266-270
+    BLA_LAUNCH_CHECK();
+    count_launch(2);
+}
+
 void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s, bool with_head = true) {
     // Z1 = W1.(X/255) + b1 ; A1 = relu(Z1)          model/mnist_nn.c:218-224
     GemmArgs g{};
@@ -443,7 +552,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
     const bool skinny = skinny_head(m, B);
     forward(m, x, x_scale, B, s, !skinny);
     // A3 = softmax(Z3); loss / accuracy; dZ3 = (A3 - Y) / 784 (in place over Z3)      :234-268
-    if (skinny) head_forward(m, y, B, m->z3, nullptr, s);
+    if (skinny) head_train(m, y, B, s);               // + dZ2 and dW3: A2 is read once (:231-278)
     else k_softmax_xent(m->z3, y, m->n[3], B, nullptr, m->z3, (float)(1.0 / (double)m->n[0]), m->stats, s);
     const float* dz3 = m->z3;
 
@@ -476,33 +585,11 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
         g.epi.gate = gate;   // A > 0  <=>  Z > 0
         gemm(g, s);
     };
+    if (skinny) bias_on_side(dz3, m->n[3], dB(m, 2));   // :271
     // Backward order: the dZ chain first, then the layer-1 gradients (86 % of the bytes to exchange) so that
     // their all-reduce runs on the collective stream while the two small layers' gradients are still being
     // computed; the reference's order (:266-293) is dW3, dA2, dW2, dA1, dW1 -- same values, no dependence.
-    auto head_wgrad = [&]() {
-        const int n2 = m->n[2], n3 = m->n[3];
-        int ctas = m->head_ctas;
-        int cols = (ceil_div(B, ctas) + 63) / 64 * 64;
-        ctas = ceil_div(B, cols);
-        bias_on_side(dz3, n3, dB(m, 2));                                                                                 // :271
-        BLA_DISPATCH_NC(n3, head_wgrad_kernel<NC><<<ctas, 256, 0, s>>>(dz3, m->a2, n2, B, cols, m->head_partial));       // :266-270
-        BLA_LAUNCH_CHECK();
-        head_wgrad_reduce_kernel<<<ceil_div(n3 * n2, 8), 256, 0, s>>>(m->head_partial, ctas, n3 * n2, dW(m, 2));
-        BLA_LAUNCH_CHECK();
-        count_launch(2);
-    };
-    if (skinny) {
-        const int n2 = m->n[2], n3 = m->n[3];
-        int blocks = ceil_div(B / 4, 256);
-        const int cap = rt().num_sms * 4;
-        if (blocks > cap) blocks = cap;
-        const size_t smem = (size_t)n2 * n3 * sizeof(float);
-        BLA_DISPATCH_NC(n3, head_dgrad_kernel<NC><<<dim3(blocks, 4), 256, smem, s>>>(W(m, 2), dz3, m->a2, n2, B, m->dz2));   // :273-278
-        BLA_LAUNCH_CHECK();
-        count_launch();
-    } else {
-        dgrad(2, dz3, m->a2, m->dz2);         // :273-278
-    }
+    if (!skinny) dgrad(2, dz3, m->a2, m->dz2);         // :273-278 (the fused head kernel has produced dZ2 already)
     dgrad(1, m->dz2, m->a1, m->dz1);      // :284-289
     wgrad(0, m->dz1, x, x_scale);         // :290-293 (X/255 again folded into alpha)
     join_side();                          // db1 is part of the first segment
@@ -515,8 +602,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
         reduce_grads(m, 0, seg1, cs);
     }
     wgrad(1, m->dz2, m->a1, 0.f);         // :279-282
-    if (skinny) head_wgrad();
-    else wgrad(2, dz3, m->a2, 0.f);       // :266-271
+    if (!skinny) wgrad(2, dz3, m->a2, 0.f);   // :266-271
     join_side();
     if (dp) {                             // the rest of the flat buffer + {loss, correct}
         BLA_CUDA(cudaEventRecord(m->ev_rest, s));

@@ -149,6 +149,16 @@ bool pool_free(void* p) {
     return true;
 }
 
+// bytes from p to the end of the library block that holds it; 0 for foreign pointers
+size_t owned_bytes_from(const void* p) {
+    if (g_blocks.empty()) return 0;
+    auto it = g_blocks.upper_bound((uintptr_t)p);
+    if (it == g_blocks.begin()) return 0;
+    --it;
+    const uintptr_t end = it->first + it->second.size;
+    return (uintptr_t)p < end ? (size_t)(end - (uintptr_t)p) : 0;
+}
+
 MemKind classify(const void* p) {
     if (!g_blocks.empty()) {
         auto it = g_blocks.upper_bound((uintptr_t)p);

@@ -43,6 +43,8 @@ void* pool_alloc(MemKind kind, size_t bytes);
 bool pool_free(void* p);
 // Kind of an arbitrary pointer: registry hit (interior pointers included), else the driver's view.
 MemKind classify(const void* p);
+// Bytes readable from p to the end of the library (pool) block that contains it; 0 for pointers the library did not allocate.
+size_t owned_bytes_from(const void* p);
 
 // ---- per-call staging scope --------------------------------------------------------------------
 // Every reference-API entry point opens a CallScope, asks it for device-usable views of its
