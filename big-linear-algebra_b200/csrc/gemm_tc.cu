@@ -204,6 +204,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// true in exactly one lane of the (converged) warp; ptxas knows the branch it guards runs on a single lane
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32"
@@ -278,7 +290,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     volatile uint32_t* lo_flags = reinterpret_cast<volatile uint32_t*>(smem_gen + (lo_flags_u32 - smem_base));
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform by construction
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
@@ -349,8 +361,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 int ki = tap / p.cv_k, kj = tap - ki * p.cv_k;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-                    if (lane == 0) {
-                        mbar_wait(bar_empty(stage), phase ^ 1);
+                    mbar_wait(bar_empty(stage), phase ^ 1);
+                    if (elect_one()) {   // one elected lane: its operands stay in uniform registers (see the plain GEMM branch)
                         mbar_arrive_expect_tx(bar_full(stage), p.stage_tx_bytes);
                         tma_load_2d(sa, &tma_a, kb * BK, m0, bar_full(stage));                     // weights [F][(ki, kj, c)]: K-major
                     }
@@ -381,8 +393,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 int oi0 = pix0 / p.cv_Wo, oj0 = pix0 - oi0 * p.cv_Wo;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-                    if (lane == 0) {
-                        mbar_wait(bar_empty(stage), phase ^ 1);
+                    mbar_wait(bar_empty(stage), phase ^ 1);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(bar_full(stage), p.stage_tx_bytes);
                         tma_load_3d(sa, &tma_a, pix0, m0, img, bar_full(stage));
                     }
@@ -395,90 +407,65 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
-        } else if (lane == 0) {
-            // two cursors over this CTA's (tile, k-block) sequence: `cur` feeds shared memory, `ahead`
-            // runs kPrefetchDistance k-blocks in front of it and only warms L2
-            struct Cursor { int tile, kb, kb1, m0, n0; bool valid; };
-            auto open_tile = [&](Cursor& c) {
-                c.valid = c.tile < total_tiles;
-                if (!c.valid) return;
-                int split;
-                decode(c.tile, split, c.m0, c.n0);
-                c.kb = split * p.kblocks_per_split;
-                c.kb1 = min(p.kblocks, c.kb + p.kblocks_per_split);
-            };
-            auto advance = [&](Cursor& c) {
-                if (++c.kb >= c.kb1) { c.tile += unit_stride; open_tile(c); }
-            };
-            auto prefetch = [&](const Cursor& c) {
-                const int k0 = c.kb * BK;
-                if (p.a_kmajor) tma_prefetch_2d(&tma_a, k0, c.m0);
-                else
-                    for (int at = 0; at < BM / 32; ++at) tma_prefetch_2d(&tma_a, c.m0 + 32 * at, k0);
-                if (p.b_kmajor) tma_prefetch_2d(&tma_b, k0, c.n0);
-                else
-                    for (int at = 0; at < p.bn / 32; ++at) tma_prefetch_2d(&tma_b, c.n0 + 32 * at, k0);
-            };
-            // Measured on B200: lookahead prefetch LOSES 8-20 % (extra TMA traffic competes with the loads, L2-resident
-            // operands gain nothing) -- kept as a switch, disabled.
-            constexpr int kPrefetchDistance = 0;
-            Cursor cur{unit0, 0, 0, 0, 0, false}, ahead{unit0, 0, 0, 0, 0, false};
-            open_tile(cur);
-            open_tile(ahead);
-            for (int i = 0; i < kPrefetchDistance && ahead.valid; ++i) { prefetch(ahead); advance(ahead); }
+        } else {
+            // Plain GEMM.  The whole warp walks the (tile, k-block) sequence and ONE ELECTED lane issues: coordinates and
+            // barrier addresses then live in uniform registers (a `lane == 0` branch makes the compiler wrap every TMA operand in
+            // a vote / broadcast retry loop).  L2 prefetch ahead of the loads was measured in round 1 (cp.async.bulk.prefetch:
+            // -8..20 %, prefetch.global.L2 from a helper warp: -10 %) and is gone.
             int stage = 0; uint32_t phase = 0;
-            while (cur.valid) {
-                mbar_wait(bar_empty(stage), phase ^ 1);
-                const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-                mbar_arrive_expect_tx(bar_full(stage), p.stage_tx_bytes);
-                const int k0 = cur.kb * BK, m0 = cur.m0, n0 = cur.n0;
-                if (p.a_kmajor) {
-                    tma_load_2d(sa, &tma_a, k0, m0, bar_full(stage));                              // box {16 k, 128 m}
-                } else if (p.a_box3) {
-                    tma_load_3d(sa, &tma_a, 0, k0, m0 >> 5, bar_full(stage));                      // box {32 m, 16 k, 4 atoms}
-                } else {
+            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+                int split, m0, n0;
+                decode(tile, split, m0, n0);
+                const int kb0 = split * p.kblocks_per_split, kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
+                const int half = p.bn / cl, nh = n0 + (int)rank * half * (cl - 1);   // a pair's CTA stages only ITS half of the B columns
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(bar_empty(stage), phase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                        const int k0 = kb * BK;
+                        mbar_arrive_expect_tx(bar_full(stage), p.stage_tx_bytes);
+                        if (p.a_kmajor) {
+                            tma_load_2d(sa, &tma_a, k0, m0, bar_full(stage));                              // box {16 k, 128 m}
+                        } else if (p.a_box3) {
+                            tma_load_3d(sa, &tma_a, 0, k0, m0 >> 5, bar_full(stage));                      // box {32 m, 16 k, 4 atoms}
+                        } else {
 #pragma unroll
-                    for (int at = 0; at < BM / 32; ++at)                                            // box {32 m, 16 k} per atom
-                        tma_load_2d(sa + at * (BK * 128), &tma_a, m0 + 32 * at, k0, bar_full(stage));
-                }
-                if (cl == 1) {
-                    if (p.b_kmajor) {
-                        tma_load_2d(sb, &tma_b, k0, n0, bar_full(stage));                          // box {16 k, bn n}
-                    } else if (p.b_box3) {
-                        tma_load_3d(sb, &tma_b, 0, k0, n0 >> 5, bar_full(stage));                  // box {32 n, 16 k, bn/32 atoms}
-                    } else {
-                        for (int at = 0; at < p.bn / 32; ++at)
-                            tma_load_2d(sb + at * (BK * 128), &tma_b, n0 + 32 * at, k0, bar_full(stage));
+                            for (int at = 0; at < BM / 32; ++at)                                            // box {32 m, 16 k} per atom
+                                tma_load_2d(sa + at * (BK * 128), &tma_a, m0 + 32 * at, k0, bar_full(stage));
+                        }
+                        if (p.b_kmajor) {
+                            tma_load_2d(sb, &tma_b, k0, nh, bar_full(stage));                              // box {16 k, bn (/2) n}
+                        } else if (p.b_box3) {
+                            tma_load_3d(sb, &tma_b, 0, k0, nh >> 5, bar_full(stage));                      // box {32 n, 16 k, atoms}
+                        } else {
+                            for (int at = 0; at < half / 32; ++at)
+                                tma_load_2d(sb + at * (BK * 128), &tma_b, nh + 32 * at, k0, bar_full(stage));
+                        }
                     }
-                } else {
-                    // this CTA stages only ITS half of the B columns (at the start of its B region)
-                    const int half = p.bn / 2, nh = n0 + (int)rank * half;
-                    if (p.b_kmajor) {                                                              // box {16 k, bn/2 n}
-                        tma_load_2d(sb, &tma_b, k0, nh, bar_full(stage));
-                    } else if (p.b_box3) {
-                        tma_load_3d(sb, &tma_b, 0, k0, nh >> 5, bar_full(stage));                  // box {32 n, 16 k, bn/64 atoms}
-                    } else {
-                        for (int at = 0; at < half / 32; ++at)
-                            tma_load_2d(sb + at * (BK * 128), &tma_b, nh + 32 * at, k0, bar_full(stage));
-                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                if (kPrefetchDistance > 0 && ahead.valid) { prefetch(ahead); advance(ahead); }
-                advance(cur);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0 && rank == 0) {   // in a pair only the leader CTA issues (for both SMs)
+        // The WHOLE warp walks the loop (uniform control flow: barrier waits, flag reads and descriptor arithmetic stay in
+        // uniform registers) and one elected lane issues.  Measured with ncu on the layer-1 GEMM: as a `lane == 0` branch the
+        // compiler wrapped every tcgen05.mma operand in a vote / elect / broadcast retry loop, ~170 dependent instructions per
+        // k-block executed by a single thread -- the issuer never waited for data, it WAS the bound (1,150 cycles per k-block
+        // with the tensor pipe 45 % busy).
+        if (rank == 0) {   // in a pair only the leader CTA issues (for both SMs)
             const uint32_t idesc = make_idesc(!p.a_kmajor, !p.b_kmajor, p.bn, cl == 2 ? 2 * BM : BM);
             // K-major (rows of BK floats = 64 B, SWIZZLE_64B): 8-row groups 512 B apart (SBO), k-step = 32 B
             // inside the swizzle row.
             // MN-major (SWIZZLE_128B_BASE32B): 32-wide atoms BK*128 B apart (LBO), 4-k groups 512 B apart
             // (SBO), k-step of 8 = 1024 B.
             const uint32_t a_lbo = p.a_kmajor ? 16u : BK * 128u, b_lbo = p.b_kmajor ? 16u : BK * 128u;
-            const uint32_t a_sbo = 512u, b_sbo = 512u;
             const uint32_t a_lt = p.a_kmajor ? 4u : 1u, b_lt = p.b_kmajor ? 4u : 1u;
-            const uint32_t a_kstep = p.a_kmajor ? 32u : 1024u, b_kstep = p.b_kmajor ? 32u : 1024u;
+            const uint32_t a_kstep = (p.a_kmajor ? 32u : 1024u) >> 4, b_kstep = (p.b_kmajor ? 32u : 1024u) >> 4;
+            // descriptor = constant fields | (shared address >> 4): built once, then only the 14-bit address field moves
+            const uint64_t a_desc0 = make_desc(0u, a_lbo, 512u, a_lt), b_desc0 = make_desc(0u, b_lbo, 512u, b_lt);
+            const bool skip_ok = p.debug != 4 && p.debug != 5;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
@@ -495,41 +482,48 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     if (cl == 1) mbar_wait(bar_split(stage), phase);            // raw tile landed AND lo tile written
                     else mbar_wait_cluster(bar_split(stage), phase);            // ... in both CTAs of the pair
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-                    uint32_t a_lo_nz = 0, b_lo_nz = 0;
+                    // lo-tile-is-zero shortcut: one word per splitter warp (in a pair the peer's arrive by st.async), read as
+                    // 128-bit broadcasts
+                    uint32_t f = 0;
 #pragma unroll
-                    {   // lo-tile-is-zero shortcut; in a pair the peer's splitters posted their words into this CTA (st.async)
-                        uint32_t f = 0;
-#pragma unroll
-                        for (int w = 0; w < kSplitWarps * cl; ++w) f |= lo_flags[stage * 2 * kSplitWarps + w];
-                        a_lo_nz = f & 1u; b_lo_nz = f & 2u;
-                        if (p.debug == 4 || p.debug == 5) a_lo_nz = b_lo_nz = 1u;   // experiments: always three products
+                    for (int w = 0; w < kSplitWarps * cl / 4; ++w) {
+                        uint32_t x, y, z, t;
+                        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(t)
+                                     : "r"(lo_flags_u32 + 4u * (uint32_t)(stage * 2 * kSplitWarps + 4 * w)));
+                        f |= x | y | z | t;
                     }
+                    const bool a_lo_nz = !skip_ok || (f & 1u), b_lo_nz = !skip_ok || (f & 2u);
+                    const uint32_t sa = (smem_base + stage * kStageBytes) >> 4, sb = sa + (kABytes >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint64_t a_hi = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lt);
-                        const uint64_t b_hi = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lt);
-                        const uint64_t a_lo = make_desc(sa + kRawBytes + ks * a_kstep, a_lbo, a_sbo, a_lt);
-                        const uint64_t b_lo = make_desc(sb + kRawBytes + ks * b_kstep, b_lbo, b_sbo, b_lt);
-                        if (cl == 1) {
-                            if (a_lo_nz) { umma_tf32(tmem_d, a_lo, b_hi, idesc, accumulate); accumulate = 1u; }
-                            if (b_lo_nz) { umma_tf32(tmem_d, a_hi, b_lo, idesc, accumulate); accumulate = 1u; }
-                            umma_tf32(tmem_d, a_hi, b_hi, idesc, accumulate);
-                        } else {
-                            if (a_lo_nz) { umma_tf32_pair(tmem_d, a_lo, b_hi, idesc, accumulate); accumulate = 1u; }
-                            if (b_lo_nz) { umma_tf32_pair(tmem_d, a_hi, b_lo, idesc, accumulate); accumulate = 1u; }
-                            umma_tf32_pair(tmem_d, a_hi, b_hi, idesc, accumulate);
+                        for (int ks = 0; ks < BK / 8; ++ks) {
+                            const uint64_t a_hi = a_desc0 + (sa + ks * a_kstep), b_hi = b_desc0 + (sb + ks * b_kstep);
+                            const uint64_t a_lo = a_hi + (kRawBytes >> 4), b_lo = b_hi + (kRawBytes >> 4);
+                            if (cl == 1) {
+                                if (a_lo_nz) { umma_tf32(tmem_d, a_lo, b_hi, idesc, accumulate); accumulate = 1u; }
+                                if (b_lo_nz) { umma_tf32(tmem_d, a_hi, b_lo, idesc, accumulate); accumulate = 1u; }
+                                umma_tf32(tmem_d, a_hi, b_hi, idesc, accumulate);
+                            } else {
+                                if (a_lo_nz) { umma_tf32_pair(tmem_d, a_lo, b_hi, idesc, accumulate); accumulate = 1u; }
+                                if (b_lo_nz) { umma_tf32_pair(tmem_d, a_hi, b_lo, idesc, accumulate); accumulate = 1u; }
+                                umma_tf32_pair(tmem_d, a_hi, b_hi, idesc, accumulate);
+                            }
+                            accumulate = 1u;
                         }
-                        accumulate = 1u;
+                        // stage reusable once these MMAs retire; with a cluster the peer fills half of this stage and this CTA
+                        // fills half of the peer's, so both CTAs' empty barriers hear from both MMA issuers
+                        if (cl == 1) tcgen05_commit(bar_empty(stage));
+                        else tcgen05_commit_pair(bar_empty(stage));
                     }
-                    // stage reusable once these MMAs retire; with a cluster the peer fills half of this stage and this CTA
-                    // fills half of the peer's, so both CTAs' empty barriers hear from both MMA issuers
-                    if (cl == 1) tcgen05_commit(bar_empty(stage));
-                    else tcgen05_commit_pair(bar_empty(stage));
+                    accumulate = 1u;
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                if (cl == 1) tcgen05_commit(bar_acc_full(acc));    // accumulator complete -> epilogue (of both CTAs)
-                else tcgen05_commit_pair(bar_acc_full(acc));
+                if (elect_one()) {
+                    if (cl == 1) tcgen05_commit(bar_acc_full(acc));    // accumulator complete -> epilogue (of both CTAs)
+                    else tcgen05_commit_pair(bar_acc_full(acc));
+                }
+                __syncwarp();
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
             }
         }
