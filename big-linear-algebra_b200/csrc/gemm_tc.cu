@@ -3,7 +3,7 @@
 //
 // Arithmetic.  Each fp32 operand x is split as x = hi + lo with hi = x truncated to TF32 (the
 // tensor core itself ignores the low 13 mantissa bits of a 32-bit operand, so the RAW fp32 tile is
-// the hi tile) and lo = tf32_rna(x - hi) (exact subtraction, 13 significant bits, rounded to 11).
+// the hi tile) and lo = x - hi (exact subtraction, 13 significant bits, of which the tensor core keeps 11).
 // Every product is issued three times, a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, into one TMEM
 // accumulator; the dropped lo.lo term and the rounding of lo are O(2^-21) relative.
 //
@@ -74,6 +74,7 @@ struct TcParams {
     const float* cv_bias;     // conv == 1: + bias[img][filter]   (the U-Net's time-embedding add, cifar_unet.c:1024-1030)
     const float* cv_add;      // conv == 1: + addend[img][filter][pixel]   (the residual connection, cifar_unet.c:1067-1071)
     int cv_final, cv_Creal;   // conv == 2 with split-K: the reduce kernel writes dW in the reference layout [F][C][k][k] (C = cv_Creal)
+    int ring;                // 0 = all stages of the geometry
     int debug;               // BLA_TC_DEBUG: 1 = no split (1xTF32: hi.hi only), 4 = never skip a zero lo tile, 5 = no split work but
                              // three products -- bottleneck experiments
 };
@@ -104,11 +105,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
-}
-// L2 prefetch of a tile that the TMA will load a few k-blocks later: turns the DRAM latency of
-// streaming operands into an L2 hit for the shared-memory pipeline.
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y), "r"(src)
@@ -271,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_c, const TcParams p) {
     constexpr int kStages = Geo<CL>::kStages;
+    const int nstages = p.ring > 0 && p.ring < kStages ? p.ring : kStages;   // BLA_TC_STAGES: a shorter ring, for latency experiments
     constexpr uint32_t kRawBytes = Geo<CL>::kRawBytes, kStageBytes = Geo<CL>::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -370,7 +367,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     if (lane < natoms && p.debug != 2)   // debug 2: no gather (the host drops the B bytes from the expected count)
                         tma_load_4d(sb + lane * (BK * 128), &tma_b, cb * BK, x0 + kj, y0 + ki, img, bar_full(stage));
                     if (++cb == p.cv_cblocks) { cb = 0; if (++kj == p.cv_k) { kj = 0; ++ki; } }
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         } else if (p.conv == 2) {
@@ -404,14 +401,15 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     pix0 += BK; oj0 += BK;
                     while (oj0 >= p.cv_Wo) { oj0 -= p.cv_Wo; ++oi0; }
                     if (pix0 == p.cv_P) { pix0 = 0; oi0 = 0; oj0 = 0; ++img; }
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         } else {
             // Plain GEMM.  The whole warp walks the (tile, k-block) sequence and ONE ELECTED lane issues: coordinates and
             // barrier addresses then live in uniform registers (a `lane == 0` branch makes the compiler wrap every TMA operand in
             // a vote / broadcast retry loop).  L2 prefetch ahead of the loads was measured in round 1 (cp.async.bulk.prefetch:
-            // -8..20 %, prefetch.global.L2 from a helper warp: -10 %) and is gone.
+            // -8..20 %, prefetch.global.L2 from a helper warp: -10 %) and again in round 2 on this loop (0..-5 %,
+            // profiles/r02_prefetch_probe.txt): the feed is not bound by DRAM latency, and it is gone.
             int stage = 0; uint32_t phase = 0;
             for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
                 int split, m0, n0;
@@ -443,7 +441,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         }
                     }
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -517,7 +515,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     }
                     accumulate = 1u;
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 if (elect_one()) {
                     if (cl == 1) tcgen05_commit(bar_acc_full(acc));    // accumulator complete -> epilogue (of both CTAs)
@@ -547,12 +545,15 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 for (int i = t; i < n_f4; i += 32 * kSplitWarps) {
                     const float4 v = raw[i];
                     float4 r;
-                    uint32_t u, any;
-                    // lo = rna_tf32(x - trunc_tf32(x)); the tensor core reads trunc_tf32(x) from the raw tile
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u))); r.x = __uint_as_float(u); any = u;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u))); r.y = __uint_as_float(u); any |= u;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u))); r.z = __uint_as_float(u); any |= u;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u))); r.w = __uint_as_float(u); any |= u;
+                    // lo = x - trunc_tf32(x), exact (at most 13 significant bits); the tensor core reads trunc_tf32(x) from the raw
+                    // tile and truncates lo to its top 11 bits: |error| <= 2^-22 |x|, the size of the dropped lo.lo term.  (Rounding
+                    // lo with cvt.rna.tf32 first -- round 1 -- compiles to a 4-instruction emulation per element; the splitter warps
+                    // were then the bound of the kernel: ncu, 950 cycles per k-block against 512 of MMA.)
+                    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    uint32_t any = (__float_as_uint(r.x) | __float_as_uint(r.y)) | (__float_as_uint(r.z) | __float_as_uint(r.w));
                     lo[i] = r;
                     any &= 0x7FFFFFFFu;                       // -0.0 is still zero
                     if (i < (int)(kABytes / 16)) nz_a |= any; else nz_b |= any;
@@ -578,7 +579,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         mbar_arrive_cluster(lbar);
                     }
                 }
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -1007,6 +1008,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     p.b_kmajor = g.conv ? cmode == 1 : g.tb;   // B stored [n][k] (and the forward conv's NHWC gather) -> K-major;  row-major [k][n] -> MN-major
     p.c = g.c; p.ldc = g.ldc; p.epi = g.epi;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("BLA_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+    { static int ring = -1; if (ring < 0) { const char* e = getenv("BLA_TC_STAGES"); ring = e ? atoi(e) : 0; } p.ring = ring; }
     p.c_vec = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 4 == 0);
     p.m_tiles = ceil_div(g.m, BM);
     p.n_tiles = ceil_div(g.n, BN);
