@@ -322,6 +322,7 @@ void gemm(const GemmArgs& g, cudaStream_t s) {
         const bool worthwhile = g.k >= 64 && ((g.m >= 128 && g.n >= 128) || (g.m >= 16 && g.n >= 16 && (double)g.m * g.n * g.k >= 1.0e8));
         if ((forced || worthwhile) && gemm_3xtf32(g, s)) return;
     }
+    if (g.mask_out && g.mask_written) *g.mask_written = false;   // only the tensor path writes the bit form of a ReLU mask
     gemm_simt(g, s);
 }
 

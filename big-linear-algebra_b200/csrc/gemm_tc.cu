@@ -63,6 +63,8 @@ struct TcParams {
     float* c; int ldc;
     float* partial;          // [splits][m][n] when splits > 1
     bla_epilogue epi;
+    uint32_t* mask_out; int mask_ld;            // bit j % 32 of mask_out[i * mask_ld + j / 32] = (C[i][j] > 0)
+    const uint32_t* gate_bits; int gate_ld;     // epi.gate in the same bit form
     bool c_vec;              // 16-byte aligned rows
     bool tma_store;          // epilogue writes C (or the split-K partials) with cp.async.bulk.tensor stores
     int cluster;             // 1, or 2: CTA PAIRS (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages only HALF of B
@@ -594,19 +596,24 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             decode(tile, split, m0, n0);
             const int n_end = min(p.n, n0 + p.bn);
             const int row_base = m0 + 32 * q;
-            if (p.epi.gate && !p.partial && row_base + lane < p.m) {
+            if (p.epi.gate && !p.gate_bits && !p.partial && row_base + lane < p.m) {
                 // The relu' gate is one 128-byte row segment per lane and 32-column chunk.  Loaded on demand it exposes a DRAM
                 // round trip per chunk (the K = 128 dgrad of the MLP spent 21 us per tile here); asked for now, while this
                 // tile's MMAs are still running, it is an L2 hit by the time the accumulator is ready.
                 const float* grow = p.epi.gate + (size_t)(row_base + lane) * p.ldc;
                 for (int col0 = n0; col0 < n_end; col0 += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + col0));
             }
+            // bit-form gate: one word per lane (row) and 32-column chunk, fetched one chunk ahead -- the first one NOW, behind the tile's MMAs
+            const uint32_t* gate_row = p.gate_bits ? p.gate_bits + (size_t)min(row_base + lane, p.m - 1) * p.gate_ld + (n0 >> 5) : nullptr;
+            uint32_t gate_next = (gate_row && !p.partial) ? __ldg(gate_row) : 0u;
             mbar_wait(bar_acc_full(acc), acc_phase);
             tcgen05_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 const int col0 = n0 + 32 * ch;
                 if (col0 >= n_end) break;            // warp-uniform
+                const uint32_t gate_w = gate_next;
+                if (gate_row && !p.partial && col0 + 32 < n_end) gate_next = __ldg(gate_row + ch + 1);
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + 32 * ch), v);
                 if (p.tma_store) {
@@ -633,7 +640,17 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 #pragma unroll
                             for (int e = 0; e < 32; ++e) o[e] = o[e] < 0.f ? 0.f : o[e];
                         }
-                        if (p.epi.gate && row_ok) {
+                        if (p.mask_out && row_ok) {   // the sign pattern of this row's 32 columns, for a later relu' gate
+                            uint32_t w = 0;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) w |= (o[e] > 0.f ? 1u : 0u) << e;
+                            p.mask_out[(size_t)i * p.mask_ld + (col0 >> 5)] = w;
+                        }
+                        if (p.gate_bits && row_ok) {   // 4 bytes per row and chunk instead of 128
+                            const uint32_t w = gate_w;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) o[e] = (w >> e) & 1u ? o[e] : 0.f;
+                        } else if (p.epi.gate && row_ok) {
                             const float* gp = p.epi.gate + (size_t)i * p.ldc + col0;
                             if (col0 + 31 < p.n) {
                                 float4 g4[8];
@@ -829,6 +846,7 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p)
             }
             part[grp][col] = acc;
             __syncthreads();
+            uint32_t nib = 0;
             if (grp == 0 && e4 < total4) {
                 float4 t = part[0][col];
 #pragma unroll
@@ -853,6 +871,16 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p)
                     o.x = epilogue_value(t.x, i, j, p); o.y = epilogue_value(t.y, i, j + 1, p);
                     o.z = epilogue_value(t.z, i, j + 2, p); o.w = epilogue_value(t.w, i, j + 3, p);
                     *reinterpret_cast<float4*>(p.c + (size_t)i * p.ldc + j) = o;
+                    if (p.mask_out) nib = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
+                }
+            }
+            if (p.mask_out && grp == 0) {
+                // n % 32 == 0 (checked by the host): the 8 lanes that share a 32-column word sit in one row; their nibbles meet by shuffles
+                uint32_t w = nib << (4 * (col & 7));
+                w |= __shfl_xor_sync(0xffffffffu, w, 1); w |= __shfl_xor_sync(0xffffffffu, w, 2); w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                if ((col & 7) == 0 && e4 < total4) {
+                    const size_t e = e4 << 2;
+                    p.mask_out[(size_t)(e / p.n) * p.mask_ld + (e % p.n >> 5)] = w;
                 }
             }
             __syncthreads();
@@ -1007,6 +1035,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     p.a_kmajor = !g.ta;           // A row-major [m][k]  -> K-major;  stored [k][m] -> MN-major
     p.b_kmajor = g.conv ? cmode == 1 : g.tb;   // B stored [n][k] (and the forward conv's NHWC gather) -> K-major;  row-major [k][n] -> MN-major
     p.c = g.c; p.ldc = g.ldc; p.epi = g.epi;
+    p.mask_out = g.mask_out; p.mask_ld = g.mask_ld; p.gate_bits = g.epi.gate ? g.gate_bits : nullptr; p.gate_ld = g.gate_ld;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("BLA_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     { static int ring = -1; if (ring < 0) { const char* e = getenv("BLA_TC_STAGES"); ring = e ? atoi(e) : 0; } p.ring = ring; }
     p.c_vec = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 4 == 0);
@@ -1138,9 +1167,14 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
             hi.c = g.c + n_main;
             if (g.epi.bias_cols) hi.epi.bias_cols = g.epi.bias_cols + n_main;
             if (g.epi.gate) hi.epi.gate = g.epi.gate + n_main;
+            if (g.gate_bits) hi.gate_bits = g.gate_bits + n_main / 32;     // n_main is a multiple of the tile width, itself a multiple of 32
+            if (g.mask_out) hi.mask_out = g.mask_out + n_main / 32;
             if (g.epi.pre_activation) hi.epi.pre_activation = g.epi.pre_activation + n_main;
             if (gemm_3xtf32(lo, s)) {
-                if (!gemm_3xtf32(hi, s)) gemm_simt(hi, s);
+                if (!gemm_3xtf32(hi, s)) {
+                    if (hi.mask_out && hi.mask_written) *hi.mask_written = false;
+                    gemm_simt(hi, s);
+                }
                 return true;
             }
         }
@@ -1173,6 +1207,11 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     memset(&mc, 0, sizeof(mc));
     p.tma_store = p.c_vec && !g.epi.pre_activation && !g.epi.bias_cols &&
                   (splits == 1 || (g.m % BM == 0 && g.n % 4 == 0));
+    if (g.mask_out && g.mask_written) {   // which of this product's launches can write the sign mask?
+        const bool can = splits == 1 ? p.tma_store : ((((size_t)g.m * g.n) & 3) == 0 && g.n % 32 == 0 && p.c_vec);
+        if (!can) { *g.mask_written = false; p.mask_out = nullptr; }
+    }
+    if (!p.tma_store) p.gate_bits = nullptr;   // the register-store epilogue reads the float gate
     if (cmode == 1 && splits == 1) {
         p.tma_store = make_map_conv_out(&mc, *g.conv);
         if (!p.tma_store) { if (ws) pool_free(ws); return false; }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstddef>
+#include <cstdint>
 
 #include "../../include/bla.h"
 
@@ -58,6 +59,13 @@ struct GemmArgs {
     float* c; int ldc;
     bla_epilogue epi;     // zero-initialised = plain store
     const ConvTc* conv;   // nullptr for a plain GEMM; else m = F, n = imgs*Ho*Wo, k = k*k*C, a = weights [F][(ki,kj,c)]
+    // ReLU masks in bit form (the MLP's relu' gates): 32 columns per word, row i at mask[i * ld .. ), bit j % 32 of word j / 32.
+    //   mask_out : bit = (C[i][j] > 0), written next to C by the launches that can (tensor path with TMA stores, its vectorised
+    //              split-K reduction); any launch that cannot clears *mask_written, and the caller falls back to the float gate
+    //   gate_bits: the same gate as epi.gate, read as one word per row and 32 columns where the kernel supports it (epi.gate must
+    //              still be set: it is what every other path reads)
+    uint32_t* mask_out; int mask_ld; bool* mask_written;
+    const uint32_t* gate_bits; int gate_ld;
     bool no_tail_split;   // internal: this call already is one half of a main / tail column split (gemm_tc.cu)
     int* plan_main_columns;   // query only: receives the column count of the first launch (n when there is no split); nothing runs
 };

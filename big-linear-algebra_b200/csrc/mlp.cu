@@ -43,6 +43,8 @@ struct bla_mlp {
     float *x, *y;                         // staging for host-side batches  [n0 x B], [n3 x B]
     unsigned char* x_u8;
     float *a1, *a2, *z3, *dz2, *dz1;      // [n1 x B] [n2 x B] [n3 x B] [n2 x B] [n1 x B]
+    uint32_t* a1_bits;                    // sign bits of A1 (32 columns per word), written by the layer-1 GEMM's epilogue: the relu' gate of
+    bool a1_bits_ok;                      // the layer-1 dgrad is then 4 bytes per row and 32 columns instead of 128
     double* stats;                        // kStatSlots x {loss_sum, num_correct} on the device (striped: ~1000 CTAs
                                           // adding into ONE pair of doubles serialise in the L2 atomic unit)
     float* head_partial;                  // [ctas][n3][n2] partial dW3 of the skinny output layer
@@ -508,6 +510,8 @@ void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s, b
     g.m = m->n[1]; g.n = B; g.k = m->n[0];
     g.a = W(m, 0); g.lda = m->n[0]; g.b = x; g.ldb = B; g.c = m->a1; g.ldc = B;
     g.epi.alpha = x_scale; g.epi.bias_rows = Bv(m, 0); g.epi.activation = BLA_ACT_RELU;
+    m->a1_bits_ok = true;
+    g.mask_out = m->a1_bits; g.mask_ld = (B + 31) / 32; g.mask_written = &m->a1_bits_ok;
     gemm(g, s);
     // A2 = relu(W2.A1 + b2)                           :226-229
     g = GemmArgs{};
@@ -583,6 +587,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
         g.a = W(m, l); g.lda = m->n[l]; g.ta = true;
         g.b = dz; g.ldb = B; g.c = out; g.ldc = B;
         g.epi.gate = gate;   // A > 0  <=>  Z > 0
+        if (gate == m->a1 && m->a1_bits_ok) { g.gate_bits = m->a1_bits; g.gate_ld = (B + 31) / 32; }
         gemm(g, s);
     };
     if (skinny) bias_on_side(dz3, m->n[3], dB(m, 2));   // :271
@@ -686,7 +691,7 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
         BLA_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[i], 0));
         bla_mlp v = *m;   // the same network looking at chunk i's slice of every per-batch buffer
         v.x += (size_t)n0 * b0; v.x_u8 += (size_t)n0 * b0; v.y += (size_t)n3 * b0;
-        v.a1 += (size_t)m->n[1] * b0; v.dz1 += (size_t)m->n[1] * b0;
+        v.a1 += (size_t)m->n[1] * b0; v.dz1 += (size_t)m->n[1] * b0; v.a1_bits += (size_t)m->n[1] * (b0 / 32);   // b0 is a multiple of 64
         v.a2 += (size_t)m->n[2] * b0; v.dz2 += (size_t)m->n[2] * b0;
         v.z3 += (size_t)n3 * b0;
         if (i > 0) v.grads = m->grads_chunk;
@@ -732,6 +737,7 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     m->x_u8 = (unsigned char*)pool_alloc(kDevice, dims[0] * B);
     m->y = (float*)pool_alloc(kDevice, dims[3] * B * sizeof(float));
     m->a1 = (float*)pool_alloc(kDevice, dims[1] * B * sizeof(float));
+    m->a1_bits = (uint32_t*)pool_alloc(kDevice, (size_t)dims[1] * ((B + 31) / 32 + 1) * sizeof(uint32_t));
     m->a2 = (float*)pool_alloc(kDevice, dims[2] * B * sizeof(float));
     m->z3 = (float*)pool_alloc(kDevice, dims[3] * B * sizeof(float));
     m->dz2 = (float*)pool_alloc(kDevice, dims[2] * B * sizeof(float));
@@ -761,7 +767,7 @@ void bla_mlp_destroy(bla_mlp* m) {
     if (!m) return;
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
     BLA_CUDA(cudaStreamSynchronize(m->copy));
-    void* bufs[] = {m->params, m->grads_own, m->reduced, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
+    void* bufs[] = {m->a1_bits, m->params, m->grads_own, m->reduced, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
     for (void* b : bufs) pool_free(b);
     cudaStreamDestroy(m->copy); cudaEventDestroy(m->ev_free); cudaEventDestroy(m->ev_y);
     for (cudaEvent_t e : m->ev_chunk) cudaEventDestroy(e);
