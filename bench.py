@@ -245,8 +245,8 @@ class Clocks:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default=os.environ.get("BLA_BENCH_PATH", "auto"), choices=["auto", "fp32", "3xtf32"])
     ap.add_argument("--no-extras", action="store_true")

@@ -1061,6 +1061,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         p.cv_bh = 32 / p.cv_bw < cv.Ho ? 32 / p.cv_bw : cv.Ho;
     }
     const int gran = p.cluster == 2 ? 64 : 32;   // whole 32-column epilogue chunks / MN-major atoms (per CTA half)
+    bool force_no_split = false;
     int conv_splits = 0;   // > 0: chosen together with the tile width below (conv forward only: measured on B200, the same model
                            // LOSES for the weight gradient (U-Net step 13.7 -> 13.9 ms) and for small plain GEMMs (1024^3: 70 -> 61 TFLOP/s))
     if (cmode == 1) {
@@ -1121,6 +1122,39 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         p.n_tiles = ceil_div(g.n, best_bn);
         p.bn = (ceil_div(g.n, p.n_tiles) + gran - 1) / gran * gran;
         if (p.bn > BN) p.bn = BN;
+        // Less than one wave of full-width tiles (the tail of the MLP's layer-1 GEMM, a 7,500-column data-parallel shard): the
+        // split-K route pays a second launch and (splits + 1) passes over the result; the alternative is ONE wave of narrow tiles.
+        // Cycle model of one k-block per CTA (profiles/r02_tma_feed_probe.txt: 105 cycles per TMA box + 86 B/clk; one 128 x 256 x 8
+        // MMA = 128 cycles; ~13 splitter instructions per float4 on 8 warps).
+        static int narrow_on = -1;
+        if (narrow_on < 0) { const char* e = getenv("BLA_TC_NARROW"); narrow_on = e ? atoi(e) : 1; }
+        const long long units_full = (long long)m_units * ceil_div(g.n, BN);
+        if (narrow_on && units_full * p.cluster * 2 <= rt().num_sms && p.kblocks >= 32 && slots / m_units >= 1) {
+            int bn_n = (ceil_div(g.n, slots / m_units) + gran - 1) / gran * gran;
+            if (bn_n < gran) bn_n = gran;
+            if (bn_n < BN) {
+                auto kb_cycles = [&](int bn) {
+                    const double cols = (double)bn / p.cluster;
+                    const double mma = 6.0 * 128.0 * bn / 256.0, tma = 2 * 105.0 + (kABytes + cols * BK * 4) / 86.0;
+                    const double split = (kABytes + cols * BK * 4) / 16.0 * 13.0 / 64.0;
+                    double t = mma > tma ? mma : tma;
+                    if (split > t) t = split;
+                    return t + 120.0;
+                };
+                long long sp = slots / units_full;
+                if (sp > p.kblocks / 16) sp = p.kblocks / 16;
+                if (sp > 64) sp = 64;
+                if (sp < 1) sp = 1;
+                const double t_split = (double)ceil_div(p.kblocks, sp) * kb_cycles(BN) +
+                                       (sp > 1 ? (double)(sp + 1) * g.m * g.n * 4.0 / 3000.0 + 6000.0 : 0.0);
+                const double t_narrow = (double)p.kblocks * kb_cycles(bn_n);
+                if (t_narrow < t_split) {
+                    p.bn = bn_n;
+                    p.n_tiles = ceil_div(g.n, bn_n);
+                    force_no_split = true;
+                }
+            }
+        }
     }
     p.stage_tx_bytes = kABytes + (uint32_t)(p.bn / p.cluster) * BK * 4;   // per CTA: its A tile + its share of the B tile
     if (p.conv && p.debug == 2) p.stage_tx_bytes = kABytes;
@@ -1183,7 +1217,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     int splits = 1;
     if (conv_splits > 0) {
         splits = conv_splits;
-    } else if (tiles * 2 <= sms && p.kblocks >= 32) {
+    } else if (!force_no_split && tiles * 2 <= sms && p.kblocks >= 32) {
         long long want = (sms / p.cluster) / (tiles / p.cluster);          // one wave: units * splits <= cluster slots
         long long maxs = p.kblocks / 16;
         splits = (int)(want < maxs ? want : maxs);

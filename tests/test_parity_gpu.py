@@ -601,8 +601,11 @@ def test_mlp_host_batch_in_chunks_equals_one_piece(bla, path):
         b.bla_mlp_set_host_chunking(net, chunk)
         stats = np.zeros(2)
         fn = b.bla_mlp_train_step_u8 if u8 else b.bla_mlp_train_step
-        fn(net, xptr, yptr, B, B, 0, 0.002, None)
-        fn(net, xptr, yptr, B, B, 0, 0.002, ptr(stats))      # totals of both steps
+        # lr 0.5: the updates (~3e-4) must stand well above the float32 spacing of the parameters themselves (7e-9 at 0.08) -- at
+        # lr 0.002 an update is ~1e-6 and every last-bit flip of a parameter is 0.5 % of it, so two correct paths that differ by 3e-6
+        # in one GEMM (split-K against one unsplit pass of narrow tiles, both inside the 3xTF32 tolerance) disagree by 8e-4
+        fn(net, xptr, yptr, B, B, 0, 0.5, None)
+        fn(net, xptr, yptr, B, B, 0, 0.5, ptr(stats))      # totals of both steps
         got = [np.empty_like(p) for p in p0]
         b.bla_mlp_get_params(net, *[ptr(g) for g in got])
         b.bla_mlp_destroy(net)
