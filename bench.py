@@ -168,7 +168,7 @@ def time_cpu_reference(steps, warmup, budget_s):
     for _ in range(steps):
         cpu.step(X, Y)
     dt = time.perf_counter() - t0
-    return dict(value=B * steps / dt, unit=UNIT, cores=1, kind=cpu.kind, ms_per_step=1e3 * dt / steps,
+    return dict(value=B * steps / dt, unit=UNIT, cores=1, kind=cpu.kind, ms_per_step=1e3 * dt / steps, columns=B,
                 sample=f"{steps} SGD steps of {B} synthetic samples (of the 60,000-sample step), reference C single-threaded "
                        f"(it has no threads), gcc -O2, 1 of {os.cpu_count()} host cores")
 
@@ -182,21 +182,21 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, args.scaling),
+            "config": dict(workload_config(world, args.scaling), sample_columns=r["columns"],
+                           sample_note="the CPU arm times a bounded %d-column sample of the 60,000-column step (per-sample cost is flat in the batch width)" % r["columns"]),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(world, scaling="weak"):
+def workload_config(world, scaling="strong", allreduce=None):
     gb = GLOBAL_BATCH * world if scaling == "weak" else GLOBAL_BATCH
     return {"workload": "model/mnist_nn.c train step: MLP 784-256-128-10, one 60000-column batch per GPU "
                         "(data-parallel column shards, one NCCL all-reduce of the flat gradient per step)"
                         if scaling == "weak" else
                         "model/mnist_nn.c train step: MLP 784-256-128-10, global batch 60000 columns split over the GPUs",
             "global_batch": gb, "per_gpu_batch": gb // world, "parallelism": f"dp{world}",
-            "allreduce": None if world == 1 else
-                         "library kernel over NVLink peer windows" if os.environ.get("BLA_PEER_ALLREDUCE", "0") not in ("", "0") else "nccl",
+            "allreduce": None if world == 1 else allreduce,
             "flop_per_sample": FLOP_PER_SAMPLE, "lr": LR}
 
 
@@ -251,9 +251,9 @@ def main():
     ap.add_argument("--path", default=os.environ.get("BLA_BENCH_PATH", "auto"), choices=["auto", "fp32", "3xtf32"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default): every GPU takes a 60,000-column shard (global batch 60,000 x N); "
-                         "strong: the 60,000 columns are split over the GPUs")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default, BASELINE.json configs[2]): the global batch of 60,000 columns is split over the GPUs; "
+                         "weak: every GPU takes a 60,000-column shard (global batch 60,000 x N)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
 
@@ -280,11 +280,57 @@ def main():
     PATH = {"auto": b.GEMM_AUTO, "fp32": b.GEMM_FP32, "3xtf32": b.GEMM_3XTF32}[args.path]
     b.bla_set_gemm_path(PATH)
 
+    dims = (C.c_int * 4)(*DIMS)
+    shapes = ((DIMS[1], DIMS[0]), (DIMS[1],), (DIMS[2], DIMS[1]), (DIMS[2],), (DIMS[3], DIMS[2]), (DIMS[3],))
+
+    def parity_batch(step, c0_, cnt):
+        """Columns [c0_, c0_ + cnt) of the step's global synthetic batch (same generator on every rank)."""
+        g = np.random.default_rng(9000 + step)
+        X = g.integers(0, 256, (DIMS[0], GLOBAL_BATCH), dtype=np.uint8)[:, c0_:c0_ + cnt].astype(np.float32)
+        labels = g.integers(0, DIMS[3], GLOBAL_BATCH)[c0_:c0_ + cnt]
+        Y = np.zeros((DIMS[3], cnt), np.float32); Y[labels, np.arange(cnt)] = 1
+        return np.ascontiguousarray(X), Y
+
+    def parity_steps(c0_, cnt, nsteps=3):
+        """nsteps SGD steps from He-uniform seed 42 on columns [c0_, c0_ + cnt) of the 60,000-column parity batches -> (params, loss sum)."""
+        net_ = b.bla_mlp_create(dims, cnt)
+        b.bla_mlp_init_params(net_, 42)
+        init = [np.empty(sh, np.float32) for sh in shapes]
+        b.bla_mlp_get_params(net_, *[g_.ctypes.data_as(C.c_void_p) for g_ in init])
+        st = np.zeros(2); loss_sum = 0.0
+        for k in range(nsteps):
+            X, Y = parity_batch(k, c0_, cnt)
+            b.bla_mlp_train_step(net_, X.ctypes.data_as(C.c_void_p), Y.ctypes.data_as(C.c_void_p), cnt, GLOBAL_BATCH, c0_, LR, st.ctypes.data_as(C.c_void_p))
+            loss_sum += st[0]
+        got = [np.empty(sh, np.float32) for sh in shapes]
+        b.bla_mlp_get_params(net_, *[g_.ctypes.data_as(C.c_void_p) for g_ in got])
+        b.bla_mlp_destroy(net_)
+        return np.concatenate([g_.ravel() for g_ in got]), loss_sum, np.concatenate([g_.ravel() for g_ in init])
+
+    # Data-parallel parity evidence for the line below (N > 1): rank 0 first runs three FULL-BATCH steps alone (no communicator yet) ...
+    dp_single = parity_steps(0, GLOBAL_BATCH) if (world > 1 and rank == 0) else None
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         b.bla_comm_init(dp.exchange_unique_id(b, dist, rank, device="cuda"), rank, world)
+    dp_parity = None
+    if world > 1:
+        # ... then all ranks run the same three steps on their column shards with the gradient all-reduce
+        c0p, cntp = dp.shard_columns(GLOBAL_BATCH, world, rank)
+        flat, loss_dp, init_flat = parity_steps(c0p, cntp)
+        t = torch.from_numpy(flat).cuda()
+        ref_t = t.clone(); dist.broadcast(ref_t, 0)
+        same = torch.tensor([1.0 if torch.equal(t, ref_t) else 0.0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ref_flat, loss_single, _ = dp_single
+            upd_dp, upd_single = flat.astype(np.float64) - init_flat, ref_flat.astype(np.float64) - init_flat
+            dp_parity = {"steps": 3, "params_bit_identical_across_ranks": bool(same.item() == 1.0),
+                         "max_rel_err_vs_single": float(np.linalg.norm(flat.astype(np.float64) - ref_flat) / np.linalg.norm(ref_flat.astype(np.float64))),
+                         "update_rel_err_vs_single": float(np.linalg.norm(upd_dp - upd_single) / np.linalg.norm(upd_single)),
+                         "loss_rel_err": float(abs(loss_dp - loss_single) / abs(loss_single)),
+                         "what": "3 SGD steps from the same init: %d column shards + all-reduce against rank 0 alone on the full 60,000-column batch" % world}
 
     def barrier():
         if dist:
@@ -293,7 +339,6 @@ def main():
 
     Bg = GLOBAL_BATCH * world if args.scaling == "weak" else GLOBAL_BATCH
     c0, Bl = dp.shard_columns(Bg, world, rank)
-    dims = (C.c_int * 4)(*DIMS)
     net = b.bla_mlp_create(dims, Bl)
     b.bla_mlp_init_params(net, 42)
 
@@ -343,6 +388,8 @@ def main():
 
     clocks = Clocks(local_rank) if rank == 0 else None
     time.sleep(0.3)
+    # device-resident steps replay one captured graph per batch buffer: every buffer is seen eagerly once and captured once in the warm-up
+    args.warmup = max(args.warmup, 2 * nbuf + 2)
     res = timed(step_resident, args.steps, args.warmup)
     clk = clocks.summary(res["t0"], res["t1"]) if clocks else None
     ms_per_step = res["ms"] / args.steps
@@ -431,6 +478,35 @@ def main():
         roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum, %s; algorithmic minimum %.1f MB (X read once, "
                                     "A1 written once, W1)" % (cj["source"], (DIMS[0] * n_main + DIMS[1] * n_main + DIMS[0] * DIMS[1]) * 4 / 1e6))
 
+    allreduce = None
+    weak = None
+    if world > 1:
+        allreduce = ("library kernel over NVLink peer windows (push + flags + rank-ordered sum + SGD update in one launch)"
+                     if b.bla_comm_peer_windows() else "nccl")
+        if args.scaling == "strong":
+            # the weak curve beside the headline: every GPU takes a whole 60,000-column batch (global batch 60,000 x N)
+            b.bla_mlp_destroy(net)
+            for p_ in Xd + Yd:
+                b.bla_free(p_)
+            wnet = b.bla_mlp_create(dims, GLOBAL_BATCH)
+            b.bla_mlp_init_params(wnet, 42)
+            wx, wy = [], []
+            for i in range(2):
+                px = rng.integers(0, 256, DIMS[0] * GLOBAL_BATCH, dtype=np.uint8)
+                pd = b.bla_malloc_device(px.nbytes); xd = b.bla_malloc_device(px.nbytes * 4)
+                b.bla_copy_h2d(pd, px.ctypes.data_as(C.c_void_p), px.nbytes); b.bla_u8_to_float(xd, pd, px.size, 1.0); b.bla_sync(); b.bla_free(pd)
+                labels = rng.integers(0, DIMS[3], GLOBAL_BATCH)
+                Y = np.zeros((DIMS[3], GLOBAL_BATCH), np.float32); Y[labels, np.arange(GLOBAL_BATCH)] = 1
+                yd = b.bla_malloc_device(Y.nbytes); b.bla_copy_h2d(yd, Y.ctypes.data_as(C.c_void_p), Y.nbytes); b.bla_sync()
+                wx.append(xd); wy.append(yd)
+            wsteps = min(args.steps, 100)
+            wr = timed(lambda i: b.bla_mlp_train_step(wnet, wx[i % 2], wy[i % 2], GLOBAL_BATCH, GLOBAL_BATCH * world, GLOBAL_BATCH * rank, LR, None), wsteps, 6)
+            weak = {"scaling": "weak", "global_batch": GLOBAL_BATCH * world, "per_gpu_batch": GLOBAL_BATCH, "ms_per_step": wr["ms"] / wsteps,
+                    "value": GLOBAL_BATCH * world / (wr["ms"] / wsteps * 1e-3), "unit": UNIT}
+            b.bla_mlp_destroy(wnet)
+            for p_ in wx + wy:
+                b.bla_free(p_)
+
     extras = None
     if not args.no_extras and rank == 0 and world == 1:
         extras = run_extras(b, torch, stream, pk)
@@ -439,6 +515,8 @@ def main():
         unet_dp = run_unet_dp(b, torch, dist, stream, world, barrier)
         if rank == 0:
             extras = {"gemm_sweep_row_sharded": sharded, "unet_data_parallel": unet_dp}
+    if rank == 0 and weak is not None:
+        extras = dict(extras or {}, weak_scaling=weak)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -452,7 +530,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": dict(workload_config(world, args.scaling), gemm_path=args.path,
+                "config": dict(workload_config(world, args.scaling, allreduce), gemm_path=args.path,
                                l2=f"inputs rotate over {nbuf} resident batches ({nbuf * x_bytes >> 20} MiB > 126 MB L2)"),
                 "tflops": value * FLOP_PER_SAMPLE / 1e12,
                 "roofline": roofline, "cpu_baseline": cpu,
@@ -465,7 +543,7 @@ def main():
                            "d2h_bytes_per_step": e2e8["d2h"] // e2e_steps, "ms_per_step": e2e8_ms,
                            "ms_per_step_one_piece": e2e8_one,
                            "api": "bla_mlp_train_step_u8(host uint8 X[784xB], Y[10xB], &stats)"},
-                "gpu_launches": int(res["launches"]), "clocks": clk,
+                "gpu_launches": int(res["launches"]), "clocks": clk, "dp_parity": dp_parity,
                 "loss_per_sample_last": float(stats[0] / max(1, Bg * args.steps)) if world == 1 else None,
                 "extras": extras}
         print(json.dumps(line), flush=True)

@@ -83,95 +83,159 @@ void comm_group_end() { ok(g.GroupEnd(), "ncclGroupEnd"); }
 }  // namespace bla
 
 // ------------------------------------------------------------------------------------------------------------------------
-// Peer window (opt-in, BLA_PEER_ALLREDUCE=1): the small gradient all-reduce as ONE kernel over NVLink peer memory.
+// All-reduce over NVLink peer memory, ONE kernel per call (default when every rank of the communicator can map every other rank's
+// window; BLA_PEER_ALLREDUCE=0 keeps NCCL).  The exchanges of this library are small (the MLP's 0.94 MB gradient, the hinge
+// classifier's 31 KB): at that size a collective is all latency, and NCCL's is two kernels' worth per call.
 //
-// Every rank owns a window of device memory (plain cudaMalloc, exported with cudaIpcGetMemHandle, the handles all-gathered
-// through NCCL once) that every other rank of the node maps.  A rank's producers write its contribution into its own window;
-// the all-reduce kernel then (1) stores the call's epoch number into its flag slot in every peer's window, (2) waits until
-// every peer's epoch has arrived in its own, (3) reads the same slice of all windows over NVLink, adds them in rank order
-// (so every rank gets the same bits) and writes the sum to a PRIVATE destination.  One launch, no ring, no staging copy:
-// at 1.9 MB (the MLP's gradient) the cost is the NVLink read of (world - 1) x 1.9 MB plus one flag round trip.
-// The sources are double-buffered by the caller (a window half is rewritten two steps later, and a peer cannot be two
-// all-reduces behind: it would not have posted the epoch this rank waited for in between), so one flag round per call is
-// enough.  Waits are bounded: a peer that never arrives sets an error word instead of hanging the GPU.
-// Status: written in round 1 after the GPU budget was spent -- not yet run on hardware, hence off by default.
+// Every rank owns a window of device memory (cudaMalloc, exported with cudaIpcGetMemHandle, the handles all-gathered through the
+// NCCL communicator once) that every other rank maps.  Window = flag block + 2 (parity) x world (source rank) data slots.
+// Kernel, per CTA c -- a CTA only ever talks to CTA c of the other ranks, there is no grid-wide step:
+//   1. epoch = my counter[c] + 1 (device memory: the kernel can be replayed from a CUDA graph with unchanged arguments)
+//   2. PUSH my slice c of the source buffer into slot [epoch & 1][my rank] of every peer's window (posted NVLink writes)
+//   3. fence, then store `epoch` into flag [my rank][c] of every peer
+//   4. wait until flag [r][c] >= epoch for every peer r in MY window: their slices have landed in my HBM
+//   5. sum the world contributions in RANK ORDER (mine from the source buffer, the peers' from my window, L2-coherent loads):
+//      every rank computes the same bits; the sum goes to dst, or straight into the parameters (params += alpha * sum)
+// Slot reuse needs no second handshake: slot [p] is rewritten two epochs later, and a peer cannot be two epochs behind -- it posted
+// the flag of epoch e - 1 that this rank waited for, after its kernel of epoch e - 2 (the last reader of the slot) had finished.
+// Waits are bounded (~4 s): a rank that never arrives raises the window's error word and the CTA leaves dst / the parameters
+// untouched; comm_peer_failed() reports it to the host.
 // ------------------------------------------------------------------------------------------------------------------------
 namespace {
 
 constexpr int kMaxPeers = 8;
-constexpr size_t kFlagBytes = 4096;          // the head of every window: one 64-byte line per writing rank + the error word
+constexpr int kPeerCtas = 148;               // upper bound of the grid of one call
+constexpr int kPeerThreads = 256;
+constexpr size_t kFlagBytes = (size_t)kMaxPeers * kPeerCtas * 8 + 256;   // flags [source rank][cta], then the error word
 
+unsigned peer_generation = 0;
 struct PeerState {
     bool tried = false, on = false;
-    size_t floats = 0;                       // payload capacity of one window, in floats
+    size_t floats = 0;                       // capacity of one data slot, in floats
     char* base[kMaxPeers] = {nullptr};       // every rank's window as mapped here (base[rank] is the local allocation)
-    unsigned long long epoch = 0;
+    unsigned long long* counters = nullptr;  // [kPeerCtas] local epoch of every CTA index
 } peer;
 
 struct PeerArgs {
-    const float* src[kMaxPeers];             // the same slice in every rank's window
-    unsigned long long* flag_out[kMaxPeers]; // this rank's slot in every peer's flag block
-    const unsigned long long* flag_in;       // the local flag block (slot r is written by rank r)
+    float* slot[kMaxPeers];                  // slot [parity 0][my rank] in every rank's window (parity 1 is `stride` floats further)
+    unsigned long long* flag_out[kMaxPeers]; // flag [my rank][0] in every rank's window
+    const unsigned long long* flag_in;       // my window's flags: [source rank][cta]
+    const float* data_in;                    // my window's slots [parity][source rank]
+    unsigned long long* counters;
     unsigned int* error;
-    float* dst;
-    size_t n;
-    unsigned long long epoch;
+    const float* src;                        // this rank's contribution (private memory)
+    float* dst;                              // sum, or parameters when `fused`
+    float alpha;
+    int fused;
+    size_t n4;                               // float4 elements of this call
+    size_t offset4;                          // where this call's range starts inside a slot
+    size_t slot_floats;                      // capacity of one slot
     int world, rank;
 };
 
-__global__ void __launch_bounds__(512) peer_allreduce_kernel(PeerArgs a) {
-    // (1) announce: everything this rank's earlier kernels wrote is visible system-wide before the flag is
-    if (blockIdx.x == 0 && threadIdx.x < a.world) {
-        __threadfence_system();
-        *(volatile unsigned long long*)a.flag_out[threadIdx.x] = a.epoch;
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(PeerArgs a) {
+    const int c = blockIdx.x, t = threadIdx.x;
+    const unsigned long long epoch = a.counters[c] + 1;
+    const size_t par_off = (epoch & 1ull) * (size_t)a.world * a.slot_floats;
+    const size_t per = (a.n4 + gridDim.x - 1) / gridDim.x;
+    const size_t beg = (size_t)c * per, end = beg + per < a.n4 ? beg + per : a.n4;
+    const float4* src4 = reinterpret_cast<const float4*>(a.src);
+    // 2. push
+    for (size_t i = beg + t; i < end; i += kPeerThreads) {
+        const float4 v = src4[i];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)
+            if (r < a.world && r != a.rank) reinterpret_cast<float4*>(a.slot[r] + par_off)[a.offset4 + i] = v;
     }
-    // (2) every CTA waits for every rank's announcement of this (or a later) call
-    if (threadIdx.x < a.world) {
-        const volatile unsigned long long* f = a.flag_in + threadIdx.x * 8;
-        long spins = 0;
-        while (*f < a.epoch) {
-            __nanosleep(200);
-            if (++spins > 10000000L) { atomicExch(a.error, 1u); break; }   // ~2 s: report, do not hang the device
-        }
+    __threadfence_system();
+    __syncthreads();
+    // 3. announce, 4. wait
+    __shared__ int failed;
+    if (t == 0) failed = 0;
+    if (t < a.world && t != a.rank) {
         __threadfence_system();
+        st_release_sys(a.flag_out[t] + c, epoch);
     }
     __syncthreads();
-    // (3) sum the windows in rank order
-    const size_t n4 = a.n / 4;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < a.world && t != a.rank) {
+        const unsigned long long* f = a.flag_in + (size_t)t * kPeerCtas + c;
+        long spins = 0;
+        while (ld_acquire_sys(f) < epoch) {
+            if (++spins > 2000) __nanosleep(200);
+            if (spins > 20000000L) { atomicExch(a.error, 1u); failed = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (!failed) {
+        // 5. sum in rank order
+        const float4* in4 = reinterpret_cast<const float4*>(a.data_in + par_off);
+        const size_t slot4 = a.slot_floats / 4;
+        float4* dst4 = reinterpret_cast<float4*>(a.dst);
+        for (size_t i = beg + t; i < end; i += kPeerThreads) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < kMaxPeers; ++r) {
-            if (r < a.world) {
-                const float4 v = __ldcv(reinterpret_cast<const float4*>(a.src[r]) + i);   // never from a stale cache line
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            for (int r = 0; r < kMaxPeers; ++r) {
+                if (r < a.world) {
+                    const float4 v = r == a.rank ? src4[i] : __ldcg(in4 + (size_t)r * slot4 + a.offset4 + i);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            }
+            if (a.fused) {
+                float4 p = dst4[i];
+                p.x = fmaf(a.alpha, acc.x, p.x); p.y = fmaf(a.alpha, acc.y, p.y); p.z = fmaf(a.alpha, acc.z, p.z); p.w = fmaf(a.alpha, acc.w, p.w);
+                dst4[i] = p;
+            } else {
+                dst4[i] = acc;
             }
         }
-        reinterpret_cast<float4*>(a.dst)[i] = acc;
     }
-    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
-        float acc = 0.f;
-        for (int r = 0; r < a.world; ++r) acc += __ldcv(a.src[r] + i);
-        a.dst[i] = acc;
+    if (t == 0) a.counters[c] = epoch;       // the flags of this epoch are out: also after a timeout, so that the ranks stay in step
+}
+
+void peer_release() {
+    ++peer_generation;
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (!peer.base[r]) continue;
+        if (r == g.rank) cudaFree(peer.base[r]);
+        else cudaIpcCloseMemHandle(peer.base[r]);
+        peer.base[r] = nullptr;
     }
+    if (peer.counters) { cudaFree(peer.counters); peer.counters = nullptr; }
+    cudaGetLastError();
+    peer.on = false;
+    peer.floats = 0;
 }
 
 // collective: every rank calls it with the same `floats`; returns whether ALL ranks mapped all windows
 bool peer_setup(size_t floats) {
     peer.tried = true;
     const char* e = getenv("BLA_PEER_ALLREDUCE");
-    if (!e || atoi(e) == 0 || !comm_active() || g.world > kMaxPeers) return false;
+    if ((e && atoi(e) == 0) || !comm_active() || g.world > kMaxPeers) return false;
     cudaStream_t s = rt().stream;
-    const size_t bytes = kFlagBytes + floats * sizeof(float);
+    BLA_CUDA(cudaStreamSynchronize(s));
+    peer_release();
+    floats = (floats + 3) / 4 * 4;
+    const size_t bytes = kFlagBytes + 2 * (size_t)g.world * floats * sizeof(float);
     int good = 1;
     char* mine = nullptr;
     cudaIpcMemHandle_t handle;
     memset(&handle, 0, sizeof(handle));
-    if (cudaMalloc((void**)&mine, bytes) != cudaSuccess || cudaMemset(mine, 0, bytes) != cudaSuccess ||
-        cudaIpcGetMemHandle(&handle, mine) != cudaSuccess) {
+    if (cudaMalloc((void**)&mine, bytes) != cudaSuccess || cudaMemset(mine, 0, kFlagBytes) != cudaSuccess ||
+        cudaIpcGetMemHandle(&handle, mine) != cudaSuccess || cudaMalloc((void**)&peer.counters, kPeerCtas * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(peer.counters, 0, kPeerCtas * sizeof(unsigned long long)) != cudaSuccess) {
         cudaGetLastError();
         good = 0;
     }
+    BLA_CUDA(cudaDeviceSynchronize());
     // all-gather the handles (and every rank's verdict so far) through the communicator that is already up
     struct Slot { cudaIpcMemHandle_t handle; int good; int pad[15]; };
     static_assert(sizeof(Slot) % 4 == 0, "slots travel as ints");
@@ -185,9 +249,10 @@ bool peer_setup(size_t floats) {
     BLA_CUDA(cudaMemcpyAsync(all.data(), all_dev, sizeof(Slot) * g.world, cudaMemcpyDeviceToHost, s));
     BLA_CUDA(cudaStreamSynchronize(s));
     for (int r = 0; r < g.world; ++r) good &= all[r].good;
+    peer.base[g.rank] = mine;
     if (good) {
         for (int r = 0; r < g.world && good; ++r) {
-            if (r == g.rank) { peer.base[r] = mine; continue; }
+            if (r == g.rank) continue;
             void* p = nullptr;
             if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
@@ -207,6 +272,7 @@ bool peer_setup(size_t floats) {
     for (int v : votes) good &= v;
     if (!good) {
         if (g.rank == 0) fprintf(stderr, "bla: peer windows unavailable (IPC / peer access), the all-reduce stays on NCCL\n");
+        peer_release();
         return false;
     }
     peer.floats = floats;
@@ -217,41 +283,50 @@ bool peer_setup(size_t floats) {
 }  // namespace
 
 namespace bla {
-// The local window's payload (room for `floats` floats), or nullptr when peer windows are off / unavailable.  Collective on
-// the first call; the size of that first call is the capacity.
-float* comm_peer_window(size_t floats) {
-    if (!peer.tried) peer_setup(floats);
-    if (!peer.on || floats > peer.floats) return nullptr;
-    return (float*)(peer.base[g.rank] + kFlagBytes);
+// Can an all-reduce of up to `floats` floats run over the peer windows?  Collective whenever the windows have to be (re)built: every
+// rank must ask with the same sizes in the same order.  Must not be called while a stream is being captured.
+bool comm_peer_ready(size_t floats) {
+    if (!peer.tried || (peer.on && floats > peer.floats)) peer_setup(floats);
+    return peer.on && floats <= peer.floats;
 }
-// dst[0..n) = sum over ranks of window[offset .. offset + n) -- `offset` in floats from the payload start, 16-byte aligned.
-// Every rank makes the same calls in the same order on stream s.
-void comm_peer_allreduce_f32(float* dst, size_t offset, size_t n, cudaStream_t s) {
+// dst[0..n) = sum over ranks of src[0..n)            (fused == false)
+// dst[0..n) += alpha * sum over ranks of src[0..n)   (fused == true: dst are the parameters)
+// `offset` (floats, a multiple of 4) places the call's range inside the slots: concurrent calls (two streams) must use disjoint
+// ranges.  n a multiple of 4, src / dst 16-byte aligned.  Every rank makes the same calls in the same order.
+void comm_peer_allreduce_f32(const float* src, float* dst, float alpha, bool fused, size_t offset, size_t n, cudaStream_t s) {
     if (!n) return;
+    if ((n & 3) || (offset & 3) || offset + n > peer.floats || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15))
+        die("bla: peer all-reduce of %zu floats at offset %zu does not fit the window contract, exiting", n, offset);
     PeerArgs a{};
     for (int r = 0; r < g.world; ++r) {
-        a.src[r] = (const float*)(peer.base[r] + kFlagBytes) + offset;
-        a.flag_out[r] = (unsigned long long*)(peer.base[r] + (size_t)g.rank * 64);
+        a.slot[r] = (float*)(peer.base[r] + kFlagBytes) + (size_t)g.rank * peer.floats;
+        a.flag_out[r] = (unsigned long long*)peer.base[r] + (size_t)g.rank * kPeerCtas;
     }
     a.flag_in = (const unsigned long long*)peer.base[g.rank];
+    a.data_in = (const float*)(peer.base[g.rank] + kFlagBytes);
+    a.counters = peer.counters;
     a.error = (unsigned int*)(peer.base[g.rank] + kFlagBytes - 64);
-    a.dst = dst;
-    a.n = n;
-    a.epoch = ++peer.epoch;
-    a.world = g.world;
-    a.rank = g.rank;
-    const int ctas = (int)std::min<size_t>(64, (n / 4 + 511) / 512 + 1);
-    peer_allreduce_kernel<<<ctas, 512, 0, s>>>(a);
+    a.src = src; a.dst = dst; a.alpha = alpha; a.fused = fused ? 1 : 0;
+    a.n4 = n / 4; a.offset4 = offset / 4; a.slot_floats = peer.floats;
+    a.world = g.world; a.rank = g.rank;
+    // the same grid on every rank (it only depends on n): ~512 float4 per CTA
+    int ctas = (int)std::min<size_t>(kPeerCtas, (a.n4 + 511) / 512);
+    if (ctas < 1) ctas = 1;
+    peer_allreduce_kernel<<<ctas, kPeerThreads, 0, s>>>(a);
     BLA_LAUNCH_CHECK();
     count_launch();
 }
-// true if a peer never arrived in some all-reduce since the last check (the results of that call are garbage)
+// true if a peer never arrived in some all-reduce since the last check (that call left its destination untouched); clears the word
 bool comm_peer_failed() {
     if (!peer.on) return false;
     unsigned int e = 0;
     BLA_CUDA(cudaMemcpy(&e, peer.base[g.rank] + kFlagBytes - 64, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e) BLA_CUDA(cudaMemset(peer.base[g.rank] + kFlagBytes - 64, 0, sizeof(e)));
     return e != 0;
 }
+bool comm_peer_on() { return peer.on; }
+// changes whenever addresses a captured graph may have baked in (the windows) are no longer valid
+unsigned comm_generation() { return peer_generation; }
 }  // namespace bla
 
 extern "C" {
@@ -275,6 +350,8 @@ void bla_comm_init(const void* id128, int rank, int world) {
 }
 
 int bla_comm_world(void) { return g.world; }
+// 1 once the gradient all-reduces of this process run over the NVLink peer windows (decided at the first data-parallel step), else 0 (NCCL)
+int bla_comm_peer_windows(void) { return peer.on ? 1 : 0; }
 int bla_comm_rank(void) { return g.rank; }
 
 void bla_allreduce_sum_f32(float* buf, size_t n) {
@@ -291,7 +368,9 @@ void bla_broadcast_f32(float* buf, size_t n, int root) {
 }
 void bla_comm_destroy(void) {
     if (g.comm) {
-        BLA_CUDA(cudaStreamSynchronize(rt().stream));
+        BLA_CUDA(cudaDeviceSynchronize());
+        peer_release();
+        peer.tried = false;
         g.CommDestroy(g.comm);
         g.comm = nullptr;
         g.world = 1;

@@ -27,9 +27,11 @@ void comm_group_end();
 cudaStream_t comm_stream();
 void comm_allreduce_f32_on(float* buf, size_t n, cudaStream_t s);
 void comm_allreduce_f64_on(double* buf, size_t n, cudaStream_t s);
-float* comm_peer_window(size_t floats);
-void comm_peer_allreduce_f32(float* dst, size_t offset, size_t n, cudaStream_t s);
+bool comm_peer_ready(size_t floats);
+bool comm_peer_on();
+void comm_peer_allreduce_f32(const float* src, float* dst, float alpha, bool fused, size_t offset, size_t n, cudaStream_t s);
 bool comm_peer_failed();
+unsigned comm_generation();
 }  // namespace bla
 
 using namespace bla;
@@ -59,13 +61,17 @@ struct bla_mlp {
     float* y_whole;                        // the labels cross in ONE copy ahead of the chunks and are cut up on the device
     cudaStream_t copy;
     cudaEvent_t ev_chunk[kMaxChunks], ev_free, ev_y;
-    // data parallel over NVLink peer windows (comm.cu, opt-in): the gradient is produced straight into this rank's window, one
-    // half per step, and summed over the ranks' windows into `reduced` by one kernel; `grads` then points into the window
-    float* grads_own;                      // the private gradient buffer `grads` starts as
-    float* window;                         // nullptr: NCCL
-    float* reduced;
-    int parity;
+    // data parallel: the gradient all-reduce runs over NVLink peer windows (comm.cu: one kernel that also applies the update) when
+    // every rank could map them, else through NCCL
+    bool peer;                             // decided collectively at the first data-parallel step
     bool peer_checked;
+    // whole-step CUDA graphs for device-resident batches (bla_mlp_train_step without a statistics read-back): one per distinct
+    // argument tuple, replayed when the same batch buffers come round again
+    struct StepGraph { const void* x; const void* y; int B, Bg, c0; float lr; unsigned gen; int path, quirks; cudaGraphExec_t exec; int launches; unsigned long long used; };
+    StepGraph graphs[16];
+    int n_graphs;
+    unsigned long long graph_clock;
+    int warm_B, warm_Bg, warm_c0;          // shape of the last eager step: its pool blocks and one-time attributes are in place
 };
 
 namespace {
@@ -528,29 +534,22 @@ void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s, b
     gemm(g, s);
 }
 
-// Where this step's gradient goes: with peer windows, the half of the window the peers are not reading any more.  Collective
-// the first time (the windows are exchanged), so every rank must reach its first data-parallel step.
-void select_grads(bla_mlp* m) {
-    if (!comm_active()) return;
-    if (!m->peer_checked) {
-        m->peer_checked = true;
-        m->window = comm_peer_window(2 * m->nparams);
-        if (m->window) m->reduced = (float*)pool_alloc(kDevice, m->nparams * sizeof(float));
-    }
-    if (!m->window) return;
-    m->grads = m->window + (size_t)m->parity * m->nparams;
-    m->parity ^= 1;
+// Collective the first time (the windows are exchanged): every rank must reach its first data-parallel step.
+void prepare_comm(bla_mlp* m) {
+    if (!comm_active() || m->peer_checked) return;
+    m->peer_checked = true;
+    m->peer = comm_peer_ready(m->nparams);
 }
-// sum over ranks of grads[off, off + n): in place through NCCL, or from the windows into `reduced`
-void reduce_grads(bla_mlp* m, size_t off, size_t n, cudaStream_t cs) {
-    if (m->window) comm_peer_allreduce_f32(m->reduced + off, (size_t)(m->grads - m->window) + off, n, cs);
+// grads[off, off + n) summed over the ranks.  Peer windows: ONE kernel that also applies the update (params += -lr * sum) -- the
+// caller then skips its axpy; NCCL: in place.
+void reduce_grads(bla_mlp* m, size_t off, size_t n, float lr, cudaStream_t cs) {
+    if (m->peer) comm_peer_allreduce_f32(m->grads + off, m->params + off, -lr, true, off, n, cs);
     else comm_allreduce_f32_on(m->grads + off, n, cs);
 }
-const float* summed_grads(const bla_mlp* m) { return m->window && comm_active() ? m->reduced : m->grads; }
 
 // forward + backward of columns [c0, c0 + B) of a Bg-column batch: gradients into m->grads (all-reduced when `reduce` and a
 // communicator is active), loss / accuracy added to m->stats
-void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, bool reduce) {
+void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, bool reduce, float lr) {
     cudaStream_t s = rt().stream;
     const int quirk = rt().quirks;
     const bool skinny = skinny_head(m, B);
@@ -604,7 +603,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
     if (dp) {
         BLA_CUDA(cudaEventRecord(m->ev_l1, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_l1, 0));
-        reduce_grads(m, 0, seg1, cs);
+        reduce_grads(m, 0, seg1, lr, cs);
     }
     wgrad(1, m->dz2, m->a1, 0.f);         // :279-282
     if (!skinny) wgrad(2, dz3, m->a2, 0.f);   // :266-271
@@ -612,7 +611,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
     if (dp) {                             // the rest of the flat buffer + {loss, correct}
         BLA_CUDA(cudaEventRecord(m->ev_rest, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
-        reduce_grads(m, seg1, m->nparams - seg1, cs);
+        reduce_grads(m, seg1, m->nparams - seg1, lr, cs);
         // {loss, correct} are all-reduced where they are READ (bla_mlp_read_stats), not here: they accumulate over steps, and
         // reducing the running totals every step would count the earlier steps once per rank again
         BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
@@ -622,10 +621,10 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
 
 void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, float lr_mult, double* stats_host) {
     if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
-    select_grads(m);
-    backprop(m, x, x_scale, y, B, Bg, c0, true);
+    prepare_comm(m);
+    backprop(m, x, x_scale, y, B, Bg, c0, true, lr_mult);
     // clip_gradient is a no-op (threshold INFINITY, :13,:296-301); scale by -lr and add  :303-315
-    k_axpy(m->params, summed_grads(m), -(float)lr_mult, m->nparams, rt().stream);
+    if (!(m->peer && comm_active())) k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, rt().stream);
     if (stats_host) bla_mlp_read_stats(m, stats_host);
 }
 
@@ -661,7 +660,7 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
     cudaStream_t s = rt().stream, cp = m->copy;
     const int n0 = m->n[0], n3 = m->n[3];
     const int chunks = ceil_div(B, cols);
-    select_grads(m);
+    prepare_comm(m);
     const size_t esz = x_is_u8 ? 1 : sizeof(float);
     const MemKind yk = classify(y);
     const bool y_on_host = yk != kDevice && yk != kManaged;
@@ -696,19 +695,73 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
         v.z3 += (size_t)n3 * b0;
         if (i > 0) v.grads = m->grads_chunk;
         if (x_is_u8) k_u8_to_float(v.x, v.x_u8, (size_t)n0 * bc, 1.0f, s);
-        backprop(&v, v.x, x_scale, v.y, bc, Bg, c0 + b0, false);
+        backprop(&v, v.x, x_scale, v.y, bc, Bg, c0 + b0, false, lr_mult);
         if (i > 0) k_axpy(m->grads, m->grads_chunk, 1.0f, m->nparams, s);
     }
     if (comm_active()) {
         cudaStream_t cs = comm_stream();
         BLA_CUDA(cudaEventRecord(m->ev_rest, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
-        reduce_grads(m, 0, m->nparams, cs);
+        reduce_grads(m, 0, m->nparams, lr_mult, cs);
         BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
         BLA_CUDA(cudaStreamWaitEvent(s, m->ev_comm, 0));
     }
-    k_axpy(m->params, summed_grads(m), -(float)lr_mult, m->nparams, s);
+    if (!(m->peer && comm_active())) k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, s);
     if (stats_host) bla_mlp_read_stats(m, stats_host);
+}
+
+// A device-resident step as ONE graph launch.  The ~17 launches, 10 event hops between the compute / side / collective streams and
+// (data parallel) the all-reduce of a step are captured the first time an argument tuple is seen after an eager step of the same
+// shape, and replayed afterwards: at a 7,500-column data-parallel shard the step is ~100 us of kernels, and issuing them one by one
+// costs as much again.  Returns false when the step has to run eagerly (first step of a shape, capture impossible, BLA_MLP_STEP_GRAPH=0).
+bool step_graph(bla_mlp* m, const float* x, const float* y, int B, int Bg, int c0, float lr) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("BLA_MLP_STEP_GRAPH"); on = e ? atoi(e) : 1; }
+    if (!on || B > m->max_batch) return false;
+    cudaStream_t s = rt().stream;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cap != cudaStreamCaptureStatusNone) return false;                    // inside somebody else's capture (bla_mlp_train_epoch)
+    if (comm_active() && !m->peer_checked) return false;                     // the window exchange is host work: first step eager
+    const unsigned gen = comm_generation();
+    const int path = rt().gemm_path, quirks = rt().quirks;
+    ++m->graph_clock;
+    for (int i = 0; i < m->n_graphs; ++i) {
+        bla_mlp::StepGraph& g = m->graphs[i];
+        if (g.x == x && g.y == y && g.B == B && g.Bg == Bg && g.c0 == c0 && g.lr == lr && g.gen == gen && g.path == path && g.quirks == quirks) {
+            BLA_CUDA(cudaGraphLaunch(g.exec, s));
+            count_launch(g.launches);
+            g.used = m->graph_clock;
+            return true;
+        }
+    }
+    if (m->warm_B != B || m->warm_Bg != Bg || m->warm_c0 != c0) return false;   // pool blocks / attributes of this shape not settled yet
+    const unsigned long long before = rt().launches;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return false; }
+    step(m, x, 1 / 255.0F, y, B, Bg, c0, lr, nullptr);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    const int launches = (int)(rt().launches - before);
+    rt().launches = before;                                                  // nothing ran while capturing
+    cudaGraphExec_t exec = nullptr;
+    if (e != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        return false;                                                        // run this one eagerly
+    }
+    cudaGraphDestroy(graph);
+    int slot = m->n_graphs;
+    if (slot == 16) {                                                        // evict the least recently used
+        slot = 0;
+        for (int i = 1; i < 16; ++i) if (m->graphs[i].used < m->graphs[slot].used) slot = i;
+        cudaGraphExecDestroy(m->graphs[slot].exec);
+    } else {
+        ++m->n_graphs;
+    }
+    m->graphs[slot] = bla_mlp::StepGraph{x, y, B, Bg, c0, lr, gen, path, quirks, exec, launches, m->graph_clock};
+    BLA_CUDA(cudaGraphLaunch(exec, s));
+    count_launch(launches);
+    return true;
 }
 
 }  // namespace
@@ -730,7 +783,7 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     m->nparams = off;
     const size_t B = (size_t)max_batch;
     m->params = (float*)pool_alloc(kDevice, off * sizeof(float));
-    m->grads = m->grads_own = (float*)pool_alloc(kDevice, off * sizeof(float));
+    m->grads = (float*)pool_alloc(kDevice, off * sizeof(float));
     BLA_CUDA(cudaMemsetAsync(m->params, 0, off * sizeof(float), rt().stream));
     BLA_CUDA(cudaMemsetAsync(m->grads, 0, off * sizeof(float), rt().stream));
     m->x = (float*)pool_alloc(kDevice, dims[0] * B * sizeof(float));
@@ -767,7 +820,8 @@ void bla_mlp_destroy(bla_mlp* m) {
     if (!m) return;
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
     BLA_CUDA(cudaStreamSynchronize(m->copy));
-    void* bufs[] = {m->a1_bits, m->params, m->grads_own, m->reduced, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
+    for (int i = 0; i < m->n_graphs; ++i) cudaGraphExecDestroy(m->graphs[i].exec);
+    void* bufs[] = {m->a1_bits, m->params, m->grads, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
     for (void* b : bufs) pool_free(b);
     cudaStreamDestroy(m->copy); cudaEventDestroy(m->ev_free); cudaEventDestroy(m->ev_y);
     for (cudaEvent_t e : m->ev_chunk) cudaEventDestroy(e);
@@ -830,7 +884,7 @@ void bla_mlp_init_params(bla_mlp* m, unsigned long long seed) {
 
 void bla_mlp_read_stats(bla_mlp* m, double* stats_host) {
     double slots[2 * kStatSlots];
-    if (m->window && comm_peer_failed()) die("bla: a rank never arrived in a peer-window all-reduce, exiting");
+    if (m->peer && comm_peer_failed()) die("bla: a rank never arrived in a peer-window all-reduce (its update was skipped), exiting");
     if (comm_active()) {   // data parallel: a collective -- every rank reads its statistics at the same point
         cudaStream_t cs = comm_stream();
         BLA_CUDA(cudaEventRecord(m->ev_rest, rt().stream));
@@ -857,9 +911,13 @@ void bla_mlp_train_step(bla_mlp* m, const float* x, const float* y, int batch, i
         step_chunked(m, x, false, y, cols, 1 / 255.0F, batch, global_batch, col_offset, lr_mult, stats_host);
         return;
     }
+    const MemKind kx = classify(x), ky = classify(y);
+    if (!stats_host && (kx == kDevice || kx == kManaged) && (ky == kDevice || ky == kManaged) && step_graph(m, x, y, batch, global_batch, col_offset, lr_mult))
+        return;
     const float* dx = resident(x, m->x, (size_t)m->n[0] * batch, s);
     const float* dy = resident(y, m->y, (size_t)m->n[3] * batch, s);
     step(m, dx, 1 / 255.0F, dy, batch, global_batch, col_offset, lr_mult, stats_host);
+    m->warm_B = batch; m->warm_Bg = global_batch; m->warm_c0 = col_offset;
 }
 
 void bla_mlp_set_host_chunking(bla_mlp* m, int chunk_cols) { m->chunk_cols = chunk_cols; }

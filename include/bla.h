@@ -298,6 +298,9 @@ void bla_unet_train_step(bla_unet* net, const float* x, const float* time_emb, c
 void bla_comm_unique_id(void* id128);
 void bla_comm_init(const void* id128, int rank, int world);
 int bla_comm_world(void);
+/* 1 once this process' small all-reduces run as the library's own kernel over NVLink peer windows (cudaIpc-mapped, csrc/comm.cu;
+ * default when every rank can map every other rank's window, BLA_PEER_ALLREDUCE=0 keeps NCCL), 0 while / when they go through NCCL */
+int bla_comm_peer_windows(void);
 int bla_comm_rank(void);
 /* In-place sum all-reduce of device buffers on the library stream. */
 void bla_allreduce_sum_f32(float* buf, size_t n);

@@ -76,6 +76,43 @@ def main():
         errs = [rel_err(g, w) for g, w in zip(got, p64)]
         ok &= all(e <= tol * steps for e in errs) and all(t.item() == 1.0 for t in gathered)
         print("DP_CHECK_OK" if ok else "DP_CHECK_FAIL", "world", world, "errs", ["%.2e" % e for e in errs], flush=True)
+    # device-resident batches: the step runs as a captured CUDA graph (csrc/mlp.cu step_graph) -- eager, captured and replayed steps
+    # over two alternating resident batches against the oracle's same six full-batch steps
+    net2 = b.bla_mlp_create(dims, cnt)
+    b.bla_mlp_set_params(net2, *[ptr(p) for p in p32])
+    q64 = [p.astype(np.float64) for p in p32]
+    bufs = []
+    for k in range(2):
+        X = rng.integers(0, 256, (784, B)).astype(np.float32)
+        labels = rng.integers(0, 10, B)
+        Y = np.zeros((10, B), np.float32); Y[labels, np.arange(B)] = 1
+        Xl, Yl = np.ascontiguousarray(X[:, off:off + cnt]), np.ascontiguousarray(Y[:, off:off + cnt])
+        xd, yd = b.bla_malloc_device(Xl.nbytes), b.bla_malloc_device(Yl.nbytes)
+        b.bla_copy_h2d(xd, ptr(Xl), Xl.nbytes); b.bla_copy_h2d(yd, ptr(Yl), Yl.nbytes); b.bla_sync()
+        bufs.append((xd, yd, X, Y))
+    launches0 = b.bla_launch_count()
+    for k in range(6):
+        xd, yd, X, Y = bufs[k % 2]
+        b.bla_mlp_train_step(net2, xd, yd, cnt, B, off, 0.02, None)
+        if rank == 0:
+            loss = C.c_double(); correct = C.c_int()
+            o64.orc_mlp_step(dims, B, *[ptr(p) for p in q64], ptr(X.astype(np.float64)), ptr(Y.astype(np.float64)), 0.02, 1,
+                             C.byref(loss), C.byref(correct), None, 1)
+    got2 = [np.empty_like(p) for p in p32]
+    b.bla_mlp_get_params(net2, *[ptr(g) for g in got2])
+    flat2 = torch.from_numpy(np.concatenate([g.ravel() for g in got2])).cuda()
+    ref2 = flat2.clone(); dist.broadcast(ref2, 0)
+    same2 = torch.tensor([1.0 if torch.equal(flat2, ref2) else 0.0], device="cuda")
+    dist.all_reduce(same2, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        errs2 = [rel_err(g, w) for g, w in zip(got2, q64)]
+        tol = 1e-5 if path == b.GEMM_FP32 else 1e-4
+        g_ok = all(e <= tol * 6 for e in errs2) and same2.item() == 1.0
+        print("DP_GRAPH_OK" if g_ok else "DP_GRAPH_FAIL", "peer_windows", int(b.bla_comm_peer_windows()), "launches", int(b.bla_launch_count() - launches0),
+              "errs", ["%.2e" % e for e in errs2], flush=True)
+    for xd, yd, _, _ in bufs:
+        b.bla_free(xd); b.bla_free(yd)
+    b.bla_mlp_destroy(net2)
     # row-sharded GEMM (BASELINE.json configs[3]): every rank multiplies its row block by the broadcast B
     n = 512
     rowsn = n // world
