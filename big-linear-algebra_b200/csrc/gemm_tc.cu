@@ -1122,17 +1122,18 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         p.n_tiles = ceil_div(g.n, best_bn);
         p.bn = (ceil_div(g.n, p.n_tiles) + gran - 1) / gran * gran;
         if (p.bn > BN) p.bn = BN;
-        // Less than one wave of full-width tiles (the tail of the MLP's layer-1 GEMM, a 7,500-column data-parallel shard): the
-        // split-K route pays a second launch and (splits + 1) passes over the result; the alternative is ONE wave of narrow tiles.
-        // Cycle model of one k-block per CTA (profiles/r02_tma_feed_probe.txt: 105 cycles per TMA box + 86 B/clk; one 128 x 256 x 8
-        // MMA = 128 cycles; ~13 splitter instructions per float4 on 8 warps).
+        // Less than one wave of tiles (the tail of the MLP's layer-1 GEMM; every GEMM of a 7,500-column data-parallel shard): wide
+        // tiles leave SMs idle -- or, for a long contraction, take the split-K route with its second launch and (splits + 1) passes
+        // over the result.  The alternative is ONE wave of narrow tiles on all SMs.  Cycle model of one k-block per CTA
+        // (profiles/r02_tma_feed_probe.txt: 105 cycles per TMA box + 86 B/clk; one 128 x 256 x 8 MMA = 128 cycles; ~13 splitter
+        // instructions per float4 on 8 warps) plus ~600 cycles of epilogue per 32-column chunk.
         static int narrow_on = -1;
         if (narrow_on < 0) { const char* e = getenv("BLA_TC_NARROW"); narrow_on = e ? atoi(e) : 1; }
         const long long units_full = (long long)m_units * ceil_div(g.n, BN);
-        if (narrow_on && units_full * p.cluster * 2 <= rt().num_sms && p.kblocks >= 32 && slots / m_units >= 1) {
+        if (narrow_on && cmode == 0 && (long long)m_units * p.n_tiles < slots && slots / m_units >= 1) {
             int bn_n = (ceil_div(g.n, slots / m_units) + gran - 1) / gran * gran;
             if (bn_n < gran) bn_n = gran;
-            if (bn_n < BN) {
+            if (bn_n < p.bn) {
                 auto kb_cycles = [&](int bn) {
                     const double cols = (double)bn / p.cluster;
                     const double mma = 6.0 * 128.0 * bn / 256.0, tma = 2 * 105.0 + (kABytes + cols * BK * 4) / 86.0;
@@ -1141,14 +1142,18 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
                     if (split > t) t = split;
                     return t + 120.0;
                 };
-                long long sp = slots / units_full;
-                if (sp > p.kblocks / 16) sp = p.kblocks / 16;
-                if (sp > 64) sp = 64;
-                if (sp < 1) sp = 1;
-                const double t_split = (double)ceil_div(p.kblocks, sp) * kb_cycles(BN) +
-                                       (sp > 1 ? (double)(sp + 1) * g.m * g.n * 4.0 / 3000.0 + 6000.0 : 0.0);
-                const double t_narrow = (double)p.kblocks * kb_cycles(bn_n);
-                if (t_narrow < t_split) {
+                double t_now;
+                if (units_full * p.cluster * 2 <= rt().num_sms && p.kblocks >= 32) {   // today: split-K over full-width tiles
+                    long long sp = slots / units_full;
+                    if (sp > p.kblocks / 16) sp = p.kblocks / 16;
+                    if (sp > 64) sp = 64;
+                    if (sp < 1) sp = 1;
+                    t_now = (double)ceil_div(p.kblocks, sp) * kb_cycles(BN) + (sp > 1 ? (double)(sp + 1) * g.m * g.n * 4.0 / 3000.0 + 6000.0 : 600.0 * BN / 32);
+                } else {
+                    t_now = (double)p.kblocks * kb_cycles(p.bn) + 600.0 * p.bn / 32;
+                }
+                const double t_narrow = (double)p.kblocks * kb_cycles(bn_n) + 600.0 * bn_n / 32;
+                if (t_narrow < t_now) {
                     p.bn = bn_n;
                     p.n_tiles = ceil_div(g.n, bn_n);
                     force_no_split = true;

@@ -589,7 +589,11 @@ def test_mlp_host_batch_in_chunks_equals_one_piece(bla, path):
     automatic rule on a pinned batch, two steps in a row (the staging buffers are reused while the step before may still read them)."""
     b = bla
     b.bla_set_gemm_path(b.GEMM_FP32 if path == "fp32" else b.GEMM_AUTO)
-    tol = 2e-5 if path == "fp32" else 1e-4
+    # auto (3xTF32): a chunk and the whole batch are different GEMM shapes and may take different tilings (split-K slices against
+    # one unsplit pass of narrow tiles); their layer-1 outputs then differ by ~4e-6 (profiles/narrow_check.py), enough to flip the
+    # relu' gate of the few pre-activations that close to zero -- each flip moves one row of dW1 by ~1/B of its size.  Measured:
+    # 5e-4 norm-wise on dW1; a wrong chunk offset or a dropped chunk is O(1/chunks).
+    tol = 2e-5 if path == "fp32" else 2e-3
     dims = (C.c_int * 4)(784, 256, 128, 10)
     shapes = ((256, 784), (256,), (128, 256), (128,), (10, 128), (10,))
     rng = np.random.default_rng(77)
@@ -601,21 +605,28 @@ def test_mlp_host_batch_in_chunks_equals_one_piece(bla, path):
         b.bla_mlp_set_host_chunking(net, chunk)
         stats = np.zeros(2)
         fn = b.bla_mlp_train_step_u8 if u8 else b.bla_mlp_train_step
-        # lr 0.5: the updates (~3e-4) must stand well above the float32 spacing of the parameters themselves (7e-9 at 0.08) -- at
-        # lr 0.002 an update is ~1e-6 and every last-bit flip of a parameter is 0.5 % of it, so two correct paths that differ by 3e-6
-        # in one GEMM (split-K against one unsplit pass of narrow tiles, both inside the 3xTF32 tolerance) disagree by 8e-4
-        fn(net, xptr, yptr, B, B, 0, 0.5, None)
-        fn(net, xptr, yptr, B, B, 0, 0.5, ptr(stats))      # totals of both steps
+        # Step 1 with lr 2: its update (~1e-3) stands well above the float32 spacing of the parameters themselves (7e-9 at 0.08), so
+        # the comparison sees the gradients and not last-bit flips of the parameters (at lr 0.002 an update is ~1e-6 and one flipped
+        # bit is 0.5 % of it).  Step 2 (small lr) reuses the staging buffers while step 1 may still read them; after it the paths
+        # are compared loosely -- two correct paths that differ by 3e-6 in one GEMM (split-K against one unsplit pass of narrow
+        # tiles, both inside the 3xTF32 tolerance) drift apart once their parameters differ.
+        fn(net, xptr, yptr, B, B, 0, 2.0, None)
+        first = [np.empty_like(p) for p in p0]
+        b.bla_mlp_get_params(net, *[ptr(g) for g in first])
+        fn(net, xptr, yptr, B, B, 0, 0.002, ptr(stats))      # totals of both steps
         got = [np.empty_like(p) for p in p0]
         b.bla_mlp_get_params(net, *[ptr(g) for g in got])
         b.bla_mlp_destroy(net)
-        return [g.astype(np.float64) - p.astype(np.float64) for g, p in zip(got, p0)], stats
+        return ([g.astype(np.float64) - p.astype(np.float64) for g, p in zip(first, p0)], stats,
+                [g.astype(np.float64) - p.astype(np.float64) for g, p in zip(got, p0)])
 
     def compare(one, many):
         assert abs(int(one[1][1]) - int(many[1][1])) <= 2          # a near-tie may flip under another summation order
         assert abs(one[1][0] - many[1][0]) <= 1e-4 * abs(one[1][0])
         for i, (d1, d2) in enumerate(zip(one[0], many[0])):
             assert rel_err(d2, d1) <= tol, (i, rel_err(d2, d1))
+        for i, (d1, d2) in enumerate(zip(one[2], many[2])):
+            assert rel_err(d2, d1) <= 4e-3, (i, rel_err(d2, d1))
 
     try:
         B = 3000
