@@ -480,9 +480,25 @@ def main():
 
     allreduce = None
     weak = None
+    comm_ab = None
     if world > 1:
         allreduce = ("library kernel over NVLink peer windows (push + flags + rank-ordered sum + SGD update in one launch)"
                      if b.bla_comm_peer_windows() else "nccl")
+        # A/B of the exchange itself: the 0.94 MB gradient all-reduce alone, and the same strong-scaling step with NCCL
+        nflat = 235520
+        gbuf = b.bla_malloc_device(nflat * 4)
+        b.bla_fill_uniform(gbuf, nflat, 5, -1e-6, 1e-6)
+        comm_ab = {"gradient_floats": nflat}
+        had_peer = bool(b.bla_comm_peer_windows())
+        for kind in (("peer_windows", 1), ("nccl", 0)) if had_peer else (("nccl", 0),):
+            b.bla_comm_set_peer_windows(kind[1])
+            r_ = timed(lambda i: b.bla_allreduce_sum_f32(gbuf, nflat), 300, 20)
+            comm_ab[kind[0] + "_allreduce_us"] = r_["ms"] / 300 * 1e3
+        if had_peer:                                   # still on NCCL: the headline step again, for the record
+            r_ = timed(step_resident, min(args.steps, 100), 2 * nbuf + 2)
+            comm_ab["ms_per_step_with_nccl"] = r_["ms"] / min(args.steps, 100)
+            b.bla_comm_set_peer_windows(1)
+        b.bla_free(gbuf)
         if args.scaling == "strong":
             # the weak curve beside the headline: every GPU takes a whole 60,000-column batch (global batch 60,000 x N)
             b.bla_mlp_destroy(net)
@@ -517,6 +533,8 @@ def main():
             extras = {"gemm_sweep_row_sharded": sharded, "unet_data_parallel": unet_dp}
     if rank == 0 and weak is not None:
         extras = dict(extras or {}, weak_scaling=weak)
+    if rank == 0 and comm_ab is not None:
+        extras = dict(extras or {}, allreduce_ab=comm_ab)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

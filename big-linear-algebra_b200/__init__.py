@@ -219,6 +219,7 @@ PROTOTYPES = {
     "bla_comm_init": (None, [C.c_void_p, C.c_int, C.c_int]),
     "bla_comm_world": (C.c_int, []),
     "bla_comm_peer_windows": (C.c_int, []),
+    "bla_comm_set_peer_windows": (None, [C.c_int]),
     "bla_comm_rank": (C.c_int, []),
     "bla_allreduce_sum_f32": (None, [C.c_void_p, C.c_size_t]),
     "bla_allreduce_sum_f64": (None, [C.c_void_p, C.c_size_t]),

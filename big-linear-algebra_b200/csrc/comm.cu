@@ -111,6 +111,7 @@ constexpr size_t kFlagBytes = (size_t)kMaxPeers * kPeerCtas * 8 + 256;   // flag
 unsigned peer_generation = 0;
 struct PeerState {
     bool tried = false, on = false;
+    bool enabled = true;                     // bla_comm_set_peer_windows(0): keep the windows, route the all-reduces through NCCL
     size_t floats = 0;                       // capacity of one data slot, in floats
     char* base[kMaxPeers] = {nullptr};       // every rank's window as mapped here (base[rank] is the local allocation)
     unsigned long long* counters = nullptr;  // [kPeerCtas] local epoch of every CTA index
@@ -286,6 +287,7 @@ namespace bla {
 // Can an all-reduce of up to `floats` floats run over the peer windows?  Collective whenever the windows have to be (re)built: every
 // rank must ask with the same sizes in the same order.  Must not be called while a stream is being captured.
 bool comm_peer_ready(size_t floats) {
+    if (!peer.enabled) return false;
     if (!peer.tried || (peer.on && floats > peer.floats)) peer_setup(floats);
     return peer.on && floats <= peer.floats;
 }
@@ -324,7 +326,7 @@ bool comm_peer_failed() {
     if (e) BLA_CUDA(cudaMemset(peer.base[g.rank] + kFlagBytes - 64, 0, sizeof(e)));
     return e != 0;
 }
-bool comm_peer_on() { return peer.on; }
+bool comm_peer_on() { return peer.on && peer.enabled; }
 // changes whenever addresses a captured graph may have baked in (the windows) are no longer valid
 unsigned comm_generation() { return peer_generation; }
 }  // namespace bla
@@ -351,11 +353,23 @@ void bla_comm_init(const void* id128, int rank, int world) {
 
 int bla_comm_world(void) { return g.world; }
 // 1 once the gradient all-reduces of this process run over the NVLink peer windows (decided at the first data-parallel step), else 0 (NCCL)
-int bla_comm_peer_windows(void) { return peer.on ? 1 : 0; }
+int bla_comm_peer_windows(void) { return peer.on && peer.enabled ? 1 : 0; }
+// Collective (every rank, same value, same point of its call sequence): 0 routes the all-reduces through NCCL, 1 back over the windows.
+void bla_comm_set_peer_windows(int on) {
+    if (rt_initialised()) BLA_CUDA(cudaDeviceSynchronize());
+    peer.enabled = on != 0;
+    ++peer_generation;   // step graphs captured under the other setting are stale
+}
 int bla_comm_rank(void) { return g.rank; }
 
+// Small buffers (<= 4 MB, whole float4s) go over the NVLink peer windows as one kernel when the windows are up; everything else,
+// and everything when they are not, through NCCL.  Collective either way.
 void bla_allreduce_sum_f32(float* buf, size_t n) {
     if (!comm_active() || !n) return;
+    if (n <= (1u << 20) && (n & 3) == 0 && ((uintptr_t)buf & 15) == 0 && comm_peer_ready(n)) {
+        comm_peer_allreduce_f32(buf, buf, 0.f, false, 0, n, rt().stream);
+        return;
+    }
     ok(g.AllReduce(buf, buf, n, ncclFloat32, ncclSum, g.comm, rt().stream), "ncclAllReduce");
 }
 void bla_allreduce_sum_f64(double* buf, size_t n) {

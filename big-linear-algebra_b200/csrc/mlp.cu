@@ -542,8 +542,9 @@ void prepare_comm(bla_mlp* m) {
 }
 // grads[off, off + n) summed over the ranks.  Peer windows: ONE kernel that also applies the update (params += -lr * sum) -- the
 // caller then skips its axpy; NCCL: in place.
+bool use_peer(const bla_mlp* m) { return m->peer && comm_peer_on(); }
 void reduce_grads(bla_mlp* m, size_t off, size_t n, float lr, cudaStream_t cs) {
-    if (m->peer) comm_peer_allreduce_f32(m->grads + off, m->params + off, -lr, true, off, n, cs);
+    if (use_peer(m)) comm_peer_allreduce_f32(m->grads + off, m->params + off, -lr, true, off, n, cs);
     else comm_allreduce_f32_on(m->grads + off, n, cs);
 }
 
@@ -600,7 +601,11 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
     const bool dp = reduce && comm_active();
     cudaStream_t cs = dp ? comm_stream() : nullptr;
     const size_t seg1 = m->off_w[1];      // [W1 | b1] occupy the first seg1 floats of the flat gradient buffer
-    if (dp) {
+    // NCCL: the layer-1 segment goes out now, under the remaining gradient GEMMs.  Peer windows: ONE call at the end -- a call is
+    // one flag round between all ranks (~5 us of NVLink latency plus whatever the ranks have drifted apart), and the whole buffer is
+    // under a megabyte.
+    const bool two_calls = dp && !use_peer(m);
+    if (two_calls) {
         BLA_CUDA(cudaEventRecord(m->ev_l1, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_l1, 0));
         reduce_grads(m, 0, seg1, lr, cs);
@@ -611,7 +616,8 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
     if (dp) {                             // the rest of the flat buffer + {loss, correct}
         BLA_CUDA(cudaEventRecord(m->ev_rest, s));
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
-        reduce_grads(m, seg1, m->nparams - seg1, lr, cs);
+        if (two_calls) reduce_grads(m, seg1, m->nparams - seg1, lr, cs);
+        else reduce_grads(m, 0, m->nparams, lr, cs);
         // {loss, correct} are all-reduced where they are READ (bla_mlp_read_stats), not here: they accumulate over steps, and
         // reducing the running totals every step would count the earlier steps once per rank again
         BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
@@ -624,7 +630,7 @@ void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int 
     prepare_comm(m);
     backprop(m, x, x_scale, y, B, Bg, c0, true, lr_mult);
     // clip_gradient is a no-op (threshold INFINITY, :13,:296-301); scale by -lr and add  :303-315
-    if (!(m->peer && comm_active())) k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, rt().stream);
+    if (!(use_peer(m) && comm_active())) k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, rt().stream);
     if (stats_host) bla_mlp_read_stats(m, stats_host);
 }
 
@@ -706,7 +712,7 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
         BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
         BLA_CUDA(cudaStreamWaitEvent(s, m->ev_comm, 0));
     }
-    if (!(m->peer && comm_active())) k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, s);
+    if (!(use_peer(m) && comm_active())) k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, s);
     if (stats_host) bla_mlp_read_stats(m, stats_host);
 }
 

@@ -301,6 +301,8 @@ int bla_comm_world(void);
 /* 1 once this process' small all-reduces run as the library's own kernel over NVLink peer windows (cudaIpc-mapped, csrc/comm.cu;
  * default when every rank can map every other rank's window, BLA_PEER_ALLREDUCE=0 keeps NCCL), 0 while / when they go through NCCL */
 int bla_comm_peer_windows(void);
+/* collective: 0 = route the all-reduces through NCCL from now on, 1 = back over the peer windows (A/B measurements, fallback) */
+void bla_comm_set_peer_windows(int on);
 int bla_comm_rank(void);
 /* In-place sum all-reduce of device buffers on the library stream. */
 void bla_allreduce_sum_f32(float* buf, size_t n);
