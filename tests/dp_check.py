@@ -113,6 +113,36 @@ def main():
     for xd, yd, _, _ in bufs:
         b.bla_free(xd); b.bla_free(yd)
     b.bla_mlp_destroy(net2)
+    # BASELINE.json configs[1] data parallel: every rank walks its own shard of the samples, the 10 x 784 gradient
+    # and the sample count are all-reduced inside bla_hinge_iteration; three iterations against the float oracle on ALL samples
+    o32 = load_oracle(np.float32)
+    nh, F = 2500 * world + 37, 784
+    hr = np.random.default_rng(11)
+    hx = hr.integers(0, 256, (nh, F)).astype(np.float32)
+    hl = hr.integers(0, 10, nh).astype(np.int32)
+    hw0 = (hr.random((10, F)) / 10 - 0.05).astype(np.float32)
+    ho, hc = dp.shard_columns(nh, world, rank)
+    store = b.bla_mnist_from_arrays(ptr(np.ascontiguousarray(hx[ho:ho + hc])), ptr(np.ascontiguousarray(hl[ho:ho + hc].astype(np.float32))), hc, F)
+    hg = b.bla_hinge_create(F, 10, hc)
+    b.bla_hinge_set_weights(hg, ptr(hw0))
+    hw_ref, hgrad_ref = hw0.copy(), np.zeros((10, F), np.float32)
+    h_ok = True
+    for it in range(3):
+        norms = np.zeros(10, np.float32); norms_ref = np.zeros(10, np.float32)
+        b.bla_hinge_iteration(hg, store, 0.001, ptr(norms))
+        if rank == 0:
+            o32.orc_hinge_iter(nh, F, ptr(hw_ref), ptr(hgrad_ref), ptr(hx), ptr(hl), C.c_float(0.001), ptr(norms_ref))
+            h_ok &= bool(np.allclose(norms, norms_ref, rtol=1e-4, atol=1e-6))
+    hgot = np.empty_like(hw0)
+    b.bla_hinge_get_weights(hg, ptr(hgot))
+    ht = torch.from_numpy(hgot.ravel().copy()).cuda()
+    href = ht.clone(); dist.broadcast(href, 0)
+    hsame = torch.tensor([1.0 if torch.equal(ht, href) else 0.0], device="cuda")
+    dist.all_reduce(hsame, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        h_ok &= rel_err(hgot, hw_ref) <= 1e-4 and hsame.item() == 1.0
+        print("HINGE_DP_OK" if h_ok else "HINGE_DP_FAIL", "weights err %.2e" % rel_err(hgot, hw_ref), "identical on all ranks", bool(hsame.item()), flush=True)
+    b.bla_hinge_destroy(hg); b.bla_mnist_destroy(store)
     # row-sharded GEMM (BASELINE.json configs[3]): every rank multiplies its row block by the broadcast B
     n = 512
     rowsn = n // world

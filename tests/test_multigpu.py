@@ -30,6 +30,6 @@ def test_data_parallel_step_matches_oracle(path, batch, allreduce):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "dp_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
-    for word in ("DP_CHECK_OK", "DP_GRAPH_OK", "SHARDED_GEMM_OK", "UNET_DP_OK"):
+    for word in ("DP_CHECK_OK", "DP_GRAPH_OK", "HINGE_DP_OK", "SHARDED_GEMM_OK", "UNET_DP_OK"):
         assert word in p.stdout, (p.stdout[-3000:], p.stderr[-3000:])
     assert ("peer_windows 1" if allreduce == "peer" else "peer_windows 0") in p.stdout, p.stdout[-2000:]
