@@ -408,18 +408,22 @@ __global__ void __launch_bounds__(kClThreads, 2) group_norm_bwd_cluster(const fl
 }
 
 // ---- persistent forward with a TMA bulk-copy prefetch ring ------------------------------------------------
-// One CTA per SM walks over (image, group) slabs.  Slab i+1 is fetched into shared memory by ONE
-// cp.async.bulk (mbarrier complete_tx) while slab i -- already moved from shared memory into registers -- is
-// reduced, normalised and written out, so HBM never waits for the two block reductions.
+// One CTA per SM walks over (image, group) slabs.  The slab buffer is cut into four quarters, each with its own mbarrier and
+// its own eight warps: as soon as a quarter's warps have moved it from shared memory into registers they re-arm it with the
+// SAME quarter of the CTA's next slab (one cp.async.bulk), so the copy engine always has up to four requests in flight and HBM
+// never waits for the block reductions, the normalisation or the stores.  (Round 1 refilled the whole buffer only after all
+// 1024 threads had emptied it: 71 % of the measured HBM bandwidth.)
 __device__ __forceinline__ uint32_t gn_smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+constexpr int kQuarterF4 = kFastThreads / 4 * kFastF4;      // 2048 float4 = 32 KB per quarter
 
 __global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_tma(const float* __restrict__ x, float* __restrict__ y, float* vars,
                                                                       float* means, GnParams p, int images) {
     extern __shared__ __align__(128) float slab[];     // up to 32768 floats
     __shared__ float red[32];
-    __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bar[4];
     const int slabs = p.G * images;
-    const uint32_t bar_a = gn_smem_u32(&bar), slab_a = gn_smem_u32(slab);
+    const int quarter = threadIdx.x >> 8, qt = threadIdx.x & 255;      // this thread's quarter of the slab and its place in it
+    const uint32_t bar_a = gn_smem_u32(&bar[quarter]), slab_a = gn_smem_u32(slab) + (uint32_t)quarter * kQuarterF4 * 16u;
     auto slab_info = [&](int sidx, size_t& off, int& n4) {
         const int g = sidx % p.G, img = sidx / p.G;
         const int c0 = g * p.group_size;
@@ -427,52 +431,59 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_tma(const floa
         n4 = (nc * p.HW) >> 2;
         off = ((size_t)img * p.C + c0) * p.HW;
     };
-    auto issue = [&](int sidx) {       // thread 0 only
+    // float4 [quarter * 2048, min(n4, (quarter + 1) * 2048)) of slab sidx -> this quarter of the buffer; true if there is any
+    auto quarter_f4 = [&](int n4) { return max(0, min(n4 - quarter * kQuarterF4, kQuarterF4)); };
+    auto issue = [&](int sidx) {       // one thread per quarter
         size_t off; int n4;
         slab_info(sidx, off, n4);
-        const uint32_t bytes = (uint32_t)n4 * 16u;
+        const uint32_t bytes = (uint32_t)quarter_f4(n4) * 16u;
+        if (!bytes) return;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-        // chunks of <= 32 KB
-        for (uint32_t done = 0; done < bytes; done += 32768u) {
-            const uint32_t sz = min(32768u, bytes - done);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(slab_a + done), "l"(reinterpret_cast<const char*>(x + off) + done), "r"(sz), "r"(bar_a) : "memory");
-        }
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(slab_a), "l"(reinterpret_cast<const char*>(x + off) + (size_t)quarter * kQuarterF4 * 16u), "r"(bytes), "r"(bar_a) : "memory");
     };
-    if (threadIdx.x == 0) {
+    if (qt == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     int sidx = blockIdx.x;
-    if (threadIdx.x == 0 && sidx < slabs) issue(sidx);
+    if (qt == 0 && sidx < slabs) issue(sidx);
     uint32_t phase = 0;
+    const float4* mine = reinterpret_cast<const float4*>(slab) + quarter * kQuarterF4;
     for (; sidx < slabs; sidx += gridDim.x) {
         size_t off; int n4;
         slab_info(sidx, off, n4);
-        // wait for this slab's bytes
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tGN_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra GN_DONE;\n\tbra GN_WAIT;\n\tGN_DONE:\n\t}"
-            ::"r"(bar_a), "r"(phase) : "memory");
-        phase ^= 1;
+        const int q4 = quarter_f4(n4);
         float4 v[kFastF4];
         float s = 0.f;
+        if (q4 > 0) {
+            // wait for this quarter's bytes
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tGN_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra GN_DONE;\n\tbra GN_WAIT;\n\tGN_DONE:\n\t}"
+                ::"r"(bar_a), "r"(phase) : "memory");
+            phase ^= 1;
+        }
 #pragma unroll
         for (int u = 0; u < kFastF4; ++u) {
-            const int i = threadIdx.x + u * kFastThreads;
-            v[u] = i < n4 ? reinterpret_cast<const float4*>(slab)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int i = qt + u * 256;
+            v[u] = i < q4 ? mine[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
         }
-        __syncthreads();                                   // everyone has left shared memory: refill it
+        // this quarter's eight warps have left it: refill it with the same quarter of the next slab
+        asm volatile("bar.sync %0, 256;" ::"r"(quarter + 1) : "memory");
         const int next = sidx + gridDim.x;
-        if (threadIdx.x == 0 && next < slabs) issue(next);
+        if (qt == 0 && next < slabs) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(next);
+        }
         const float inv_n = 1.f / (float)(4 * n4);
         const float mean = block_total_1024(s, red) * inv_n;
         float q = 0.f;
 #pragma unroll
         for (int u = 0; u < kFastF4; ++u) {
-            const int i = threadIdx.x + u * kFastThreads;
-            if (i < n4) {
+            const int i = qt + u * 256;
+            if (i < q4) {
                 const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
                 q += (a * a + b * b) + (c * c + d * d);
             }
@@ -483,14 +494,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_tma(const floa
             means[sidx] = mean;                            // [img][g] == sidx
             vars[sidx] = p.quirk ? var : denom;
         }
-        float4* ys = reinterpret_cast<float4*>(y + off);
+        float4* ys = reinterpret_cast<float4*>(y + off) + quarter * kQuarterF4;
+        const size_t e0 = off + 4 * (size_t)quarter * kQuarterF4;
 #pragma unroll
         for (int u = 0; u < kFastF4; ++u) {
-            const int i = threadIdx.x + u * kFastThreads;
-            if (i < n4) {
+            const int i = qt + u * 256;
+            if (i < q4) {
                 float4 o;
                 o.x = (v[u].x - mean) / denom; o.y = (v[u].y - mean) / denom; o.z = (v[u].z - mean) / denom; o.w = (v[u].w - mean) / denom;
-                ys[i] = gn_post4(o, off + 4 * (size_t)i, p);
+                ys[i] = gn_post4(o, e0 + 4 * (size_t)i, p);
             }
         }
     }
@@ -623,12 +635,16 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
     extern __shared__ __align__(128) float stage[];        // [x half | dy half], each up to 16384 floats
     __shared__ float red2[2][32];
     __shared__ float slots2[2][2];
-    __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bar[4];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int slabs = p.G * images;
-    const uint32_t bar_a = gn_smem_u32(&bar), st_a = gn_smem_u32(stage);
     constexpr int kHalfFloats = kFastThreads * F4 * 4;     // 16384
+    constexpr int kQF4 = kFastThreads / 4 * F4;            // 1024 float4 of x and of dy per quarter
+    // the CTA's share is cut into four quarters (x and dy pieces side by side in time: one mbarrier per quarter); the eight warps
+    // that own a quarter refill it with the same quarter of the cluster's next slab as soon as they hold it in registers
+    const int quarter = threadIdx.x >> 8, qt = threadIdx.x & 255;
+    const uint32_t bar_a = gn_smem_u32(&bar[quarter]), st_a = gn_smem_u32(stage) + (uint32_t)quarter * kQF4 * 16u;
     int par = 0;
     auto slab_info = [&](int sidx, size_t& off, int& beg, int& end) {
         const int g = sidx % p.G, img = sidx / p.G;
@@ -640,49 +656,56 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
         end = min(n4, beg + per);
         off = ((size_t)img * p.C + c0) * p.HW;
     };
-    auto issue = [&](int sidx) {       // thread 0 only
+    auto quarter_f4 = [&](int beg, int end) { return max(0, min(end - beg - quarter * kQF4, kQF4)); };
+    auto issue = [&](int sidx) {       // one thread per quarter
         size_t off; int beg, end;
         slab_info(sidx, off, beg, end);
-        const uint32_t bytes = (uint32_t)max(0, end - beg) * 16u;
+        const uint32_t bytes = (uint32_t)quarter_f4(beg, end) * 16u;
+        if (!bytes) return;
+        const size_t src = ((size_t)beg + (size_t)quarter * kQF4) * 16;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * bytes) : "memory");
-        for (uint32_t done = 0; done < bytes; done += 32768u) {
-            const uint32_t sz = min(32768u, bytes - done);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(st_a + done), "l"(reinterpret_cast<const char*>(x + off) + (size_t)beg * 16 + done), "r"(sz), "r"(bar_a) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(st_a + (uint32_t)kHalfFloats * 4u + done), "l"(reinterpret_cast<const char*>(dy + off) + (size_t)beg * 16 + done),
-                           "r"(sz), "r"(bar_a) : "memory");
-        }
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(st_a), "l"(reinterpret_cast<const char*>(x + off) + src), "r"(bytes), "r"(bar_a) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(st_a + (uint32_t)kHalfFloats * 4u), "l"(reinterpret_cast<const char*>(dy + off) + src), "r"(bytes), "r"(bar_a) : "memory");
     };
-    if (threadIdx.x == 0) {
+    if (qt == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
     int sidx = cid;
-    if (threadIdx.x == 0 && sidx < slabs) issue(sidx);
+    if (qt == 0 && sidx < slabs) issue(sidx);
     uint32_t phase = 0;
+    const float4* xq = reinterpret_cast<const float4*>(stage) + quarter * kQF4;
+    const float4* dq = reinterpret_cast<const float4*>(stage + kHalfFloats) + quarter * kQF4;
     for (; sidx < slabs; sidx += ncl) {
         size_t off; int beg, end;
         slab_info(sidx, off, beg, end);
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tGNB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra GNB_DONE;\n\tbra GNB_WAIT;\n\tGNB_DONE:\n\t}"
-            ::"r"(bar_a), "r"(phase) : "memory");
-        phase ^= 1;
+        const int q4 = quarter_f4(beg, end);
+        if (q4 > 0) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tGNB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra GNB_DONE;\n\tbra GNB_WAIT;\n\tGNB_DONE:\n\t}"
+                ::"r"(bar_a), "r"(phase) : "memory");
+            phase ^= 1;
+        }
         const float mu = means[sidx], sd = stdevs[sidx];
+        const int qbeg = beg + quarter * kQF4;                 // slab float4 index of this quarter's first element
         float4 w[F4], d[F4];
 #pragma unroll
         for (int u = 0; u < F4; ++u) {
-            const int i = threadIdx.x + u * kFastThreads;
-            const bool ok = beg + i < end;
-            w[u] = ok ? reinterpret_cast<const float4*>(stage)[i] : make_float4(mu, mu, mu, mu);
-            d[u] = ok ? gn_gate4(reinterpret_cast<const float4*>(stage + kHalfFloats)[i], w[u], mu, off + 4 * (size_t)(beg + i), p)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int i = qt + u * 256;
+            const bool ok = i < q4;
+            w[u] = ok ? xq[i] : make_float4(mu, mu, mu, mu);
+            d[u] = ok ? gn_gate4(dq[i], w[u], mu, off + 4 * (size_t)(qbeg + i), p) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncthreads();                                   // shared memory is free again: prefetch the next slab
+        asm volatile("bar.sync %0, 256;" ::"r"(quarter + 1) : "memory");   // this quarter is free again: prefetch the next slab's
         const int next = sidx + ncl;
-        if (threadIdx.x == 0 && next < slabs) issue(next);
+        if (qt == 0 && next < slabs) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(next);
+        }
         float gs = 0.f, gw = 0.f;
 #pragma unroll
         for (int u = 0; u < F4; ++u) {
@@ -710,15 +733,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
         const int nc = min(p.group_size, p.C - g * p.group_size);
         const float inv_n = 1.f / (float)(nc * p.HW);
         const float mean_g = tot[0] * inv_n, mean_gw = tot[1] * inv_n;
-        float4* ds = reinterpret_cast<float4*>(dx + off) + beg;
+        float4* ds = reinterpret_cast<float4*>(dx + off) + qbeg;
 #pragma unroll
         for (int u = 0; u < F4; ++u) {
-            const int i = threadIdx.x + u * kFastThreads;
-            if (beg + i < end) {
+            const int i = qt + u * 256;
+            if (i < q4) {
                 float4 o;
                 o.x = (d[u].x - mean_g - w[u].x * mean_gw) / sd; o.y = (d[u].y - mean_g - w[u].y * mean_gw) / sd;
                 o.z = (d[u].z - mean_g - w[u].z * mean_gw) / sd; o.w = (d[u].w - mean_g - w[u].w * mean_gw) / sd;
-                ds[i] = gn_add4(o, off + 4 * (size_t)(beg + i), p);
+                ds[i] = gn_add4(o, off + 4 * (size_t)(qbeg + i), p);
             }
         }
     }
