@@ -634,8 +634,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
     constexpr int F4 = 4;                                  // float4 per thread per tensor: 2 CTAs x 1024 x 4 x 4 = 32768 elements
     extern __shared__ __align__(128) float stage[];        // [x half | dy half], each up to 16384 floats
     __shared__ float red2[2][32];
-    __shared__ float slots2[2][2];
+    __shared__ __align__(16) float inbox[2][2][2];         // [parity][source CTA][sum]: delivered by st.async, see the loop
     __shared__ __align__(8) unsigned long long bar[4];
+    __shared__ __align__(8) unsigned long long xbar[2];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int slabs = p.G * images;
@@ -671,9 +672,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
     };
     if (qt == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        if (quarter < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gn_smem_u32(&xbar[quarter])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    int it = 0;                                            // slabs done: inbox / xbar [it & 1], in phase (it >> 1) & 1
+    cluster.sync();                                        // the peer's xbar is initialised before anything is delivered to it
     const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
     int sidx = cid;
     if (qt == 0 && sidx < slabs) issue(sidx);
@@ -713,9 +716,13 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
             gs += (d[u].x + d[u].y) + (d[u].z + d[u].w);
             gw += (w[u].x * d[u].x + w[u].y * d[u].y) + (w[u].z * d[u].z + w[u].w * d[u].w);
         }
-        // CTA totals of both sums in ONE shuffle + shared-memory pass -> slots, exchanged through DSMEM (same summation order in
-        // both CTAs).  The slots alternate between two pairs: a CTA can be at most one cluster barrier ahead of its peer, so
-        // the pair written in iteration k+2 has been read by the peer in iteration k -- one cluster barrier per slab, not two.
+        // CTA totals of both sums in ONE shuffle + shared-memory pass.  Lane 0 of warp k (k = 0: sum dy, 1: sum w.dy) then DELIVERS its
+        // total into inbox[par][rank][k] of BOTH CTAs of the cluster with st.async, which completes 4 bytes on the receiving CTA's
+        // mbarrier xbar[par]: every thread waits for the 16 bytes of its own CTA's inbox and adds the two CTAs' totals in rank order
+        // (same bits in both).  No cluster barrier and no release fence in the loop -- round 2's barrier.cluster.arrive.release made
+        // all 1024 threads wait for their dx stores of the slab before to drain (ncu: 16 % of the kernel's stall samples on that one
+        // ERRBAR / UCGABAR_ARV pair).  The inboxes alternate: a CTA can be at most one slab ahead of its peer (it needs the peer's
+        // totals of slab k to leave slab k), so inbox[par] is rewritten only after both CTAs have read it two slabs earlier.
         float tot[2];
         gs = warp_sum(gs); gw = warp_sum(gw);
         if ((threadIdx.x & 31) == 0) { red2[0][threadIdx.x >> 5] = gs; red2[1][threadIdx.x >> 5] = gw; }
@@ -723,11 +730,26 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
         if (threadIdx.x < 64) {
             float v = red2[threadIdx.x >> 5][threadIdx.x & 31];
             v = warp_sum(v);
-            if ((threadIdx.x & 31) == 0) slots2[par][threadIdx.x >> 5] = v;
+            if ((threadIdx.x & 31) == 0) {
+                const int k = threadIdx.x >> 5;
+                if (k == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gn_smem_u32(&xbar[par])), "r"(16u) : "memory");
+                const uint32_t slot = gn_smem_u32(&inbox[par][rank][k]), bar_l = gn_smem_u32(&xbar[par]);
+#pragma unroll
+                for (uint32_t dst = 0; dst < 2; ++dst) {
+                    uint32_t slot_c, bar_c;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(slot_c) : "r"(slot), "r"(dst));
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar_c) : "r"(bar_l), "r"(dst));
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                                 ::"r"(slot_c), "r"(__float_as_uint(v)), "r"(bar_c) : "memory");
+                }
+            }
         }
-        cluster.sync();
-        tot[0] = *cluster.map_shared_rank(&slots2[par][0], 0) + *cluster.map_shared_rank(&slots2[par][0], 1);
-        tot[1] = *cluster.map_shared_rank(&slots2[par][1], 0) + *cluster.map_shared_rank(&slots2[par][1], 1);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tGNX_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra GNX_DONE;\n\tbra GNX_WAIT;\n\tGNX_DONE:\n\t}"
+            ::"r"(gn_smem_u32(&xbar[par])), "r"((uint32_t)(it >> 1) & 1u) : "memory");
+        ++it;
+        tot[0] = *(volatile float*)&inbox[par][0][0] + *(volatile float*)&inbox[par][1][0];
+        tot[1] = *(volatile float*)&inbox[par][0][1] + *(volatile float*)&inbox[par][1][1];
         par ^= 1;
         const int g = sidx % p.G;
         const int nc = min(p.group_size, p.C - g * p.group_size);

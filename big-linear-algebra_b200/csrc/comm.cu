@@ -90,14 +90,16 @@ void comm_group_end() { ok(g.GroupEnd(), "ncclGroupEnd"); }
 // Every rank owns a window of device memory (cudaMalloc, exported with cudaIpcGetMemHandle, the handles all-gathered through the
 // NCCL communicator once) that every other rank maps.  Window = flag block + 2 (parity) x world (source rank) data slots.
 // Kernel, per CTA c -- a CTA only ever talks to CTA c of the other ranks, there is no grid-wide step:
-//   1. epoch = my counter[c] + 1 (device memory: the kernel can be replayed from a CUDA graph with unchanged arguments)
-//   2. PUSH my slice c of the source buffer into slot [epoch & 1][my rank] of every peer's window (posted NVLink writes)
+//   1. epoch = my counter[c] + 1, parity = low bit of the window's call counter (both in device memory: the kernel can be replayed
+//      from a CUDA graph with unchanged arguments)
+//   2. PUSH my slice c of the source buffer into slot [parity][my rank] of every peer's window (posted NVLink writes)
 //   3. fence, then store `epoch` into flag [my rank][c] of every peer
 //   4. wait until flag [r][c] >= epoch for every peer r in MY window: their slices have landed in my HBM
 //   5. sum the world contributions in RANK ORDER (mine from the source buffer, the peers' from my window, L2-coherent loads):
 //      every rank computes the same bits; the sum goes to dst, or straight into the parameters (params += alpha * sum)
-// Slot reuse needs no second handshake: slot [p] is rewritten two epochs later, and a peer cannot be two epochs behind -- it posted
-// the flag of epoch e - 1 that this rank waited for, after its kernel of epoch e - 2 (the last reader of the slot) had finished.
+// Slot reuse needs no second handshake: slot [p] is rewritten two CALLS later, and a peer cannot be two calls behind -- it posted
+// the flags of call k - 1 that this rank waited for, after its kernel of call k - 2 (the last reader of the slot) had finished.  The
+// parity is per call, not per CTA, so calls of different sizes (different grids) may follow each other.
 // Waits are bounded (~4 s): a rank that never arrives raises the window's error word and the CTA leaves dst / the parameters
 // untouched; comm_peer_failed() reports it to the host.
 // ------------------------------------------------------------------------------------------------------------------------
@@ -114,7 +116,7 @@ struct PeerState {
     bool enabled = true;                     // bla_comm_set_peer_windows(0): keep the windows, route the all-reduces through NCCL
     size_t floats = 0;                       // capacity of one data slot, in floats
     char* base[kMaxPeers] = {nullptr};       // every rank's window as mapped here (base[rank] is the local allocation)
-    unsigned long long* counters = nullptr;  // [kPeerCtas] local epoch of every CTA index
+    unsigned long long* counters = nullptr;  // [kPeerCtas] last flag value of every CTA index, [kPeerCtas] calls so far, [kPeerCtas + 1] end-of-call ticket
 } peer;
 
 struct PeerArgs {
@@ -143,10 +145,55 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// 3. fence + announce `value` in flag [my rank][c] of every peer, 4. wait for flag [r][c] >= value of every peer r in MY window.
+// Returns false after the bounded wait (~4 s) gave up on a peer: the window's error word is raised, the caller leaves its
+// destination untouched but still advances its counters so that the ranks stay in step.
+__device__ __forceinline__ bool peer_handshake(const PeerArgs& a, int c, int t, unsigned long long value, int* failed) {
+    __threadfence_system();
+    if (t == 0) *failed = 0;
+    __syncthreads();
+    if (t < a.world && t != a.rank) {
+        __threadfence_system();
+        st_release_sys(a.flag_out[t] + c, value);
+        const unsigned long long* f = a.flag_in + (size_t)t * kPeerCtas + c;
+        long spins = 0;
+        while (ld_acquire_sys(f) < value) {
+            if (++spins > 2000) __nanosleep(200);
+            if (spins > 20000000L) { atomicExch(a.error, 1u); *failed = 1; break; }
+        }
+    }
+    __syncthreads();
+    return *failed == 0;
+}
+// End of a call, thread 0 of every CTA: the CTA's flag counter, and -- by the last CTA to get here -- the call counter whose low bit
+// is the slot parity of the NEXT call (read by every CTA of that call at its start: the kernels of one stream do not overlap).
+__device__ __forceinline__ void peer_finish(const PeerArgs& a, int c, unsigned long long flag_value, unsigned long long call) {
+    a.counters[c] = flag_value;
+    __threadfence();
+    unsigned long long* calls = a.counters + kPeerCtas;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(a.counters + kPeerCtas + 1);
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        *ticket = 0u;
+        *calls = call + 1;
+    }
+}
+__device__ __forceinline__ void peer_apply(const PeerArgs& a, float4* dst4, size_t i, const float4& acc) {
+    if (a.fused) {
+        float4 p = dst4[i];
+        p.x = fmaf(a.alpha, acc.x, p.x); p.y = fmaf(a.alpha, acc.y, p.y); p.z = fmaf(a.alpha, acc.z, p.z); p.w = fmaf(a.alpha, acc.w, p.w);
+        dst4[i] = p;
+    } else {
+        dst4[i] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(PeerArgs a) {
     const int c = blockIdx.x, t = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     const unsigned long long epoch = a.counters[c] + 1;
-    const size_t par_off = (epoch & 1ull) * (size_t)a.world * a.slot_floats;
+    const unsigned long long call = *reinterpret_cast<volatile unsigned long long*>(a.counters + kPeerCtas);
+    const size_t par_off = (call & 1ull) * (size_t)a.world * a.slot_floats;
     const size_t per = (a.n4 + gridDim.x - 1) / gridDim.x;
     const size_t beg = (size_t)c * per, end = beg + per < a.n4 ? beg + per : a.n4;
     const float4* src4 = reinterpret_cast<const float4*>(a.src);
@@ -157,26 +204,8 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(PeerArgs a
         for (int r = 0; r < kMaxPeers; ++r)
             if (r < a.world && r != a.rank) reinterpret_cast<float4*>(a.slot[r] + par_off)[a.offset4 + i] = v;
     }
-    __threadfence_system();
-    __syncthreads();
-    // 3. announce, 4. wait
     __shared__ int failed;
-    if (t == 0) failed = 0;
-    if (t < a.world && t != a.rank) {
-        __threadfence_system();
-        st_release_sys(a.flag_out[t] + c, epoch);
-    }
-    __syncthreads();
-    if (t < a.world && t != a.rank) {
-        const unsigned long long* f = a.flag_in + (size_t)t * kPeerCtas + c;
-        long spins = 0;
-        while (ld_acquire_sys(f) < epoch) {
-            if (++spins > 2000) __nanosleep(200);
-            if (spins > 20000000L) { atomicExch(a.error, 1u); failed = 1; break; }
-        }
-    }
-    __syncthreads();
-    if (!failed) {
+    if (peer_handshake(a, c, t, epoch, &failed)) {
         // 5. sum in rank order
         const float4* in4 = reinterpret_cast<const float4*>(a.data_in + par_off);
         const size_t slot4 = a.slot_floats / 4;
@@ -190,16 +219,73 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(PeerArgs a
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                 }
             }
-            if (a.fused) {
-                float4 p = dst4[i];
-                p.x = fmaf(a.alpha, acc.x, p.x); p.y = fmaf(a.alpha, acc.y, p.y); p.z = fmaf(a.alpha, acc.z, p.z); p.w = fmaf(a.alpha, acc.w, p.w);
-                dst4[i] = p;
-            } else {
-                dst4[i] = acc;
+            peer_apply(a, dst4, i, acc);
+        }
+    }
+    if (t == 0) peer_finish(a, c, epoch, call);   // the flags of this call are out: also after a timeout, so that the ranks stay in step
+}
+
+// The same exchange in TWO rounds for larger buffers on >= 4 ranks: reduce-scatter, then all-gather.  The one-round kernel moves
+// (world - 1) x n floats out of and into every GPU (6.6 MB for the MLP's gradient on 8 ranks: 34 us measured, most of it transfer);
+// here the buffer is cut into `world` owner segments, every rank sends each owner only that owner's segment, the owner adds the
+// world contributions in rank order and sends the SUM back to everybody: 2 x (world - 1) / world x n floats per GPU, a quarter of
+// the bytes at 8 ranks, for one more flag round.  Every rank applies the owner's bits: identical results on all ranks.
+// CTA c handles piece c of EVERY segment, so as before it only ever talks to CTA c of the other ranks.
+__global__ void __launch_bounds__(kPeerThreads) peer_allreduce_two_round_kernel(PeerArgs a) {
+    const int c = blockIdx.x, t = threadIdx.x, world = a.world, me = a.rank;
+    pdl_trigger();
+    pdl_wait();
+    const unsigned long long f1 = a.counters[c] + 1, f2 = f1 + 1;
+    const unsigned long long call = *reinterpret_cast<volatile unsigned long long*>(a.counters + kPeerCtas);
+    const size_t par_off = (call & 1ull) * (size_t)world * a.slot_floats;
+    const size_t seg4 = (a.n4 + world - 1) / world;                       // float4 per owner segment
+    const size_t per = (seg4 + gridDim.x - 1) / gridDim.x;
+    const size_t qb = (size_t)c * per, qe = qb + per < seg4 ? qb + per : seg4;
+    const float4* src4 = reinterpret_cast<const float4*>(a.src);
+    const float4* in4 = reinterpret_cast<const float4*>(a.data_in + par_off);
+    const size_t slot4 = a.slot_floats / 4;
+    float4* dst4 = reinterpret_cast<float4*>(a.dst);
+    // round 1: my values of owner r's segment -> slot [me] of r's window, at the element's own position
+    for (size_t q = qb + t; q < qe; q += kPeerThreads) {
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+            const size_t g = (size_t)r * seg4 + q;
+            if (r < world && r != me && g < a.n4) reinterpret_cast<float4*>(a.slot[r] + par_off)[a.offset4 + g] = src4[g];
+        }
+    }
+    __shared__ int failed[2];   // one word per round: the second round's reset must not race with late readers of the first
+    bool ok = peer_handshake(a, c, t, f1, &failed[0]);
+    if (ok) {
+        // my segment: rank-ordered sum, applied here and sent to everybody (slot [me] of their windows, my segment's positions)
+        for (size_t q = qb + t; q < qe; q += kPeerThreads) {
+            const size_t g = (size_t)me * seg4 + q;
+            if (g >= a.n4) break;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r) {
+                if (r < world) {
+                    const float4 v = r == me ? src4[g] : __ldcg(in4 + (size_t)r * slot4 + a.offset4 + g);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r)
+                if (r < world && r != me) reinterpret_cast<float4*>(a.slot[r] + par_off)[a.offset4 + g] = acc;
+            peer_apply(a, dst4, g, acc);
+        }
+    }
+    ok = peer_handshake(a, c, t, f2, &failed[1]) && ok;
+    if (ok) {
+        // round 2: the other owners' sums have landed in my window
+        for (size_t q = qb + t; q < qe; q += kPeerThreads) {
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r) {
+                const size_t g = (size_t)r * seg4 + q;
+                if (r < world && r != me && g < a.n4) peer_apply(a, dst4, g, __ldcg(in4 + (size_t)r * slot4 + a.offset4 + g));
             }
         }
     }
-    if (t == 0) a.counters[c] = epoch;       // the flags of this epoch are out: also after a timeout, so that the ranks stay in step
+    if (t == 0) peer_finish(a, c, f2, call);
 }
 
 void peer_release() {
@@ -231,8 +317,8 @@ bool peer_setup(size_t floats) {
     cudaIpcMemHandle_t handle;
     memset(&handle, 0, sizeof(handle));
     if (cudaMalloc((void**)&mine, bytes) != cudaSuccess || cudaMemset(mine, 0, kFlagBytes) != cudaSuccess ||
-        cudaIpcGetMemHandle(&handle, mine) != cudaSuccess || cudaMalloc((void**)&peer.counters, kPeerCtas * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(peer.counters, 0, kPeerCtas * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaIpcGetMemHandle(&handle, mine) != cudaSuccess || cudaMalloc((void**)&peer.counters, (kPeerCtas + 2) * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(peer.counters, 0, (kPeerCtas + 2) * sizeof(unsigned long long)) != cudaSuccess) {
         cudaGetLastError();
         good = 0;
     }
@@ -311,11 +397,20 @@ void comm_peer_allreduce_f32(const float* src, float* dst, float alpha, bool fus
     a.src = src; a.dst = dst; a.alpha = alpha; a.fused = fused ? 1 : 0;
     a.n4 = n / 4; a.offset4 = offset / 4; a.slot_floats = peer.floats;
     a.world = g.world; a.rank = g.rank;
-    // the same grid on every rank (it only depends on n): ~512 float4 per CTA
-    int ctas = (int)std::min<size_t>(kPeerCtas, (a.n4 + 511) / 512);
-    if (ctas < 1) ctas = 1;
-    peer_allreduce_kernel<<<ctas, kPeerThreads, 0, s>>>(a);
-    BLA_LAUNCH_CHECK();
+    // kernel and grid depend on (world, n, BLA_PEER_TWO_ROUNDS) only: the same on every rank
+    static int two_env = -2;
+    if (two_env == -2) { const char* e = getenv("BLA_PEER_TWO_ROUNDS"); two_env = e ? atoi(e) : -1; }
+    const bool two = two_env >= 0 ? (two_env != 0 && g.world >= 2) : (g.world >= 4 && n >= 65536);
+    if (two) {
+        const size_t seg4 = (a.n4 + g.world - 1) / g.world;
+        int ctas = (int)std::min<size_t>(kPeerCtas, (seg4 + 127) / 128);
+        if (ctas < 1) ctas = 1;
+        BLA_CUDA(launch_pdl(peer_allreduce_two_round_kernel, dim3(ctas), dim3(kPeerThreads), 0, s, 1, a));
+    } else {
+        int ctas = (int)std::min<size_t>(kPeerCtas, (a.n4 + 511) / 512);   // ~512 float4 per CTA
+        if (ctas < 1) ctas = 1;
+        BLA_CUDA(launch_pdl(peer_allreduce_kernel, dim3(ctas), dim3(kPeerThreads), 0, s, 1, a));
+    }
     count_launch();
 }
 // true if a peer never arrived in some all-reduce since the last check (that call left its destination untouched); clears the word

@@ -21,6 +21,8 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 // out[i] = op(x[i], y[i]); out may alias x.  NIN = number of inputs actually read (1 or 2).
 template <int NIN, class Op>
 __global__ void __launch_bounds__(kThreads) ew_vec_kernel(float* out, const float* x, const float* y, size_t n, Op op) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     const size_t n4 = n >> 2;
     const size_t stride = (size_t)gridDim.x * kThreads;
     size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -56,6 +58,8 @@ __global__ void __launch_bounds__(kThreads) ew_vec_kernel(float* out, const floa
 // fallback for pointers that are not 16-byte aligned (interior pointers such as buffer + 1)
 template <int NIN, class Op>
 __global__ void __launch_bounds__(kThreads) ew_scalar_kernel(float* out, const float* x, const float* y, size_t n, Op op) {
+    pdl_trigger();
+    pdl_wait();
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) out[i] = op(x[i], NIN == 2 ? y[i] : 0.f);
 }
@@ -75,11 +79,10 @@ void launch_ew(float* out, const float* x, const float* y, size_t n, Op op, cuda
     if (n == 0) return;
     bool vec = aligned16(out) && aligned16(x) && (NIN == 1 || aligned16(y));
     if (vec) {
-        ew_vec_kernel<NIN, Op><<<grid_for(n >> 2 ? n >> 2 : 1, kUnroll), kThreads, 0, s>>>(out, x, y, n, op);
+        BLA_CUDA(launch_pdl(ew_vec_kernel<NIN, Op>, dim3(grid_for(n >> 2 ? n >> 2 : 1, kUnroll)), dim3(kThreads), 0, s, 1, out, x, y, n, op));
     } else {
-        ew_scalar_kernel<NIN, Op><<<grid_for(n, 4), kThreads, 0, s>>>(out, x, y, n, op);
+        BLA_CUDA(launch_pdl(ew_scalar_kernel<NIN, Op>, dim3(grid_for(n, 4)), dim3(kThreads), 0, s, 1, out, x, y, n, op));
     }
-    BLA_LAUNCH_CHECK();
     count_launch();
 }
 

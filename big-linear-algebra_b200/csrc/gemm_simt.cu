@@ -285,6 +285,11 @@ void gemm_simt(const GemmArgs& g, cudaStream_t s) {
         if (splits > 128) splits = 128;
         if (splits < 1) splits = 1;
     }
+    const bool own_ws = g.workspace != nullptr;   // a GEMM beside the library stream: the caller's scratch, never the pool
+    if (own_ws && (size_t)g.m * g.n > 0) {
+        const long long fit = (long long)(g.workspace_floats / ((size_t)g.m * g.n));
+        if (splits > fit) splits = fit < 1 ? 1 : (int)fit;
+    }
     float* ws = nullptr;
     if (splits > 1) {
         int chunk = ceil_div(g.k, splits);
@@ -292,7 +297,7 @@ void gemm_simt(const GemmArgs& g, cudaStream_t s) {
         splits = ceil_div(g.k, chunk);
         p.k_chunk = chunk;
         if (splits > 1) {
-            ws = (float*)pool_alloc(kDevice, (size_t)splits * g.m * g.n * sizeof(float));
+            ws = own_ws ? g.workspace : (float*)pool_alloc(kDevice, (size_t)splits * g.m * g.n * sizeof(float));
             p.partial = ws;
         }
     }
@@ -308,7 +313,7 @@ void gemm_simt(const GemmArgs& g, cudaStream_t s) {
         splitk_reduce_kernel<<<(int)blocks, kThreads, 0, s>>>(p, splits);
         BLA_LAUNCH_CHECK();
         count_launch();
-        pool_free(ws);   // stream-ordered reuse: the pool only serves this one stream
+        if (!own_ws) pool_free(ws);   // stream-ordered reuse: the pool only serves this one stream
     }
 }
 

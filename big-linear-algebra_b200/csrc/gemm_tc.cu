@@ -319,6 +319,10 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    // Programmatic dependent launch (runtime.h): everything above touched only shared memory, TMEM and the kernel parameters, and may
+    // have run while the previous kernel of the stream was still draining; from here on global memory is read and written.
+    pdl_trigger();
+    pdl_wait();
 
     // Work units.  cluster == 1: a unit is one 128 x bn tile.  cluster == 2: a unit is a 256 x bn tile computed by a CTA
     // PAIR with tcgen05.mma.cta_group::2: CTA r owns rows 128r.. (its own A tile and TMEM accumulator) and stages only
@@ -828,6 +832,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 // sums split-K partials in a fixed order and applies the epilogue.  Block = 64 float4 columns x 4 split groups:
 // every thread keeps 8 independent 128-bit loads in flight, the four group sums are combined through shared memory.
 __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p) {
+    pdl_trigger();
+    pdl_wait();   // launched with programmatic serialisation right behind the GEMM whose partials it folds
     const size_t total = (size_t)p.m * p.n;
     if ((total & 3) == 0 && (p.n & 3) == 0 && (p.c_vec || p.conv == 1 || p.cv_final)) {
         __shared__ float4 part[4][64];
@@ -1233,8 +1239,10 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     splits = ceil_div(p.kblocks, p.kblocks_per_split);
     p.splits = splits;
     float* ws = nullptr;
+    const bool own_ws = g.workspace != nullptr;   // the caller's scratch (a GEMM beside the library stream), never the pool then
+    if (own_ws && splits > 1 && (size_t)splits * g.m * g.n > g.workspace_floats) return false;
     if (splits > 1) {
-        ws = (float*)pool_alloc(kDevice, (size_t)splits * g.m * g.n * sizeof(float));
+        ws = own_ws ? g.workspace : (float*)pool_alloc(kDevice, (size_t)splits * g.m * g.n * sizeof(float));
         p.partial = ws;
         if (cmode == 2 && g.conv->dw_final && g.n % 4 == 0) {
             p.cv_final = 1; p.cv_Creal = g.conv->C_real; p.c = g.conv->dw_final;
@@ -1253,10 +1261,10 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     if (!p.tma_store) p.gate_bits = nullptr;   // the register-store epilogue reads the float gate
     if (cmode == 1 && splits == 1) {
         p.tma_store = make_map_conv_out(&mc, *g.conv);
-        if (!p.tma_store) { if (ws) pool_free(ws); return false; }
+        if (!p.tma_store) { if (ws && !own_ws) pool_free(ws); return false; }
     } else if (cmode == 1) {   // split-K partials [splits][F][imgs*P] (F a multiple of 128 here); the reduce kernel writes y
         p.tma_store = make_map_c(&mc, ws, (long long)splits * g.m, g.n, g.n);
-        if (!p.tma_store) { if (ws) pool_free(ws); return false; }
+        if (!p.tma_store) { if (ws && !own_ws) pool_free(ws); return false; }
     } else if (p.tma_store) {
         p.tma_store = splits == 1 ? make_map_c(&mc, g.c, g.m, g.n, g.ldc) : make_map_c(&mc, ws, (long long)splits * g.m, g.n, g.n);
     }
@@ -1268,7 +1276,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         if (e != cudaSuccess) {
             cudaGetLastError();
             g_tc_broken = true;
-            if (ws) pool_free(ws);
+            if (ws && !own_ws) pool_free(ws);
             return false;
         }
         attr_set = true;
@@ -1276,24 +1284,8 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     const long long units = tiles / p.cluster * splits;
     const int slots = sms / p.cluster;
     const int grid = (int)(units < slots ? units : slots) * p.cluster;
-    if (p.cluster == 1) {
-        gemm_3xtf32_kernel<1><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, mc, p);
-        BLA_LAUNCH_CHECK();
-    } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = kSmemBytes;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        BLA_CUDA(cudaLaunchKernelEx(&cfg, gemm_3xtf32_kernel<2>, ma, mb, mc, p));
-    }
+    if (p.cluster == 1) BLA_CUDA(launch_pdl(gemm_3xtf32_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, s, 1, ma, mb, mc, p));
+    else BLA_CUDA(launch_pdl(gemm_3xtf32_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, s, 2, ma, mb, mc, p));
     count_launch();
     ++g_tc_launches;
     if (ws) {
@@ -1301,10 +1293,9 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
         size_t blocks = (totalc / 4 + 63) / 64;   // 64 float4 columns per block on the vector path
         size_t cap = (size_t)sms * 8;
         if (blocks > cap) blocks = cap;
-        tc_splitk_reduce_kernel<<<(int)blocks, 256, 0, s>>>(p);
-        BLA_LAUNCH_CHECK();
+        BLA_CUDA(launch_pdl(tc_splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, s, 1, p));
         count_launch();
-        pool_free(ws);
+        if (!own_ws) pool_free(ws);
     }
     return true;
 }

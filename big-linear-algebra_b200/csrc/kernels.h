@@ -66,6 +66,10 @@ struct GemmArgs {
     //              still be set: it is what every other path reads)
     uint32_t* mask_out; int mask_ld; bool* mask_written;
     const uint32_t* gate_bits; int gate_ld;
+    // Split-K partial sums normally come from the stream-ordered pool, which serves ONE stream: a GEMM issued on a second stream that
+    // runs beside the library stream brings its own scratch; the pool is then never touched (the tensor path declines a split that
+    // does not fit and the FP32 kernel takes fewer slices).
+    float* workspace; size_t workspace_floats;
     bool no_tail_split;   // internal: this call already is one half of a main / tail column split (gemm_tc.cu)
     int* plan_main_columns;   // query only: receives the column count of the first launch (n when there is no split); nothing runs
 };

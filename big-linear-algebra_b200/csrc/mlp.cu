@@ -54,6 +54,9 @@ struct bla_mlp {
     cudaEvent_t ev_l1, ev_rest, ev_comm;   // ordering between the compute stream and the collective stream
     cudaStream_t side;                     // bias-gradient window sums run here, next to the wgrad GEMMs
     cudaEvent_t ev_fork, ev_join;
+    cudaStream_t side2;                    // the layer-2 weight gradient runs here, beside the layer-1 dgrad / wgrad chain (both only need dZ2)
+    cudaEvent_t ev_fork2, ev_join2;
+    float* ws2;                            // its split-K scratch (the pool serves the library stream only): 64 slices of [n2 x n1]
     // host batches in column chunks: chunk i+1 crosses PCIe on `copy` while chunk i is trained on the compute stream
     static constexpr int kMaxChunks = 16;
     int chunk_cols;                        // < 0: automatic (pinned host batches only), 0: off, > 0: forced chunk width
@@ -256,6 +259,8 @@ __global__ void __launch_bounds__(256, 3) head_train_kernel(const float* __restr
     float* w_s = a_s + (size_t)hidden * kHeadPitch;           // [hidden][NCP]   w_s[k][r] = W3[r][k]
     float* d_s = w_s + (size_t)hidden * NCP;                  // [kHeadCols][NCP] dZ3 of the tile
     float* part = d_s + kHeadCols * NCP;                      // [3][kHeadCols][NC + 1] partial logits of k groups 1..3
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation behind the layer-2 GEMM (W3 too may still be in the update's flight)
     for (int e = threadIdx.x; e < hidden * NCP; e += 256) {
         const int k = e / NCP, r = e % NCP;
         w_s[e] = r < NC ? W3[(size_t)r * hidden + k] : 0.f;
@@ -489,7 +494,7 @@ void head_forward(bla_mlp* m, const float* y, int B, float* dz, float* probs, cu
 
 // the training step's output layer: one pass over A2 gives dZ3 (into z3), dZ2, the loss statistics and one dW3 partial per CTA,
 // which a second small launch folds in a fixed order                                              model/mnist_nn.c:231-278
-void head_train(bla_mlp* m, const float* y, int B, cudaStream_t s) {
+int head_train(bla_mlp* m, const float* y, int B, cudaStream_t s) {
     const int n2 = m->n[2], n3 = m->n[3], ncp = (n3 + 3) / 4 * 4;
     int ctas = ceil_div(B, kHeadCols);
     const int cap = std::min(m->head_ctas, rt().num_sms * 3);
@@ -501,13 +506,18 @@ void head_train(bla_mlp* m, const float* y, int B, cudaStream_t s) {
             BLA_CUDA(cudaFuncSetAttribute(head_train_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             attr_done[NC] = true;
         }
-        head_train_kernel<NC><<<ctas, 256, smem, s>>>(W(m, 2), Bv(m, 2), m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2,
-                                                      m->head_partial, m->stats);
+        BLA_CUDA(launch_pdl(head_train_kernel<NC>, dim3(ctas), dim3(256), smem, s, 1, (const float*)W(m, 2), (const float*)Bv(m, 2),
+                            (const float*)m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2, m->head_partial, m->stats));
     });
+    count_launch();
+    return ctas;
+}
+// dW3 = the fixed-order sum of the head kernel's per-CTA partials                                 model/mnist_nn.c:266-270
+void head_wgrad_fold(bla_mlp* m, int parts, cudaStream_t s) {
+    const int n2 = m->n[2], n3 = m->n[3];
+    head_wgrad_reduce_kernel<<<ceil_div(n3 * n2, 8), 256, 0, s>>>(m->head_partial, parts, n3 * n2, dW(m, 2));
     BLA_LAUNCH_CHECK();
-    head_wgrad_reduce_kernel<<<ceil_div(n3 * n2, 8), 256, 0, s>>>(m->head_partial, ctas, n3 * n2, dW(m, 2));   // :266-270
-    BLA_LAUNCH_CHECK();
-    count_launch(2);
+    count_launch();
 }
 
 void forward(bla_mlp* m, const float* x, float x_scale, int B, cudaStream_t s, bool with_head = true) {
@@ -548,15 +558,28 @@ void reduce_grads(bla_mlp* m, size_t off, size_t n, float lr, cudaStream_t cs) {
     else comm_allreduce_f32_on(m->grads + off, n, cs);
 }
 
+// Programmatic dependent launches are suspended inside the step (they lose here: runtime.h); BLA_MLP_PDL=1 keeps them, for A/B runs.
+struct StepPdlOff {
+    PdlOff* off;
+    StepPdlOff() {
+        static int keep = -1;
+        if (keep < 0) { const char* e = getenv("BLA_MLP_PDL"); keep = e ? atoi(e) : 0; }
+        off = keep ? nullptr : new PdlOff;
+    }
+    ~StepPdlOff() { delete off; }
+};
+
 // forward + backward of columns [c0, c0 + B) of a Bg-column batch: gradients into m->grads (all-reduced when `reduce` and a
 // communicator is active), loss / accuracy added to m->stats
 void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, bool reduce, float lr) {
     cudaStream_t s = rt().stream;
     const int quirk = rt().quirks;
     const bool skinny = skinny_head(m, B);
+    StepPdlOff pdl_guard;
     forward(m, x, x_scale, B, s, !skinny);
     // A3 = softmax(Z3); loss / accuracy; dZ3 = (A3 - Y) / 784 (in place over Z3)      :234-268
-    if (skinny) head_train(m, y, B, s);               // + dZ2 and dW3: A2 is read once (:231-278)
+    int head_parts = 0;
+    if (skinny) head_parts = head_train(m, y, B, s);  // + dZ2 and dW3 partials: A2 is read once (:231-278)
     else k_softmax_xent(m->z3, y, m->n[3], B, nullptr, m->z3, (float)(1.0 / (double)m->n[0]), m->stats, s);
     const float* dz3 = m->z3;
 
@@ -572,14 +595,15 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
         BLA_CUDA(cudaEventRecord(m->ev_join, m->side));
         BLA_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
     };
-    auto wgrad = [&](int l, const float* dz, const float* act_prev, float alpha) {   // dW_l = dZ_l . A_{l-1}^T
+    auto wgrad = [&](int l, const float* dz, const float* act_prev, float alpha, cudaStream_t on = nullptr) {   // dW_l = dZ_l . A_{l-1}^T
         GemmArgs g{};
         g.m = m->n[l + 1]; g.n = m->n[l]; g.k = B;
         g.a = dz; g.lda = B; g.b = act_prev; g.ldb = B; g.tb = true;
         g.c = dW(m, l); g.ldc = m->n[l];
         g.epi.alpha = alpha;
         bias_on_side(dz, m->n[l + 1], dB(m, l));                                                          // :271,:282,:293
-        gemm(g, s);
+        if (on) { g.workspace = m->ws2; g.workspace_floats = (size_t)64 * m->n[2] * m->n[1]; }
+        gemm(g, on ? on : s);
     };
     auto dgrad = [&](int l, const float* dz, const float* gate, float* out) {         // dZ_{l-1} = relu'(Z) (.) (W_l^T . dZ_l)
         GemmArgs g{};
@@ -590,11 +614,25 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
         if (gate == m->a1 && m->a1_bits_ok) { g.gate_bits = m->a1_bits; g.gate_ld = (B + 31) / 32; }
         gemm(g, s);
     };
-    if (skinny) bias_on_side(dz3, m->n[3], dB(m, 2));   // :271
+    if (skinny) {                                       // off the critical path: nothing before the update reads dW3 / db3
+        bias_on_side(dz3, m->n[3], dB(m, 2));           // :271
+        head_wgrad_fold(m, head_parts, m->side);
+    }
     // Backward order: the dZ chain first, then the layer-1 gradients (86 % of the bytes to exchange) so that
     // their all-reduce runs on the collective stream while the two small layers' gradients are still being
     // computed; the reference's order (:266-293) is dW3, dA2, dW2, dA1, dW1 -- same values, no dependence.
     if (!skinny) dgrad(2, dz3, m->a2, m->dz2);         // :273-278 (the fused head kernel has produced dZ2 already)
+    // dW2 = dZ2.A1^T depends on nothing below: it runs on a second stream beside the dZ1 -> dW1 chain.  At a 7,500-column shard every
+    // GEMM of the step is less than a wave (dgrad 80 CTAs, wgrad2 56), so the two share the SMs; at 60,000 columns its CTAs fill the
+    // tail of the dgrad's last wave.  BLA_MLP_FORK=0 keeps everything on one stream (A/B).
+    static int fork_on = -1;
+    if (fork_on < 0) { const char* e = getenv("BLA_MLP_FORK"); fork_on = e ? atoi(e) : 1; }
+    if (fork_on) {
+        BLA_CUDA(cudaEventRecord(m->ev_fork2, s));
+        BLA_CUDA(cudaStreamWaitEvent(m->side2, m->ev_fork2, 0));
+        wgrad(1, m->dz2, m->a1, 0.f, m->side2);   // :279-282
+        BLA_CUDA(cudaEventRecord(m->ev_join2, m->side2));
+    }
     dgrad(1, m->dz2, m->a1, m->dz1);      // :284-289
     wgrad(0, m->dz1, x, x_scale);         // :290-293 (X/255 again folded into alpha)
     join_side();                          // db1 is part of the first segment
@@ -610,7 +648,8 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
         BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_l1, 0));
         reduce_grads(m, 0, seg1, lr, cs);
     }
-    wgrad(1, m->dz2, m->a1, 0.f);         // :279-282
+    if (fork_on) BLA_CUDA(cudaStreamWaitEvent(s, m->ev_join2, 0));
+    else wgrad(1, m->dz2, m->a1, 0.f);    // :279-282
     if (!skinny) wgrad(2, dz3, m->a2, 0.f);   // :266-271
     join_side();
     if (dp) {                             // the rest of the flat buffer + {loss, correct}
@@ -628,6 +667,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
 void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, float lr_mult, double* stats_host) {
     if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
     prepare_comm(m);
+    StepPdlOff pdl_guard;
     backprop(m, x, x_scale, y, B, Bg, c0, true, lr_mult);
     // clip_gradient is a no-op (threshold INFINITY, :13,:296-301); scale by -lr and add  :303-315
     if (!(use_peer(m) && comm_active())) k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, rt().stream);
@@ -667,6 +707,7 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
     const int n0 = m->n[0], n3 = m->n[3];
     const int chunks = ceil_div(B, cols);
     prepare_comm(m);
+    StepPdlOff pdl_guard;
     const size_t esz = x_is_u8 ? 1 : sizeof(float);
     const MemKind yk = classify(y);
     const bool y_on_host = yk != kDevice && yk != kManaged;
@@ -809,6 +850,10 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_l1, cudaEventDisableTiming));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_rest, cudaEventDisableTiming));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_comm, cudaEventDisableTiming));
+    BLA_CUDA(cudaStreamCreateWithFlags(&m->side2, cudaStreamNonBlocking));
+    BLA_CUDA(cudaEventCreateWithFlags(&m->ev_fork2, cudaEventDisableTiming));
+    BLA_CUDA(cudaEventCreateWithFlags(&m->ev_join2, cudaEventDisableTiming));
+    m->ws2 = (float*)pool_alloc(kDevice, (size_t)64 * dims[2] * dims[1] * sizeof(float));
     m->chunk_cols = -1;
     if (const char* e = getenv("BLA_MLP_CHUNK_COLS")) m->chunk_cols = atoi(e);
     m->grads_chunk = (float*)pool_alloc(kDevice, off * sizeof(float));
@@ -827,11 +872,13 @@ void bla_mlp_destroy(bla_mlp* m) {
     BLA_CUDA(cudaStreamSynchronize(rt().stream));
     BLA_CUDA(cudaStreamSynchronize(m->copy));
     for (int i = 0; i < m->n_graphs; ++i) cudaGraphExecDestroy(m->graphs[i].exec);
-    void* bufs[] = {m->a1_bits, m->params, m->grads, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial};
+    void* bufs[] = {m->a1_bits, m->params, m->grads, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial, m->ws2};
     for (void* b : bufs) pool_free(b);
     cudaStreamDestroy(m->copy); cudaEventDestroy(m->ev_free); cudaEventDestroy(m->ev_y);
     for (cudaEvent_t e : m->ev_chunk) cudaEventDestroy(e);
     cudaStreamDestroy(m->side); cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join);
+    BLA_CUDA(cudaStreamSynchronize(m->side2));
+    cudaStreamDestroy(m->side2); cudaEventDestroy(m->ev_fork2); cudaEventDestroy(m->ev_join2);
     cudaEventDestroy(m->ev_l1); cudaEventDestroy(m->ev_rest); cudaEventDestroy(m->ev_comm);
     free(m);
 }

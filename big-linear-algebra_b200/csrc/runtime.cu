@@ -31,6 +31,14 @@ void check(cudaError_t e, const char* what, const char* file, int line) {
 static Runtime g_rt;
 static bool g_init = false;
 
+static int g_pdl_off = 0;
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("BLA_PDL"); on = e ? atoi(e) : 1; }
+    return on != 0 && g_pdl_off == 0;
+}
+PdlOff::PdlOff() { ++g_pdl_off; }
+PdlOff::~PdlOff() { --g_pdl_off; }
 bool rt_initialised() { return g_init; }
 
 void rt_init(int device) {

@@ -87,4 +87,47 @@ private:
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// A kernel whose every thread passes pdl_wait() before its first access to global memory may be launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs then become resident -- and run their prologue (barrier
+// initialisation, TMEM allocation, descriptor prefetch, index arithmetic) -- while the previous kernel of the stream is still
+// draining, and block in pdl_wait() until that kernel has completed and its writes are visible.  pdl_trigger() in the EARLIER kernel
+// only says "my dependents may be made resident once all my CTAs are"; it orders nothing.  A kernel launched with the attribute that
+// never waits would race with its predecessor, so the attribute is given per launch site (launch_pdl), never globally.
+// BLA_PDL=0 launches everything fully serialised (A/B).  PdlOff suspends it for a scope: CTAs that are resident but still waiting hold their
+// SM's shared memory, which starves kernels of OTHER streams that could have run there -- measured on the MLP step (bias sums and the
+// layer-2 weight gradient run beside the main chain): 338.7 us without, 374.5 us with programmatic launches at 60,000 columns, 97.9 /
+// 102.7 us at 7,500; the single-stream U-Net step gains 4 % (12.42 -> 11.91 ms).  profiles/r02_ab.txt
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+struct PdlOff { PdlOff(); ~PdlOff(); };
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = (unsigned)n;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace bla
