@@ -498,7 +498,7 @@ def main():
     if generic:
         roofline["generic_fp32_operands"] = generic
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (taken at the N=1 shape, tensor path)
-    cap = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_dominant.json")
+    cap = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_dominant.json")
     if used_tc and Bl == 60000 and os.path.isfile(cap) and json.load(open(cap)).get("columns", Bl) == n_main:
         with open(cap) as f:
             cj = json.load(f)

@@ -306,6 +306,8 @@ __device__ __forceinline__ float cluster_total(float v, float* slot /* one float
 template <int CL>
 __global__ void __launch_bounds__(kClThreads, 2) group_norm_fwd_cluster(const float* __restrict__ x, float* __restrict__ y, float* vars,
                                                                         float* means, GnParams p) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     constexpr int F4 = 8;
     __shared__ float red[kClThreads / 32];
     __shared__ float slots[2];
@@ -361,6 +363,8 @@ template <int CL>
 __global__ void __launch_bounds__(kClThreads, 2) group_norm_bwd_cluster(const float* __restrict__ dy, float* __restrict__ dx,
                                                                         const float* __restrict__ x, const float* __restrict__ means,
                                                                         const float* __restrict__ stdevs, GnParams p) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     constexpr int F4 = 4;
     __shared__ float red[kClThreads / 32];
     __shared__ float slots[2];
@@ -418,6 +422,8 @@ constexpr int kQuarterF4 = kFastThreads / 4 * kFastF4;      // 2048 float4 = 32 
 
 __global__ void __launch_bounds__(kFastThreads, 1) group_norm_fwd_tma(const float* __restrict__ x, float* __restrict__ y, float* vars,
                                                                       float* means, GnParams p, int images) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     extern __shared__ __align__(128) float slab[];     // up to 32768 floats
     __shared__ float red[32];
     __shared__ __align__(8) unsigned long long bar[4];
@@ -517,6 +523,8 @@ template <int F4>
 __global__ void __launch_bounds__(kSmallThreads) group_norm_bwd_small(const float* __restrict__ dy, float* __restrict__ dx,
                                                                       const float* __restrict__ x, const float* __restrict__ means,
                                                                       const float* __restrict__ stdevs, GnParams p) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     __shared__ float red[2][kSmallThreads / 32];
     const int g = blockIdx.x, img = blockIdx.y;
     const int c0 = g * p.group_size;
@@ -567,6 +575,8 @@ __global__ void __launch_bounds__(kSmallThreads) group_norm_bwd_small(const floa
 template <int F4>
 __global__ void __launch_bounds__(kSmallThreads) group_norm_fwd_small(const float* __restrict__ x, float* __restrict__ y, float* vars, float* means,
                                                                       GnParams p) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     __shared__ float red[2][kSmallThreads / 32];
     const int g = blockIdx.x, img = blockIdx.y;
     const int c0 = g * p.group_size;
@@ -631,6 +641,8 @@ __global__ void __launch_bounds__(kSmallThreads) group_norm_fwd_small(const floa
 __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const float* __restrict__ dy, float* __restrict__ dx,
                                                                       const float* __restrict__ x, const float* __restrict__ means,
                                                                       const float* __restrict__ stdevs, GnParams p, int images) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     constexpr int F4 = 4;                                  // float4 per thread per tensor: 2 CTAs x 1024 x 4 x 4 = 32768 elements
     extern __shared__ __align__(128) float stage[];        // [x half | dy half], each up to 16384 floats
     __shared__ float red2[2][32];
@@ -770,21 +782,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) group_norm_bwd_tma(const floa
     cluster.sync();
 }
 
-template <int CL, class Kernel, class... Args>
-void launch_cluster(Kernel kernel, dim3 grid, cudaStream_t s, Args... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kClThreads);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    BLA_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+template <int CL, class... KArgs, class... Args>
+void launch_cluster(void (*kernel)(KArgs...), dim3 grid, cudaStream_t s, Args... args) {
+    BLA_CUDA(launch_pdl(kernel, grid, dim3(kClThreads), 0, s, CL, args...));
 }
 
 
@@ -802,8 +802,8 @@ void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int i
     if (vec_ok && slab <= (size_t)kSmallThreads * 8 * 4 && (long long)p.G * images >= 2LL * rt().num_sms) {
         // many small slabs: one small register-resident CTA each (the persistent kernel's per-slab barrier chain costs more than
         // these slabs' transfer time)
-        if (slab <= (size_t)kSmallThreads * 2 * 4) group_norm_fwd_small<2><<<grid, kSmallThreads, 0, s>>>(x, y, vars, means, p);
-        else group_norm_fwd_small<8><<<grid, kSmallThreads, 0, s>>>(x, y, vars, means, p);
+        if (slab <= (size_t)kSmallThreads * 2 * 4) BLA_CUDA(launch_pdl(group_norm_fwd_small<2>, dim3(grid), dim3(kSmallThreads), 0, s, 1, x, y, vars, means, p));
+        else BLA_CUDA(launch_pdl(group_norm_fwd_small<8>, dim3(grid), dim3(kSmallThreads), 0, s, 1, x, y, vars, means, p));
     } else if (vec_ok && slab <= (size_t)kFastThreads * kFastF4 * 4 && (long long)p.G * images >= 2LL * rt().num_sms) {
         // many slabs: persistent CTAs with a TMA prefetch of the next slab
         static bool attr = false;
@@ -811,7 +811,7 @@ void k_group_norm_fwd(const float* x, float* y, float* vars, float* means, int i
             BLA_CUDA(cudaFuncSetAttribute(group_norm_fwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastThreads * kFastF4 * 16));
             attr = true;
         }
-        group_norm_fwd_tma<<<rt().num_sms, kFastThreads, slab * sizeof(float), s>>>(x, y, vars, means, p, images);
+        BLA_CUDA(launch_pdl(group_norm_fwd_tma, dim3(rt().num_sms), dim3(kFastThreads), slab * sizeof(float), s, 1, x, y, vars, means, p, images));
     } else if (vec_ok && slab <= (size_t)2 * kClThreads * 8 * 4) {
         // cluster of 2 CTAs x 512 threads x 8 float4 covers 32768 elements (32 channels x 32 x 32)
         launch_cluster<2>(group_norm_fwd_cluster<2>, dim3(2 * p.G, images), s, x, y, vars, means, p);
@@ -841,8 +841,8 @@ void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* m
     const bool vec_ok = al16(dy) && al16(dx) && al16(x) && al16(p.addend) && (HW % 4 == 0);
     const bool tail_ok = (C % group_size == 0) || (((size_t)(C % group_size) * HW) % 4 == 0);
     if (vec_ok && tail_ok && slab <= (size_t)kSmallThreads * 8 * 4 && (long long)p.G * images >= 2LL * rt().num_sms) {
-        if (slab <= (size_t)kSmallThreads * 2 * 4) group_norm_bwd_small<2><<<grid, kSmallThreads, 0, s>>>(dy, dx, x, means, stdevs, p);
-        else group_norm_bwd_small<8><<<grid, kSmallThreads, 0, s>>>(dy, dx, x, means, stdevs, p);
+        if (slab <= (size_t)kSmallThreads * 2 * 4) BLA_CUDA(launch_pdl(group_norm_bwd_small<2>, dim3(grid), dim3(kSmallThreads), 0, s, 1, dy, dx, x, means, stdevs, p));
+        else BLA_CUDA(launch_pdl(group_norm_bwd_small<8>, dim3(grid), dim3(kSmallThreads), 0, s, 1, dy, dx, x, means, stdevs, p));
     } else if (vec_ok && tail_ok && slab <= (size_t)2 * kFastThreads * 4 * 4 && slab % 8 == 0 && (long long)p.G * images >= (long long)rt().num_sms) {
         // many slabs: persistent 2-CTA clusters with TMA prefetch (each CTA's half slab must be a whole number of float4)
         static bool attr = false;
@@ -851,17 +851,7 @@ void k_group_norm_bwd(const float* dy, float* dx, const float* x, const float* m
             BLA_CUDA(cudaFuncSetAttribute(group_norm_bwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr = true;
         }
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((rt().num_sms / 2) * 2);
-        cfg.blockDim = dim3(kFastThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr1[1];
-        attr1[0].id = cudaLaunchAttributeClusterDimension;
-        attr1[0].val.clusterDim.x = 2; attr1[0].val.clusterDim.y = 1; attr1[0].val.clusterDim.z = 1;
-        cfg.attrs = attr1;
-        cfg.numAttrs = 1;
-        BLA_CUDA(cudaLaunchKernelEx(&cfg, group_norm_bwd_tma, dy, dx, x, means, stdevs, p, images));
+        BLA_CUDA(launch_pdl(group_norm_bwd_tma, dim3((rt().num_sms / 2) * 2), dim3(kFastThreads), (size_t)smem, s, 2, dy, dx, x, means, stdevs, p, images));
     } else if (vec_ok && tail_ok && slab <= (size_t)4 * kClThreads * 4 * 4) {
         // cluster of 4 CTAs x 512 threads x (4 + 4) float4: x and dy are read from HBM exactly once
         launch_cluster<4>(group_norm_bwd_cluster<4>, dim3(4 * p.G, images), s, dy, dx, x, means, stdevs, p);

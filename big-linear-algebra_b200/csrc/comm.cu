@@ -149,11 +149,12 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 // Returns false after the bounded wait (~4 s) gave up on a peer: the window's error word is raised, the caller leaves its
 // destination untouched but still advances its counters so that the ranks stay in step.
 __device__ __forceinline__ bool peer_handshake(const PeerArgs& a, int c, int t, unsigned long long value, int* failed) {
-    __threadfence_system();
     if (t == 0) *failed = 0;
+    // The CTA barrier orders every thread's pushes before the flag writers' st.release.sys, and a release is cumulative over what
+    // happens-before it: ONE system-scope release per peer and CTA.  (Round 2's first version had all 256 threads of all CTAs execute
+    // __threadfence_system() -- twice -- before the flags: 28 us per call on 2 GPUs, most of it those ~60,000 MEMBAR.SYS.)
     __syncthreads();
     if (t < a.world && t != a.rank) {
-        __threadfence_system();
         st_release_sys(a.flag_out[t] + c, value);
         const unsigned long long* f = a.flag_in + (size_t)t * kPeerCtas + c;
         long spins = 0;

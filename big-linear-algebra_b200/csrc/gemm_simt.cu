@@ -63,6 +63,8 @@ __device__ __forceinline__ float epilogue_value(float acc, int i, int j, const S
 
 template <int BM, int BN, bool TA, bool TB>
 __global__ void __launch_bounds__(kThreads, 2) gemm_simt_kernel(const SimtParams p) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     constexpr int TM = BM / 16, TN = BN / 16;   // 8x8 (128) or 4x4 (64)
     constexpr int GM = TM / 4, GN = TN / 4;     // float4 groups per thread along m / n
     constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
@@ -236,6 +238,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_simt_kernel(const SimtParams
 
 // sums the split-K partials in a fixed order and applies the epilogue
 __global__ void __launch_bounds__(kThreads) splitk_reduce_kernel(const SimtParams p, int splits) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     const size_t total = (size_t)p.m * p.n;
     for (size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (size_t)gridDim.x * kThreads) {
         float s = 0.f;
@@ -247,10 +251,10 @@ __global__ void __launch_bounds__(kThreads) splitk_reduce_kernel(const SimtParam
 
 template <int BM, int BN>
 void launch_tile(const SimtParams& p, bool ta, bool tb, dim3 grid, cudaStream_t s) {
-    if (!ta && !tb) gemm_simt_kernel<BM, BN, false, false><<<grid, kThreads, 0, s>>>(p);
-    else if (!ta && tb) gemm_simt_kernel<BM, BN, false, true><<<grid, kThreads, 0, s>>>(p);
-    else if (ta && !tb) gemm_simt_kernel<BM, BN, true, false><<<grid, kThreads, 0, s>>>(p);
-    else gemm_simt_kernel<BM, BN, true, true><<<grid, kThreads, 0, s>>>(p);
+    if (!ta && !tb) BLA_CUDA(launch_pdl(gemm_simt_kernel<BM, BN, false, false>, dim3(grid), dim3(kThreads), 0, s, 1, p));
+    else if (!ta && tb) BLA_CUDA(launch_pdl(gemm_simt_kernel<BM, BN, false, true>, dim3(grid), dim3(kThreads), 0, s, 1, p));
+    else if (ta && !tb) BLA_CUDA(launch_pdl(gemm_simt_kernel<BM, BN, true, false>, dim3(grid), dim3(kThreads), 0, s, 1, p));
+    else BLA_CUDA(launch_pdl(gemm_simt_kernel<BM, BN, true, true>, dim3(grid), dim3(kThreads), 0, s, 1, p));
     BLA_LAUNCH_CHECK();
     count_launch();
 }
@@ -310,7 +314,7 @@ void gemm_simt(const GemmArgs& g, cudaStream_t s) {
         size_t blocks = (total + kThreads - 1) / kThreads;
         size_t cap = (size_t)sms * 8;
         if (blocks > cap) blocks = cap;
-        splitk_reduce_kernel<<<(int)blocks, kThreads, 0, s>>>(p, splits);
+        BLA_CUDA(launch_pdl(splitk_reduce_kernel, dim3((int)blocks), dim3(kThreads), 0, s, 1, p, splits));
         BLA_LAUNCH_CHECK();
         count_launch();
         if (!own_ws) pool_free(ws);   // stream-ordered reuse: the pool only serves this one stream

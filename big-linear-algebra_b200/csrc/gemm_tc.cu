@@ -1306,6 +1306,8 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
 // coalesced along the image row, stores are one float4 (4 channels) per thread = full 128-byte lines per pixel.
 __global__ void __launch_bounds__(256) nchw_to_padded_nhwc_kernel(const float* __restrict__ x, float* __restrict__ xp, int C, int Cp, int H, int W,
                                                                   int Hp, int Wp, int pt, int pl, int dil) {
+    pdl_trigger();
+    pdl_wait();   // runtime.h: launched with programmatic serialisation
     __shared__ float tile[32][33];   // [channel][pixel]
     const int img = blockIdx.y, q0 = blockIdx.x * 32, npix = Hp * Wp;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -1361,7 +1363,7 @@ float* padded_nhwc(const float* in, int imgs, int C, int Cp, int H, int W, int H
     int gz = ceil_div(4LL * rt().num_sms, (long long)px_tiles * imgs);     // enough blocks for ~4 per SM
     if (gz > c_tiles) gz = c_tiles;
     if (gz < 1) gz = 1;
-    nchw_to_padded_nhwc_kernel<<<dim3(px_tiles, imgs, gz), 256, 0, s>>>(in, xp, C, Cp, H, W, Hp, Wp, pad_top, pad_left, dil);
+    BLA_CUDA(launch_pdl(nchw_to_padded_nhwc_kernel, dim3(px_tiles, imgs, gz), dim3(256), 0, s, 1, in, xp, C, Cp, H, W, Hp, Wp, pad_top, pad_left, dil));
     BLA_LAUNCH_CHECK();
     count_launch();
     return xp;

@@ -278,8 +278,13 @@ void bla_unet_init_params(bla_unet* net, unsigned long long seed);
 void bla_unet_set_params(bla_unet* net, const float* flat);   /* host or device */
 void bla_unet_get_params(bla_unet* net, float* flat);
 void bla_unet_get_grads(bla_unet* net, float* flat);
-/* save_parameters / load_parameters (cifar_unet.c:1484-1802): the reference's directory of CSV files (one per tensor,
- * data/cifar_unet/<level>/resnet_<i>/conv_1.csv ...; Q, K, V unpacked into query / key / value.csv), lib/csv.c's format. */
+/* save_parameters / load_parameters (cifar_unet.c:1484-1802): the reference's directory of CSV files, file for file
+ * (data/cifar_unet/<level>/resnet_<i>/conv_1.csv ...; Q, K, V unpacked into query / key / value.csv), lib/csv.c's format.
+ * Either program reads what the other wrote.  As in the reference, every ResNet block has a conv_3.csv (zeros here where
+ * in == out channels: forward() never reads those kernels, :1062-1066, and this library keeps none), and conv_1.csv /
+ * conv_3.csv of down_1/resnet_2 and up_{1..4}/resnet_1 hold only the input channels save_parameters declares (:1557,
+ * :1614-1653: 3 of 128, C of 2C); the channels that format drops are written beside them as conv_1_rest.csv /
+ * conv_3_rest.csv.  Loading a directory without *_rest.csv (one the reference wrote) leaves those channels unchanged. */
 void bla_unet_save_csv(bla_unet* net, const char* dir);
 void bla_unet_load_csv(bla_unet* net, const char* dir);
 /* forward() on x [imgs][3][H][W] with one time embedding row per image, time_emb [imgs][time_dim] (the reference never

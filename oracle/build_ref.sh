@@ -114,6 +114,13 @@ if [ -f "$BLA_DIR/libbla.so" ]; then
   # the reference's own U-Net build (double, as shipped) for comparison runs
   $CC $CFLAGS -o "$OUT/bin/ref_cifar_unet_f64" "$GEN/f64/model/cifar_unet.c" "$GEN/f64/lib/matrix.c" "$GEN/f64/lib/csv.c" \
       "$GEN/f64/lib/cifar10.c" "$GEN/f64/lib/bmp.c" "$GEN/f64/lib/conv.c" "$GEN/f64/lib/norm.c" "$GEN/f64/lib/util.c" -lm
+  # checkpoint round trip through the reference's own load_parameters / save_parameters (cifar_unet.c:1545-1802; its main() never
+  # calls load_parameters, :1902): reads data/cifar_unet under the current directory and writes it back.  For the U-Net checkpoint
+  # interoperability test (tests/test_checkpoint_gpu.py).
+  printf '%s\n' '#define main ref_cifar_unet_main' '#include "cifar_unet.c"' '#undef main' \
+      'int main(void) { ModelParams p; allocate_model_params(&p); load_parameters(&p); save_parameters(&p); return 0; }' > "$GEN/f64/model/unet_ckpt.c"
+  $CC $CFLAGS -o "$OUT/bin/ref_unet_ckpt_f64" "$GEN/f64/model/unet_ckpt.c" "$GEN/f64/lib/matrix.c" "$GEN/f64/lib/csv.c" \
+      "$GEN/f64/lib/cifar10.c" "$GEN/f64/lib/bmp.c" "$GEN/f64/lib/conv.c" "$GEN/f64/lib/norm.c" "$GEN/f64/lib/util.c" -lm
 else
   echo "build_ref: $BLA_DIR/libbla.so not built yet -- skipping the relinked programs" >&2
 fi

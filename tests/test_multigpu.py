@@ -20,16 +20,19 @@ def _ngpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("path,batch,allreduce", [("fp32", "2000", "peer"), ("3xtf32", "4096", "peer"), ("fp32", "1001", "peer"), ("fp32", "2000", "nccl")])
+@pytest.mark.parametrize("path,batch,allreduce", [("fp32", "2000", "peer"), ("3xtf32", "4096", "peer"), ("fp32", "1001", "peer"), ("fp32", "2000", "nccl"),
+                                                  ("fp32", "2000", "peer_two_rounds")])
 def test_data_parallel_step_matches_oracle(path, batch, allreduce):
     """Data-parallel MLP steps (host batches, then device-resident batches replayed as step graphs), the row-sharded GEMM and the
     data-parallel U-Net step against the oracle / float64, with the gradient all-reduce as the library's own kernel over NVLink
     peer windows (the default, csrc/comm.cu) and through NCCL (BLA_PEER_ALLREDUCE=0)."""
     n = min(_ngpu(), 2 if batch != "4096" else 4)
-    env = dict(os.environ, DP_PATH=path, DP_BATCH=batch, BLA_PEER_ALLREDUCE="1" if allreduce == "peer" else "0")
+    env = dict(os.environ, DP_PATH=path, DP_BATCH=batch, BLA_PEER_ALLREDUCE="0" if allreduce == "nccl" else "1")
+    if allreduce == "peer_two_rounds":   # the reduce-scatter + all-gather kernel is the default from 4 ranks and 256 KB: force it at 2
+        env["BLA_PEER_TWO_ROUNDS"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "dp_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     for word in ("DP_CHECK_OK", "DP_GRAPH_OK", "HINGE_DP_OK", "SHARDED_GEMM_OK", "UNET_DP_OK"):
         assert word in p.stdout, (p.stdout[-3000:], p.stderr[-3000:])
-    assert ("peer_windows 1" if allreduce == "peer" else "peer_windows 0") in p.stdout, p.stdout[-2000:]
+    assert ("peer_windows 0" if allreduce == "nccl" else "peer_windows 1") in p.stdout, p.stdout[-2000:]
