@@ -199,6 +199,11 @@ void bla_mnist_gather(bla_mnist* m, const int* indices_host, int count, float* x
 void bla_mlp_train_epoch(bla_mlp* net, bla_mnist* data, int batch_size, float lr_mult, double* stats_host) {
     const int n = data->n;
     if (n <= 0 || batch_size <= 0) return;
+    int dims[4];
+    bla_mlp_dims(net, dims);
+    if (dims[0] != data->features)
+        die("bla: bla_mlp_train_epoch: the network takes %d inputs, the dataset has %d features, exiting", dims[0], data->features);
+    const int classes = dims[3];                                                        // 10 in the reference (:16)
     cudaStream_t s = rt().stream;
     const int num_batches = (int)ceil((float)n / (float)batch_size);                    // :187
     bla_mnist_reset(data);                                                              // :189-190
@@ -208,13 +213,13 @@ void bla_mlp_train_epoch(bla_mlp* net, bla_mnist* data, int batch_size, float lr
     BLA_CUDA(cudaMemcpyAsync(data->idx_dev, data->idx_pin, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
     rt().h2d_bytes += (size_t)n * sizeof(int);
     float* xb = (float*)pool_alloc(kDevice, (size_t)data->features * batch_size * sizeof(float));
-    float* yb = (float*)pool_alloc(kDevice, (size_t)10 * batch_size * sizeof(float));
+    float* yb = (float*)pool_alloc(kDevice, (size_t)classes * batch_size * sizeof(float));
     double stats[2];
     bla_mlp_read_stats(net, stats);                                                     // clear the accumulators
     auto eager_step = [&](int j) {
         const int remaining = n - j * batch_size;
         const int cnt = remaining > batch_size ? batch_size : remaining;                // :194-195
-        mnist_gather_launch(data, data->idx_dev + (size_t)j * batch_size, cnt, xb, yb, 10, s);
+        mnist_gather_launch(data, data->idx_dev + (size_t)j * batch_size, cnt, xb, yb, classes, s);
         bla_mlp_train_step(net, xb, yb, cnt, cnt, 0, lr_mult, nullptr);
     };
     // Small batches are launch-bound (~20 launches of a few microseconds each): the gather + step of one full batch is captured
@@ -238,7 +243,7 @@ void bla_mlp_train_epoch(bla_mlp* net, bla_mnist* data, int batch_size, float lr
         cudaGraphExec_t exec = nullptr;
         // a stream that cannot be captured (the caller handed bla_set_stream the legacy default stream): stay eager
         if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-            mnist_gather_launch(data, data->idx_dev, batch_size, xb, yb, 10, s, data->cursor);
+            mnist_gather_launch(data, data->idx_dev, batch_size, xb, yb, classes, s, data->cursor);
             bla_mlp_train_step(net, xb, yb, batch_size, batch_size, 0, lr_mult, nullptr);
             cursor_advance_kernel<<<1, 1, 0, s>>>(data->cursor, batch_size);
             BLA_LAUNCH_CHECK();

@@ -328,7 +328,9 @@ void gemm(const GemmArgs& g, cudaStream_t s) {
         // AUTO: tensor path where a 128x256 tcgen05 tile is not mostly padding, or where a skinny product is long enough that
         // even a mostly empty tile beats the FP32 FMA kernel (the U-Net's attention projections: 16384 x 48 x 256 and their
         // weight gradients 256 x 48 x 16384)
-        const bool worthwhile = g.k >= 64 && ((g.m >= 128 && g.n >= 128) || (g.m >= 16 && g.n >= 16 && (double)g.m * g.n * g.k >= 1.0e8));
+        static double skinny_min = -1.0;   // BLA_TC_SKINNY_MIN: m*n*k from which a skinny product takes the tensor path (tuning probe)
+        if (skinny_min < 0) { const char* e = getenv("BLA_TC_SKINNY_MIN"); skinny_min = e ? atof(e) : 1.0e8; }
+        const bool worthwhile = g.k >= 64 && ((g.m >= 128 && g.n >= 128) || (g.m >= 16 && g.n >= 16 && (double)g.m * g.n * g.k >= skinny_min));
         if ((forced || worthwhile) && gemm_3xtf32(g, s)) return;
     }
     if (g.mask_out && g.mask_written) *g.mask_written = false;   // only the tensor path writes the bit form of a ReLU mask

@@ -867,6 +867,8 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     return m;
 }
 
+void bla_mlp_dims(const bla_mlp* m, int dims[4]) { memcpy(dims, m->n, sizeof(m->n)); }
+
 void bla_mlp_destroy(bla_mlp* m) {
     if (!m) return;
     BLA_CUDA(cudaStreamSynchronize(rt().stream));

@@ -265,7 +265,13 @@ int bla_device_count(void) {
 void bla_init(int device) { rt_init(device); }
 void bla_sync(void) { BLA_CUDA(cudaStreamSynchronize(rt().stream)); }
 void* bla_stream(void) { return (void*)rt().stream; }
-void bla_set_stream(void* s) { rt().stream = s ? (cudaStream_t)s : rt().own_stream; }
+// The pool hands a freed block to the next allocation without waiting (stream-ordered reuse: it serves ONE stream), so work in
+// flight on the outgoing stream is drained before the library moves to another one.
+void bla_set_stream(void* s) {
+    cudaStream_t next = s ? (cudaStream_t)s : rt().own_stream;
+    if (next != rt().stream && rt().stream) BLA_CUDA(cudaStreamSynchronize(rt().stream));
+    rt().stream = next;
+}
 const char* bla_version(void) { return "bla-b200 0.1 (sm_100a)"; }
 
 void bla_set_gemm_path(int path) {

@@ -145,6 +145,8 @@ typedef struct bla_mlp bla_mlp;
 /* dims = {inputs, hidden1, hidden2, classes} (784, 256, 128, 10 in the reference, :25-28);
  * max_batch = the largest LOCAL batch (columns per GPU) a step will be given. */
 bla_mlp* bla_mlp_create(const int dims[4], int max_batch);
+/* the four layer widths the network was created with */
+void bla_mlp_dims(const bla_mlp* net, int dims[4]);
 void bla_mlp_destroy(bla_mlp* net);
 /* Parameters in the reference's layout: W_l [n_l x n_{l-1}] row-major, b_l [n_l] (:165-170).
  * Pointers may be host or device memory. */
