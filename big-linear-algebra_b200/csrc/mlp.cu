@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
 // this one moves A2 once in, dZ2 once out.  Tile rows are 68 floats apart: float4 stores stay aligned, a column walk (lanes =
 // consecutive hidden units, phase 3) reads 128-bit quads from 8 distinct 4-bank groups = conflict free.
 constexpr int kHeadCols = 64, kHeadPitch = 68;
-template <int NC>
-__global__ void __launch_bounds__(256, 3) head_train_kernel(const float* __restrict__ W3, const float* __restrict__ b3,
+template <int NC, int MINB>
+__global__ void __launch_bounds__(256, MINB) head_train_kernel(const float* __restrict__ W3, const float* __restrict__ b3,
                                                             const float* __restrict__ A2, const float* __restrict__ Y, int hidden, int B,
                                                             float scale, float* __restrict__ dz3, float* __restrict__ dz2,
                                                             float* __restrict__ partial, double* stats) {
@@ -496,18 +496,25 @@ void head_forward(bla_mlp* m, const float* y, int B, float* dz, float* probs, cu
 // which a second small launch folds in a fixed order                                              model/mnist_nn.c:231-278
 int head_train(bla_mlp* m, const float* y, int B, cudaStream_t s) {
     const int n2 = m->n[2], n3 = m->n[3], ncp = (n3 + 3) / 4 * 4;
+    static int occ = -1;   // BLA_HEAD_OCC=4: four CTAs per SM (64 registers) instead of three (A/B probe)
+    if (occ < 0) { const char* e = getenv("BLA_HEAD_OCC"); occ = e && atoi(e) == 4 ? 4 : 3; }
     int ctas = ceil_div(B, kHeadCols);
-    const int cap = std::min(m->head_ctas, rt().num_sms * 3);
+    const int cap = std::min(m->head_ctas, rt().num_sms * occ);
     if (ctas > cap) ctas = cap;
     const size_t smem = ((size_t)n2 * kHeadPitch + (size_t)n2 * ncp + (size_t)kHeadCols * ncp + 3 * (size_t)kHeadCols * (n3 + 1)) * sizeof(float);
-    static bool attr_done[kMaxClasses + 1] = {};
+    static bool attr_done[kMaxClasses + 1][2] = {};
     BLA_DISPATCH_NC(n3, {
-        if (!attr_done[NC]) {
-            BLA_CUDA(cudaFuncSetAttribute(head_train_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_done[NC] = true;
+        if (!attr_done[NC][occ - 3]) {
+            if (occ == 4) BLA_CUDA(cudaFuncSetAttribute(head_train_kernel<NC, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            else BLA_CUDA(cudaFuncSetAttribute(head_train_kernel<NC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_done[NC][occ - 3] = true;
         }
-        BLA_CUDA(launch_pdl(head_train_kernel<NC>, dim3(ctas), dim3(256), smem, s, 1, (const float*)W(m, 2), (const float*)Bv(m, 2),
-                            (const float*)m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2, m->head_partial, m->stats));
+        if (occ == 4)
+            BLA_CUDA(launch_pdl(head_train_kernel<NC, 4>, dim3(ctas), dim3(256), smem, s, 1, (const float*)W(m, 2), (const float*)Bv(m, 2),
+                                (const float*)m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2, m->head_partial, m->stats));
+        else
+            BLA_CUDA(launch_pdl(head_train_kernel<NC, 3>, dim3(ctas), dim3(256), smem, s, 1, (const float*)W(m, 2), (const float*)Bv(m, 2),
+                                (const float*)m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2, m->head_partial, m->stats));
     });
     count_launch();
     return ctas;

@@ -264,7 +264,7 @@ typedef struct bla_unet_config {
 	unsigned long long seed; /* dropout masks: element i of block b at step t is dropped iff
 	                          * bla_host_uniform(seed + 7919*t + node_id(b))[i] < dropout */
 } bla_unet_config;
-/* Builds forward()'s graph (cifar_unet.c:1099-1168): 22 ResNet blocks, 5 attention blocks, 3 stride-2 convs, nearest-
+/* Builds forward()'s graph (cifar_unet.c:1099-1168): 18 ResNet blocks, 5 attention blocks, 3 stride-2 convs, nearest-
  * neighbour up-sampling, skip concatenations, group norm + ReLU + 3-channel output conv.  Parameters are ONE flat buffer;
  * tensor i is [offset, offset + size) with the reference's per-file layout (conv kernels [F][C][k][k], time_weight
  * [time_dim][C], attention weight [key_dim][C]); Q, K, V projections are packed as the columns of one [C][3*key_dim]. */
