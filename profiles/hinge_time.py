@@ -1,6 +1,6 @@
 import ctypes as C, sys, time, os
 import numpy as np
-sys.path.insert(0, '/root/repo'); sys.path.insert(0,'/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import bla_b200 as b
 b.bla_init(0)
 n=60000

@@ -28,7 +28,7 @@ def test_data_parallel_step_matches_oracle(path, batch, allreduce):
     peer windows (the default, csrc/comm.cu) and through NCCL (BLA_PEER_ALLREDUCE=0)."""
     n = min(_ngpu(), 2 if batch != "4096" else 4)
     env = dict(os.environ, DP_PATH=path, DP_BATCH=batch, BLA_PEER_ALLREDUCE="0" if allreduce == "nccl" else "1")
-    if allreduce == "peer_two_rounds":   # the reduce-scatter + all-gather kernel is the default from 4 ranks and 256 KB: force it at 2
+    if allreduce == "peer_two_rounds":   # the reduce-scatter + all-gather kernel is the default on 8 ranks from 256 KB: force it at 2
         env["BLA_PEER_TWO_ROUNDS"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "dp_check.py")]
