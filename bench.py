@@ -465,7 +465,8 @@ def main():
     gemm_ms = gr["ms"] / 20
     gemm_flop = 2.0 * DIMS[1] * DIMS[0] * n_main
     achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12
-    layer_ms = timed(gemm_layer, 20, 5)["ms"] / 20
+    layer_r = timed(gemm_layer, 20, 5)
+    layer_ms = layer_r["ms"] / 20
     # the same launch on operands with a non-zero low part (uniform floats instead of integer pixels): all three MMAs per product
     xg = b.bla_malloc_device(DIMS[0] * Bl * 4)
     b.bla_fill_uniform(xg, DIMS[0] * Bl, 11, -1.0, 1.0)
@@ -491,10 +492,10 @@ def main():
         bound = "fp32-simt"
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "kernel": "layer-1 forward GEMM, main launch 256x784x%d of the %d columns (38%% of step flops; the rest of the layer is a "
-                          "split-K tail launch)" % (n_main, Bl),
+                          "tail launch over the remaining columns)" % (n_main, Bl),
                 "ms_per_launch": gemm_ms, "peak_note": note,
                 "whole_layer": {"shape": "256x784x%d" % Bl, "ms": layer_ms, "tflops": 2.0 * DIMS[1] * DIMS[0] * Bl / (layer_ms * 1e-3) / 1e12,
-                                "launches": 1 if n_main == Bl else 3}}
+                                "launches": layer_r["launches"] // 20}}
     if generic:
         roofline["generic_fp32_operands"] = generic
         roofline["frac_of_nominal"] = achieved / (2250.0 / 4.0)   # nominal dense bf16 2250 TFLOP/s / 2 (tf32) / 2 (MMAs per product)
