@@ -67,6 +67,7 @@ struct TcParams {
     const uint32_t* gate_bits; int gate_ld;     // epi.gate in the same bit form
     bool c_vec;              // 16-byte aligned rows
     bool tma_store;          // epilogue writes C (or the split-K partials) with cp.async.bulk.tensor stores
+    int pdl_early;           // trigger the stream's next kernel at the start (runtime.h) or leave it to this kernel's exit
     int cluster;             // 1, or 2: CTA PAIRS (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages only HALF of B
     // implicit-GEMM convolution (conv != 0): B[k'][n] is gathered from x [img][C][H][W] by 4-D TMA boxes, k' = (ki, kj, c)
     // and n = (img, oi, oj); C is y [img][F][P] written by 3-D TMA boxes.  See conv2d_forward_tc().
@@ -321,7 +322,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     const uint32_t tmem_base = *tmem_slot_gen;
     // Programmatic dependent launch (runtime.h): everything above touched only shared memory, TMEM and the kernel parameters, and may
     // have run while the previous kernel of the stream was still draining; from here on global memory is read and written.
-    pdl_trigger();
+    if (p.pdl_early) pdl_trigger();
     pdl_wait();
 
     // Work units.  cluster == 1: a unit is one 128 x bn tile.  cluster == 2: a unit is a 256 x bn tile computed by a CTA
@@ -832,7 +833,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 // sums split-K partials in a fixed order and applies the epilogue.  Block = 64 float4 columns x 4 split groups:
 // every thread keeps 8 independent 128-bit loads in flight, the four group sums are combined through shared memory.
 __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcParams p) {
-    pdl_trigger();
+    if (p.pdl_early) pdl_trigger();
     pdl_wait();   // launched with programmatic serialisation right behind the GEMM whose partials it folds
     const size_t total = (size_t)p.m * p.n;
     if ((total & 3) == 0 && (p.n & 3) == 0 && (p.c_vec || p.conv == 1 || p.cv_final)) {
@@ -1043,6 +1044,7 @@ bool gemm_3xtf32(const GemmArgs& g, cudaStream_t s) {
     p.c = g.c; p.ldc = g.ldc; p.epi = g.epi;
     p.mask_out = g.mask_out; p.mask_ld = g.mask_ld; p.gate_bits = g.epi.gate ? g.gate_bits : nullptr; p.gate_ld = g.gate_ld;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("BLA_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+    p.pdl_early = pdl_early() ? 1 : 0;
     { static int ring = -1; if (ring < 0) { const char* e = getenv("BLA_TC_STAGES"); ring = e ? atoi(e) : 0; } p.ring = ring; }
     p.c_vec = (((uintptr_t)g.c & 15) == 0) && (g.ldc % 4 == 0);
     p.m_tiles = ceil_div(g.m, BM);

@@ -252,14 +252,14 @@ template <int NC, int MINB>
 __global__ void __launch_bounds__(256, MINB) head_train_kernel(const float* __restrict__ W3, const float* __restrict__ b3,
                                                             const float* __restrict__ A2, const float* __restrict__ Y, int hidden, int B,
                                                             float scale, float* __restrict__ dz3, float* __restrict__ dz2,
-                                                            float* __restrict__ partial, double* stats) {
+                                                            float* __restrict__ partial, double* stats, int pdl_early_trigger) {
     constexpr int NCP = (NC + 3) / 4 * 4;
     extern __shared__ __align__(16) float head_smem[];
     float* a_s = head_smem;                                   // [hidden][kHeadPitch]
     float* w_s = a_s + (size_t)hidden * kHeadPitch;           // [hidden][NCP]   w_s[k][r] = W3[r][k]
     float* d_s = w_s + (size_t)hidden * NCP;                  // [kHeadCols][NCP] dZ3 of the tile
     float* part = d_s + kHeadCols * NCP;                      // [3][kHeadCols][NC + 1] partial logits of k groups 1..3
-    pdl_trigger();
+    if (pdl_early_trigger) pdl_trigger();
     pdl_wait();   // runtime.h: launched with programmatic serialisation behind the layer-2 GEMM (W3 too may still be in the update's flight)
     for (int e = threadIdx.x; e < hidden * NCP; e += 256) {
         const int k = e / NCP, r = e % NCP;
@@ -511,10 +511,10 @@ int head_train(bla_mlp* m, const float* y, int B, cudaStream_t s) {
         }
         if (occ == 4)
             BLA_CUDA(launch_pdl(head_train_kernel<NC, 4>, dim3(ctas), dim3(256), smem, s, 1, (const float*)W(m, 2), (const float*)Bv(m, 2),
-                                (const float*)m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2, m->head_partial, m->stats));
+                                (const float*)m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2, m->head_partial, m->stats, pdl_early() ? 1 : 0));
         else
             BLA_CUDA(launch_pdl(head_train_kernel<NC, 3>, dim3(ctas), dim3(256), smem, s, 1, (const float*)W(m, 2), (const float*)Bv(m, 2),
-                                (const float*)m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2, m->head_partial, m->stats));
+                                (const float*)m->a2, y, n2, B, (float)(1.0 / (double)m->n[0]), m->z3, m->dz2, m->head_partial, m->stats, pdl_early() ? 1 : 0));
     });
     count_launch();
     return ctas;
@@ -567,13 +567,23 @@ void reduce_grads(bla_mlp* m, size_t off, size_t n, float lr, cudaStream_t cs) {
 
 // Programmatic dependent launches are suspended inside the step (they lose here: runtime.h); BLA_MLP_PDL=1 keeps them, for A/B runs.
 struct StepPdlOff {
+    // Programmatic launches inside the step.  With early triggers (runtime.h) they lose at every size: waiting CTAs hold SMs against
+    // the kernels of the step's other streams.  Pre-staged only (PdlLate: the next kernel becomes resident when this one's CTAs have
+    // exited, only the launch gap is hidden) they gain while the step's GEMMs are less than a wave -- measured per shard step:
+    // 97.9 -> 95.4 us at 7,500 columns, 121.5 -> 119.2 at 15,000, 194.7 -> 184.8 at 30,000 -- and lose at 60,000 (339.8 -> 365.7),
+    // profiles/r02_pdl_late.txt.  BLA_MLP_PDL: -1 = by size (default), 0 = never, 1 = early triggers, 2 = pre-staged only.
     PdlOff* off;
-    StepPdlOff() {
-        static int keep = -1;
-        if (keep < 0) { const char* e = getenv("BLA_MLP_PDL"); keep = e ? atoi(e) : 0; }
-        off = keep ? nullptr : new PdlOff;
+    PdlLate* late;
+    explicit StepPdlOff(int B) {
+        static int env = -2;
+        if (env == -2) { const char* e = getenv("BLA_MLP_PDL"); env = e ? atoi(e) : -1; }
+        const int mode = env >= 0 ? env : (B <= 256 * rt().num_sms ? 2 : 0);
+        off = mode ? nullptr : new PdlOff;
+        late = mode == 2 ? new PdlLate : nullptr;
     }
-    ~StepPdlOff() { delete off; }
+    ~StepPdlOff() { delete off; delete late; }
+    StepPdlOff(const StepPdlOff&) = delete;
+    StepPdlOff& operator=(const StepPdlOff&) = delete;
 };
 
 // forward + backward of columns [c0, c0 + B) of a Bg-column batch: gradients into m->grads (all-reduced when `reduce` and a
@@ -582,7 +592,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
     cudaStream_t s = rt().stream;
     const int quirk = rt().quirks;
     const bool skinny = skinny_head(m, B);
-    StepPdlOff pdl_guard;
+    StepPdlOff pdl_guard(B);
     forward(m, x, x_scale, B, s, !skinny);
     // A3 = softmax(Z3); loss / accuracy; dZ3 = (A3 - Y) / 784 (in place over Z3)      :234-268
     int head_parts = 0;
@@ -674,7 +684,7 @@ void backprop(bla_mlp* m, const float* x, float x_scale, const float* y, int B, 
 void step(bla_mlp* m, const float* x, float x_scale, const float* y, int B, int Bg, int c0, float lr_mult, double* stats_host) {
     if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
     prepare_comm(m);
-    StepPdlOff pdl_guard;
+    StepPdlOff pdl_guard(B);
     backprop(m, x, x_scale, y, B, Bg, c0, true, lr_mult);
     // clip_gradient is a no-op (threshold INFINITY, :13,:296-301); scale by -lr and add  :303-315
     if (!(use_peer(m) && comm_active())) k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, rt().stream);
@@ -714,7 +724,7 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
     const int n0 = m->n[0], n3 = m->n[3];
     const int chunks = ceil_div(B, cols);
     prepare_comm(m);
-    StepPdlOff pdl_guard;
+    StepPdlOff pdl_guard(cols);
     const size_t esz = x_is_u8 ? 1 : sizeof(float);
     const MemKind yk = classify(y);
     const bool y_on_host = yk != kDevice && yk != kManaged;

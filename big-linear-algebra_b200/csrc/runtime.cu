@@ -39,6 +39,10 @@ bool pdl_enabled() {
 }
 PdlOff::PdlOff() { ++g_pdl_off; }
 PdlOff::~PdlOff() { --g_pdl_off; }
+static int g_pdl_late = 0;
+bool pdl_early() { return g_pdl_late == 0; }
+PdlLate::PdlLate() { ++g_pdl_late; }
+PdlLate::~PdlLate() { --g_pdl_late; }
 bool rt_initialised() { return g_init; }
 
 void rt_init(int device) {

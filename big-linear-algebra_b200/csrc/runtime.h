@@ -104,6 +104,11 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 #endif
 bool pdl_enabled();
 struct PdlOff { PdlOff(); ~PdlOff(); };
+// Inside a PdlLate scope kernels that take the hint (the tensor GEMM, its split-K fold, the MLP head kernel) do NOT trigger their
+// dependents early: the next kernel is only pre-staged and becomes resident when this one's CTAs have exited -- the launch gap is
+// hidden, but no waiting CTA holds an SM against the kernels of the step's other streams.
+bool pdl_early();
+struct PdlLate { PdlLate(); ~PdlLate(); };
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x, Args... args) {
     cudaLaunchConfig_t cfg{};
