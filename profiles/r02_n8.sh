@@ -5,5 +5,4 @@ mkdir -p gpurun_out
 DP_PATH=fp32 DP_BATCH=4096 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 tests/dp_check.py > gpurun_out/r02_dp_check_n8.log 2>&1
 grep -E "OK|peer_windows|FAIL|Error" gpurun_out/r02_dp_check_n8.log | head -20
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 8 --steps 200 --warmup 20 --no-extras > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err
-BLA_PEER_TWO_ROUNDS=0 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29545 bench.py --gpus 8 --steps 200 --warmup 20 --no-extras > gpurun_out/r02_bench_n8_one_round.json 2> gpurun_out/r02_bench_n8_one_round.err
 tail -c 700 gpurun_out/r02_bench_n8.json
