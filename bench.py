@@ -429,6 +429,13 @@ def main():
     b.bla_mlp_set_host_chunking(net, 0)       # the same call with the batch staged in one piece, for the record
     e2e_one = timed(step_e2e, e2e_steps, 2)["ms"] / e2e_steps
     b.bla_mlp_set_host_chunking(net, -1)
+    # ... and with the host-side byte packing of whole-number pixels off: the float chunks of round 1 (190.6 MB per step)
+    e2e_float = None
+    if hasattr(b, "bla_mlp_set_host_packing"):
+        b.bla_mlp_set_host_packing(net, 0)
+        e2e_f = timed(step_e2e, e2e_steps, 2)
+        e2e_float = {"ms_per_step": e2e_f["ms"] / e2e_steps, "h2d_bytes_per_step": e2e_f["h2d"] // e2e_steps}
+        b.bla_mlp_set_host_packing(net, -1)
 
     # the same end-to-end step from BYTE pixels (MNIST's native storage; additive entry point): 4x less PCIe traffic
     hx8 = b.bla_malloc_pinned(DIMS[0] * Bl)
@@ -585,8 +592,11 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"] // e2e_steps,
                         "d2h_bytes_per_step": e2e["d2h"] // e2e_steps, "ms_per_step": e2e_ms,
                         "launches_per_step": e2e["launches"] // e2e_steps, "ms_per_step_one_piece": e2e_one,
-                        "api": "bla_mlp_train_step(host float32 X[784xB], Y[10xB], &stats), batch staged in column chunks "
-                               "behind the training of the chunk before"},
+                        "float_chunks": e2e_float,
+                        "api": "bla_mlp_train_step(host float32 X[784xB], Y[10xB], &stats): the batch is staged in column chunks behind "
+                               "the training of the chunk before; chunks whose values are whole numbers 0..255 (checked bit for bit on "
+                               "the host, every step, inside the timed region) cross PCIe as bytes and are widened on the device -- "
+                               "h2d_bytes_per_step counts what was copied; `float_chunks` = the same call with that packing off"},
                 "e2e_u8": {"value": Bg / (e2e8_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e8["h2d"] // e2e_steps,
                            "d2h_bytes_per_step": e2e8["d2h"] // e2e_steps, "ms_per_step": e2e8_ms,
                            "ms_per_step_one_piece": e2e8_one,

@@ -205,6 +205,8 @@ PROTOTYPES = {
     "bla_mlp_create": (C.c_void_p, [C.POINTER(C.c_int), C.c_int]),
     "bla_mlp_destroy": (None, [C.c_void_p]),
     "bla_mlp_dims": (None, [C.c_void_p, C.c_void_p]),
+    "bla_mlp_set_host_packing": (None, [C.c_void_p, C.c_int]),
+    "bla_pack_pixels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bla_mlp_set_params": (None, [C.c_void_p] * 7),
     "bla_mlp_get_params": (None, [C.c_void_p] * 7),
     "bla_mlp_save_csv": (None, [C.c_void_p, C.c_char_p]),

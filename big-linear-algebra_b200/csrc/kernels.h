@@ -24,6 +24,8 @@ void k_add_tile_rows(float* a, int rows, int cols, const float* b, cudaStream_t 
 void k_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t s);                      // lib/matrix.c:105
 void k_fill_uniform(float* dst, size_t n, unsigned long long seed, float lo, float hi, cudaStream_t s);
 void k_u8_to_float(float* dst, const unsigned char* src, size_t n, float scale, cudaStream_t s);
+// host_pack.cpp: dst[i] = (unsigned char)src[i]; true when every src[i] is bit for bit one of 0.0f .. 255.0f
+bool pack_row_u8(const float* src, unsigned char* dst, int n);
 
 // ---- reductions (reduce.cu): warp-shuffle trees, two deterministic stages ---------------------
 // `work` must hold reduce_workspace_bytes() bytes of device scratch.

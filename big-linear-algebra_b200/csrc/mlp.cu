@@ -12,6 +12,10 @@
 // Activations are features x batch (batch = columns), exactly the reference's layout, so a
 // data-parallel shard is a column range and gradients are plain sums over ranks.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -64,6 +68,11 @@ struct bla_mlp {
     float* y_whole;                        // the labels cross in ONE copy ahead of the chunks and are cut up on the device
     cudaStream_t copy;
     cudaEvent_t ev_chunk[kMaxChunks], ev_free, ev_y;
+    // float host batches whose values are whole numbers 0..255 (MNIST pixels as the reference's CSV loader delivers them) cross PCIe
+    // as BYTES: host threads pack chunk k+1 into this pinned buffer while chunk k is copied and trained (step_packed)
+    unsigned char* pack;                   // pinned [n0 x max_batch], allocated at the first packed step
+    int pack_mode;                         // < 0: automatic, 0: off, > 0: forced (BLA_MLP_PACK, bla_mlp_set_host_packing)
+    cudaEvent_t ev_pack;                   // the last copy out of `pack`
     // data parallel: the gradient all-reduce runs over NVLink peer windows (comm.cu: one kernel that also applies the update) when
     // every rank could map them, else through NCCL
     bool peer;                             // decided collectively at the first data-parallel step
@@ -774,6 +783,176 @@ void step_chunked(bla_mlp* m, const void* x, bool x_is_u8, const float* y, int c
     if (stats_host) bla_mlp_read_stats(m, stats_host);
 }
 
+// ---- host batches of whole-number pixels as bytes -------------------------------------------------------------------
+// model/mnist_nn.c feeds float matrices whose values are the integers 0..255 of the CSV file (lib/mnist_csv2.c:13-34); as floats a
+// 60,000-column batch is 188 MB and the step is PCIe-bound (3.4 ms of transfer around 0.34 ms of training).  The values are exact
+// in a byte, so the library packs them on the host -- checked element by element, bit for bit: a chunk with any other value (a
+// fraction, a negative zero, a NaN) crosses as floats -- ships a quarter of the bytes and widens them again on the device
+// (k_u8_to_float, exact).  Chunk k+1 is packed by a persistent pool of host threads while chunk k is copied and trained; the chunks
+// are those of step_chunked, so the result is bit-identical to the unpacked path.
+struct PackJob {
+    const float* x = nullptr; unsigned char* out = nullptr;
+    int n0 = 0, B = 0, cols = 0, chunks = 0, blocks = 0, rows_per_block = 0, total = 0;
+    std::atomic<int> next{0};
+    std::atomic<int> done[bla_mlp::kMaxChunks];
+    std::atomic<int> bad[bla_mlp::kMaxChunks];
+};
+struct HostPool {
+    std::mutex mu;
+    std::condition_variable cv;
+    unsigned gen = 0;
+    int threads = 0;
+    std::atomic<int> active{0};
+    PackJob job;
+};
+HostPool& host_pool() { static HostPool* p = new HostPool; return *p; }   // never destroyed: its threads outlive main()
+
+// one work item = rows_per_block rows of one chunk: float [rows][B] columns b0.. -> bytes [rows][bc] of the chunk's contiguous block
+void pack_item(PackJob& j, int item) {
+    const int k = item / j.blocks, rb = item - k * j.blocks;
+    const int b0 = k * j.cols, bc = std::min(j.cols, j.B - b0);
+    const int r0 = rb * j.rows_per_block, r1 = std::min(j.n0, r0 + j.rows_per_block);
+    bool exact = true;
+    for (int r = r0; r < r1; ++r)
+        exact &= pack_row_u8(j.x + (size_t)r * j.B + b0, j.out + (size_t)j.n0 * b0 + (size_t)r * bc, bc);   // host_pack.cpp (SSE2)
+    const unsigned diff = exact ? 0u : 1u;
+    if (diff) j.bad[k].store(1, std::memory_order_relaxed);
+    j.done[k].fetch_add(1, std::memory_order_release);
+}
+void pack_worker() {
+    HostPool& hp = host_pool();
+    unsigned seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(hp.mu);
+            hp.cv.wait(lk, [&] { return hp.gen != seen; });
+            seen = hp.gen;
+            hp.active.fetch_add(1);
+        }
+        for (;;) {
+            const int item = hp.job.next.fetch_add(1, std::memory_order_relaxed);
+            if (item >= hp.job.total) break;
+            pack_item(hp.job, item);
+        }
+        hp.active.fetch_sub(1);
+    }
+}
+void pack_submit(const float* x, unsigned char* out, int n0, int B, int cols, int chunks) {
+    HostPool& hp = host_pool();
+    std::unique_lock<std::mutex> lk(hp.mu);
+    if (!hp.threads) {
+        unsigned hc = std::thread::hardware_concurrency();
+        int t = (int)std::min<unsigned>(hc ? hc : 4u, 16u) - 1;   // the calling thread packs too
+        if (const char* e = getenv("BLA_HOST_THREADS")) t = atoi(e) - 1;
+        if (t < 0) t = 0;
+        for (int i = 0; i < t; ++i) std::thread(pack_worker).detach();
+        hp.threads = t + 1;
+    }
+    while (hp.active.load() != 0) { lk.unlock(); std::this_thread::yield(); lk.lock(); }   // stragglers of the job before
+    PackJob& j = hp.job;
+    j.x = x; j.out = out; j.n0 = n0; j.B = B; j.cols = cols; j.chunks = chunks;
+    j.rows_per_block = 16;
+    j.blocks = ceil_div(n0, j.rows_per_block);
+    j.total = chunks * j.blocks;
+    for (int k = 0; k < chunks; ++k) { j.done[k].store(0); j.bad[k].store(0); }
+    j.next.store(0);
+    ++hp.gen;
+    lk.unlock();
+    hp.cv.notify_all();
+}
+// true once chunk k is packed (the caller packs items itself while it waits); *exact = every value of the chunk was a whole byte
+void pack_wait(int k, bool* exact) {
+    PackJob& j = host_pool().job;
+    while (j.done[k].load(std::memory_order_acquire) < j.blocks) {
+        const int item = j.next.fetch_add(1, std::memory_order_relaxed);
+        if (item < j.total) pack_item(j, item);
+        else std::this_thread::yield();
+    }
+    *exact = j.bad[k].load(std::memory_order_relaxed) == 0;
+}
+
+bool want_packing(const bla_mlp* m, int B, MemKind kind) {
+    if (kind == kDevice || kind == kManaged || m->chunk_cols == 0 || m->pack_mode == 0) return false;
+    return m->pack_mode > 0 || (size_t)B * m->n[0] >= ((size_t)4 << 20);   // automatic: from 16 MB of floats
+}
+
+// false: the batch does not start with whole bytes -- nothing was queued, the caller takes the float paths
+bool step_packed(bla_mlp* m, const float* x, const float* y, float x_scale, int B, int Bg, int c0, float lr_mult, double* stats_host) {
+    if (B > m->max_batch) die("bla: bla_mlp_train_step batch %d exceeds max_batch %d, exiting", B, m->max_batch);
+    cudaStream_t s = rt().stream, cp = m->copy;
+    const int n0 = m->n[0], n3 = m->n[3];
+    int cols = m->chunk_cols > 0 ? (m->chunk_cols + 63) / 64 * 64 : 6144;    // the chunks of step_chunked (mlp.cu: host_chunk_cols)
+    while (ceil_div(B, cols) > bla_mlp::kMaxChunks) cols += 64;
+    const int chunks = ceil_div(B, cols);
+    if (!m->pack) {
+        m->pack = (unsigned char*)pool_alloc(kPinned, (size_t)n0 * m->max_batch);
+        BLA_CUDA(cudaEventCreateWithFlags(&m->ev_pack, cudaEventDisableTiming));
+        BLA_CUDA(cudaEventRecord(m->ev_pack, m->copy));
+    }
+    BLA_CUDA(cudaEventSynchronize(m->ev_pack));           // the copies of the step before have left the pinned buffer
+    pack_submit(x, m->pack, n0, B, cols, chunks);
+    {   // a batch of other values (normalised pixels, anything with a fraction) is recognised at its first chunk
+        bool exact = false;
+        pack_wait(0, &exact);
+        if (!exact) {
+            host_pool().job.next.store(host_pool().job.total);   // nothing more to pack; stragglers finish the item they hold
+            return false;
+        }
+    }
+    prepare_comm(m);
+    StepPdlOff pdl_guard(cols);
+    const MemKind yk = classify(y);
+    const bool y_on_host = yk != kDevice && yk != kManaged;
+    BLA_CUDA(cudaEventRecord(m->ev_free, s));               // the staging buffers may still be read by the step before this one
+    BLA_CUDA(cudaStreamWaitEvent(cp, m->ev_free, 0));
+    const float* y_src = y;
+    if (y_on_host) {
+        BLA_CUDA(cudaMemcpyAsync(m->y_whole, y, (size_t)n3 * B * sizeof(float), cudaMemcpyHostToDevice, cp));
+        BLA_CUDA(cudaEventRecord(m->ev_y, cp));
+        BLA_CUDA(cudaStreamWaitEvent(s, m->ev_y, 0));
+        rt().h2d_bytes += (size_t)n3 * B * sizeof(float);
+        y_src = m->y_whole;
+    }
+    for (int i = 0; i < chunks; ++i) {
+        const int b0 = i * cols, bc = std::min(cols, B - b0);
+        bool exact = false;
+        pack_wait(i, &exact);
+        if (exact) {
+            BLA_CUDA(cudaMemcpyAsync(m->x_u8 + (size_t)n0 * b0, m->pack + (size_t)n0 * b0, (size_t)n0 * bc, cudaMemcpyHostToDevice, cp));
+            rt().h2d_bytes += (size_t)n0 * bc;
+        } else {   // some value of the chunk is not a whole byte: the floats themselves, as step_chunked sends them
+            BLA_CUDA(cudaMemcpy2DAsync(m->x + (size_t)n0 * b0, bc * sizeof(float), x + b0, B * sizeof(float), bc * sizeof(float), n0,
+                                       cudaMemcpyDefault, cp));
+            rt().h2d_bytes += (size_t)n0 * bc * sizeof(float);
+        }
+        BLA_CUDA(cudaEventRecord(m->ev_chunk[i], cp));
+        if (i == chunks - 1) BLA_CUDA(cudaEventRecord(m->ev_pack, cp));
+        BLA_CUDA(cudaMemcpy2DAsync(m->y + (size_t)n3 * b0, bc * sizeof(float), y_src + b0, B * sizeof(float), bc * sizeof(float), n3,
+                                   cudaMemcpyDefault, s));
+        BLA_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[i], 0));
+        bla_mlp v = *m;   // the same network looking at chunk i's slice of every per-batch buffer
+        v.x += (size_t)n0 * b0; v.x_u8 += (size_t)n0 * b0; v.y += (size_t)n3 * b0;
+        v.a1 += (size_t)m->n[1] * b0; v.dz1 += (size_t)m->n[1] * b0; v.a1_bits += (size_t)m->n[1] * (b0 / 32);   // b0 is a multiple of 64
+        v.a2 += (size_t)m->n[2] * b0; v.dz2 += (size_t)m->n[2] * b0;
+        v.z3 += (size_t)n3 * b0;
+        if (i > 0) v.grads = m->grads_chunk;
+        if (exact) k_u8_to_float(v.x, v.x_u8, (size_t)n0 * bc, 1.0f, s);
+        backprop(&v, v.x, x_scale, v.y, bc, Bg, c0 + b0, false, lr_mult);
+        if (i > 0) k_axpy(m->grads, m->grads_chunk, 1.0f, m->nparams, s);
+    }
+    if (comm_active()) {
+        cudaStream_t cs = comm_stream();
+        BLA_CUDA(cudaEventRecord(m->ev_rest, s));
+        BLA_CUDA(cudaStreamWaitEvent(cs, m->ev_rest, 0));
+        reduce_grads(m, 0, m->nparams, lr_mult, cs);
+        BLA_CUDA(cudaEventRecord(m->ev_comm, cs));
+        BLA_CUDA(cudaStreamWaitEvent(s, m->ev_comm, 0));
+    }
+    if (!(use_peer(m) && comm_active())) k_axpy(m->params, m->grads, -(float)lr_mult, m->nparams, s);
+    if (stats_host) bla_mlp_read_stats(m, stats_host);
+    return true;
+}
+
 // A device-resident step as ONE graph launch.  The ~17 launches, 10 event hops between the compute / side / collective streams and
 // (data parallel) the all-reduce of a step are captured the first time an argument tuple is seen after an eager step of the same
 // shape, and replayed afterwards: at a 7,500-column data-parallel shard the step is ~100 us of kernels, and issuing them one by one
@@ -873,6 +1052,9 @@ bla_mlp* bla_mlp_create(const int dims[4], int max_batch) {
     m->ws2 = (float*)pool_alloc(kDevice, (size_t)64 * dims[2] * dims[1] * sizeof(float));
     m->chunk_cols = -1;
     if (const char* e = getenv("BLA_MLP_CHUNK_COLS")) m->chunk_cols = atoi(e);
+    m->pack = nullptr;
+    m->pack_mode = -1;
+    if (const char* e = getenv("BLA_MLP_PACK")) m->pack_mode = atoi(e);
     m->grads_chunk = (float*)pool_alloc(kDevice, off * sizeof(float));
     m->y_whole = (float*)pool_alloc(kDevice, dims[3] * B * sizeof(float));
     BLA_CUDA(cudaEventCreateWithFlags(&m->ev_y, cudaEventDisableTiming));
@@ -893,6 +1075,7 @@ void bla_mlp_destroy(bla_mlp* m) {
     for (int i = 0; i < m->n_graphs; ++i) cudaGraphExecDestroy(m->graphs[i].exec);
     void* bufs[] = {m->a1_bits, m->params, m->grads, m->grads_chunk, m->y_whole, m->x, m->x_u8, m->y, m->a1, m->a2, m->z3, m->dz2, m->dz1, m->stats, m->head_partial, m->ws2};
     for (void* b : bufs) pool_free(b);
+    if (m->pack) { pool_free(m->pack); cudaEventDestroy(m->ev_pack); }
     cudaStreamDestroy(m->copy); cudaEventDestroy(m->ev_free); cudaEventDestroy(m->ev_y);
     for (cudaEvent_t e : m->ev_chunk) cudaEventDestroy(e);
     cudaStreamDestroy(m->side); cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join);
@@ -979,6 +1162,8 @@ void bla_mlp_read_stats(bla_mlp* m, double* stats_host) {
 void bla_mlp_train_step(bla_mlp* m, const float* x, const float* y, int batch, int global_batch, int col_offset, float lr_mult,
                         double* stats_host) {
     cudaStream_t s = rt().stream;
+    if (want_packing(m, batch, classify(x)) && step_packed(m, x, y, 1 / 255.0F, batch, global_batch, col_offset, lr_mult, stats_host))
+        return;
     if (const int cols = host_chunk_cols(m, batch, classify(x), sizeof(float))) {
         step_chunked(m, x, false, y, cols, 1 / 255.0F, batch, global_batch, col_offset, lr_mult, stats_host);
         return;
@@ -993,6 +1178,22 @@ void bla_mlp_train_step(bla_mlp* m, const float* x, const float* y, int batch, i
 }
 
 void bla_mlp_set_host_chunking(bla_mlp* m, int chunk_cols) { m->chunk_cols = chunk_cols; }
+void bla_mlp_set_host_packing(bla_mlp* m, int mode) { m->pack_mode = mode; }
+
+int bla_pack_pixels(const float* x, int rows, int cols, int chunk_cols, unsigned char* out, int* exact) {
+    if (rows <= 0 || cols <= 0 || chunk_cols <= 0) return 0;
+    const int chunks = ceil_div(cols, chunk_cols);
+    if (chunks > bla_mlp::kMaxChunks) die("bla: bla_pack_pixels takes at most %d chunks, exiting", bla_mlp::kMaxChunks);
+    pack_submit(x, out, rows, cols, chunk_cols, chunks);
+    int all = 1;
+    for (int k = 0; k < chunks; ++k) {
+        bool ok = false;
+        pack_wait(k, &ok);
+        if (exact) exact[k] = ok ? 1 : 0;
+        all &= ok ? 1 : 0;
+    }
+    return all;
+}
 
 void bla_mlp_train_step_u8(bla_mlp* m, const unsigned char* x_u8, const float* y, int batch, int global_batch, int col_offset,
                            float lr_mult, double* stats_host) {

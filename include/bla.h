@@ -174,6 +174,15 @@ void bla_mlp_train_step_u8(bla_mlp* net, const unsigned char* x_u8, const float*
  * batches of >= 32768 columns in two halves: the strided copies need long rows); 0: off; > 0: this chunk width
  * (rounded up to 64 columns, at most 16 chunks) for any host batch. */
 void bla_mlp_set_host_chunking(bla_mlp* net, int chunk_cols);
+/* Float host batches whose values are the whole numbers 0..255 (pixels as the reference's CSV loader delivers them, mnist_nn.c:
+ * 204-209) cross PCIe as bytes: packed on the host, every value checked bit for bit, chunk by chunk behind the chunk before; any
+ * other chunk crosses as floats.  Same chunks as bla_mlp_set_host_chunking, same result bit for bit.  mode < 0: automatic (batches of
+ * at least 16 MB; default), 0: never, > 0: always.  BLA_MLP_PACK sets the default, BLA_HOST_THREADS the size of the packing pool. */
+void bla_mlp_set_host_packing(bla_mlp* net, int mode);
+/* The host half of that path on its own (no device needed): x [rows x cols] floats -> bytes, column chunk k (chunk_cols wide, at most
+ * 16 chunks) as one contiguous [rows x width_k] block at out + rows * k * chunk_cols; exact[k] (may be NULL) = 1 when every value of
+ * chunk k was a whole number 0..255 bit for bit (only then are its bytes meaningful).  Returns 1 when all chunks were exact. */
+int bla_pack_pixels(const float* x, int rows, int cols, int chunk_cols, unsigned char* out, int* exact);
 /* Forward only (model/mnist_nn.c:446-463, `run`): probs [classes x batch] out. */
 void bla_mlp_forward(bla_mlp* net, const float* x, int batch, float* probs);
 /* {loss_sum, num_correct} accumulated on the device since the last call (then cleared).  With an active communicator this is a

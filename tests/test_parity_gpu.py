@@ -582,6 +582,60 @@ def test_mlp_full_size_step_is_the_sum_of_its_column_shards(bla, path):
         b.bla_set_gemm_path(b.GEMM_FP32)
 
 
+def test_mlp_whole_number_host_batch_crosses_as_bytes_with_identical_results(bla):
+    """A float host batch of whole numbers 0..255 (what the reference's CSV loader hands mnist_nn.c:204-209) is packed to bytes on the
+    host, chunk by chunk, and widened again on the device (csrc/mlp.cu: step_packed): a quarter of the PCIe bytes, and -- same chunks,
+    exact conversion -- parameters BIT-IDENTICAL to the float chunks.  A chunk holding any other value crosses as floats (still
+    identical); a batch that does not start with whole numbers takes the float path altogether."""
+    b = bla
+    b.bla_set_gemm_path(b.GEMM_AUTO)
+    dims = (C.c_int * 4)(784, 256, 128, 10)
+    shapes = ((256, 784), (256,), (128, 256), (128,), (10, 128), (10,))
+    rng = np.random.default_rng(78)
+    p0 = [f32(rng.uniform(-0.08, 0.08, s)) for s in shapes]
+    B = 7000                                              # 1024-column chunks: 6 full + 856
+    labels = rng.integers(0, 10, B)
+    Y = np.zeros((10, B), np.float32); Y[labels, np.arange(B)] = 1
+
+    def run(X, pack):
+        net = b.bla_mlp_create(dims, B)
+        b.bla_mlp_set_params(net, *[ptr(p) for p in p0])
+        b.bla_mlp_set_host_chunking(net, 1024)
+        b.bla_mlp_set_host_packing(net, pack)
+        stats = np.zeros(2)
+        h0 = b.bla_h2d_bytes()
+        b.bla_mlp_train_step(net, ptr(X), ptr(Y), B, B, 0, 0.5, None)
+        b.bla_mlp_train_step(net, ptr(X), ptr(Y), B, B, 0, 0.01, ptr(stats))   # the pinned pack buffer is reused
+        moved = b.bla_h2d_bytes() - h0
+        got = [np.empty_like(p) for p in p0]
+        b.bla_mlp_get_params(net, *[ptr(g) for g in got])
+        b.bla_mlp_destroy(net)
+        return got, stats, moved
+
+    try:
+        X = rng.integers(0, 256, (784, B)).astype(np.float32)
+        ref, ref_stats, ref_bytes = run(X, 0)
+        got, stats, moved = run(X, 1)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g, r)
+        assert np.array_equal(stats, ref_stats)
+        assert ref_bytes == 2 * (784 + 10) * B * 4 and moved == 2 * (784 * B + 10 * B * 4)     # bytes for the pixels, floats for the labels
+        X2 = X.copy(); X2[300, 3500] = 17.25                                                  # chunk 3 is not whole numbers
+        ref2, _, _ = run(X2, 0)
+        got2, _, moved2 = run(X2, 1)
+        for g, r in zip(got2, ref2):
+            assert np.array_equal(g, r)
+        assert moved2 == 2 * (784 * (B - 1024) + 784 * 1024 * 4 + 10 * B * 4)
+        X3 = (X / 255.0).astype(np.float32)                                                   # normalised pixels: the float path
+        ref3, _, ref3_bytes = run(X3, 0)
+        got3, _, moved3 = run(X3, 1)
+        for g, r in zip(got3, ref3):
+            assert np.array_equal(g, r)
+        assert moved3 == ref3_bytes
+    finally:
+        b.bla_set_gemm_path(b.GEMM_FP32)
+
+
 @pytest.mark.parametrize("path", ["fp32", "auto"])
 def test_mlp_host_batch_in_chunks_equals_one_piece(bla, path):
     """Host batches cross PCIe in column chunks while the chunk before is trained (bla_mlp_set_host_chunking): the step must be the
@@ -649,7 +703,14 @@ def test_mlp_host_batch_in_chunks_equals_one_piece(bla, path):
         hy_np[:] = 0; hy_np[labels, np.arange(B)] = 1
         h0 = b.bla_h2d_bytes()
         many = run(B, hx, hy, -1, False)
-        assert b.bla_h2d_bytes() - h0 >= 2 * (784 + 10) * B * 4
+        # whole-number pixels: the automatic rule also packs them to bytes on the host (step_packed; the labels stay floats)
+        assert b.bla_h2d_bytes() - h0 == 2 * (784 * B + 10 * B * 4)
+        compare(run(B, hx, hy, 0, False), many)
+        # the same batch with a fraction in every chunk: the float chunks of the automatic rule
+        hx_np[5, ::1000] = 0.5
+        h0 = b.bla_h2d_bytes()
+        many = run(B, hx, hy, -1, False)
+        assert b.bla_h2d_bytes() - h0 == 2 * (784 + 10) * B * 4
         compare(run(B, hx, hy, 0, False), many)
         b.bla_free(hx); b.bla_free(hy)
     finally:
