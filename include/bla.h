@@ -177,7 +177,7 @@ void bla_mlp_set_host_chunking(bla_mlp* net, int chunk_cols);
 /* Float host batches whose values are the whole numbers 0..255 (pixels as the reference's CSV loader delivers them, mnist_nn.c:
  * 204-209) cross PCIe as bytes: packed on the host, every value checked bit for bit, chunk by chunk behind the chunk before; any
  * other chunk crosses as floats.  Same chunks as bla_mlp_set_host_chunking, same result bit for bit.  mode < 0: automatic (batches of
- * at least 16 MB; default), 0: never, > 0: always.  BLA_MLP_PACK sets the default, BLA_HOST_THREADS the size of the packing pool. */
+ * at least 16 MB in a process without a communicator: the ranks of one box share the host's memory bandwidth; default), 0: never, > 0: always.  BLA_MLP_PACK sets the default, BLA_HOST_THREADS the size of the packing pool. */
 void bla_mlp_set_host_packing(bla_mlp* net, int mode);
 /* The host half of that path on its own (no device needed): x [rows x cols] floats -> bytes, column chunk k (chunk_cols wide, at most
  * 16 chunks) as one contiguous [rows x width_k] block at out + rows * k * chunk_cols; exact[k] (may be NULL) = 1 when every value of
